@@ -1,0 +1,422 @@
+// Implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma (accumulators in
+// TMEM) -> fused epilogue.  One kernel template serves every conv of the Darknet-53 / YOLOv3
+// stack declared by the reference in src/space/yolov3_detect.py:196-311 (_conv_block /
+// make_yolov3_model) and the FaceDetector head of src/space/face_detection.py:348-352.
+//
+// GEMM view:  D[M, N] = A[M, K] * W[N, K]^T,  M = pixels of the compute domain,
+// N = Cout, K = taps * Cin.  Activations are NHWC bf16 stored with a one-pixel zero halo
+// ("padded" geometry) so that a 3x3 tap is a pure ROW SHIFT of the 2-D matrix [rows, C]:
+// the A tile of tap (r,s) is the 128 consecutive rows starting at m0 + (r-1)*(W+2) + (s-1).
+// Rows before 0 / past the end are zero-filled by TMA.  Stride-2 convs read a 4-phase
+// (space-to-depth by parity) copy written by the producing layer, which again makes every tap a
+// row shift.  Halo / out-of-image rows are computed and thrown away (never stored), so the halo
+// of every activation buffer keeps the zeros it was allocated with = ZeroPadding2D(1).
+//
+// Epilogue (all fp32, one rounding per stored tensor): + bias (BatchNorm eps=1e-3 folded on the
+// host, yolov3_detect.py:212) -> LeakyReLU(0.1) (:213) -> + residual (:215) -> bf16 store in
+// the geometry the consumer wants: padded NHWC, 4-phase (next conv has stride 2), 2x nearest
+// up-sampled into a channel slice of a concat buffer (:282-283, :298-299), or dense fp32 head
+// logits (:278, :294, :308).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
+// Persistent: grid = min(#tiles, #SMs * occupancy); tiles are strided by gridDim.x.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace fvy {
+
+enum OutKind : int {
+    OUT_NONE = 0,
+    OUT_PADDED = 1,      // [n][H+2][W+2][pitch] bf16, interior only
+    OUT_PHASE = 2,       // [4][nmax][H/2+1][W/2+1][pitch] bf16 (consumer is a stride-2 3x3 conv)
+    OUT_UP2_PADDED = 3,  // 2x nearest up-sample into [n][2H+2][2W+2][pitch] bf16
+    OUT_HEAD_F32 = 4     // [n][H][W][c_real] fp32, dense, no halo
+};
+
+struct OutDesc {
+    void* ptr;
+    int kind;
+    int pitch;    // elements per pixel row of the destination buffer
+    int choff;    // first destination channel
+    int nmax;     // batch capacity of the buffer (phase stride)
+    int c_real;   // valid channels (heads: 18 / 255 / 6); others: >= BLOCK_N * num_n_tiles
+};
+
+struct ConvParams {
+    int num_taps;
+    int k_chunks;        // K chunks (of BLOCK_K channels) per tap
+    int a_choff;         // first channel of the A buffer
+    int tap_off[9];      // row shift per tap
+    int m_total;         // rows of the compute domain = batch * dom_plane
+    int dom_plane;       // rows per image in the compute domain
+    int dom_w;           // row pitch (pixels) of the compute domain
+    int dom_off;         // 1: padded domain (h = y-1), 0: phase / dense domain (h = y)
+    int H, W;            // valid output extent
+    int num_m_tiles, num_n_tiles;
+    int leaky;
+    const float* bias;   // [num_n_tiles * BLOCK_N] fp32
+    const __nv_bfloat16* res;   // padded geometry at (H, W), or nullptr
+    int res_pitch, res_choff;
+    OutDesc out[2];
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a pipeline bug traps (-> CUDA error at the next sync) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) {
+            printf("fvy: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// mbarrier arrives once all MMAs issued so far by this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread t of the warp gets TMEM lane (base_lane + t), columns [col, col+32).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// Descriptors (bit layouts: PTX ISA "tcgen05 matrix / instruction descriptor")
+// ----------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor for a K-major operand tile whose rows are BK*2 bytes wide and were
+// written by TMA with the matching swizzle (BK=64 -> 128B swizzle, BK=32 -> 64B swizzle):
+//   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
+//   [32,46) stride byte offset >> 4 = (8 rows * row bytes) >> 4     [46,48) version = 1 (sm_100)
+//   [49,52) base offset = 0 (tile bases are 1024-byte aligned)       [61,64) layout: 2 = SW128, 4 = SW64
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    constexpr uint64_t row_bytes = BK * 2;
+    constexpr uint64_t sbo = (8 * row_bytes) >> 4;
+    constexpr uint64_t layout = (BK == 64) ? 2 : 4;
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1),
+// A and B K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Kernel
+// ----------------------------------------------------------------------------------------------
+constexpr int kBlockM = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+template <int BN, int BK>
+struct SmemLayout {
+    static constexpr int a_bytes = kBlockM * BK * 2;
+    static constexpr int b_bytes = BN * BK * 2;
+    static constexpr int stage_bytes = a_bytes + b_bytes;
+    static constexpr int barrier_bytes = 1024;   // full/empty/tmem barriers + tmem ptr, keeps tiles 1024-aligned
+    static constexpr int bytes(int stages) { return barrier_bytes + stages * stage_bytes + 1024 /* alignment slack */; }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ ConvParams p, const int num_stages) {
+    using L = SmemLayout<BN, BK>;
+    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages; BN in {32,64,128,256}
+    constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]
+    uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
+    uint64_t* tmem_full = empty_bar + kMaxStages;                        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                                // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint8_t* tiles = smem + L::barrier_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int k_iters = p.num_taps * p.k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.num_n_tiles) * kBlockM;
+                const int n0 = (tile % p.num_n_tiles) * BN;
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    const int row = m0 + p.tap_off[tap];
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = tiles + stage * L::stage_bytes;
+                        uint8_t* sb = sa + L::a_bytes;
+                        mbar_expect_tx(&full_bar[stage], L::stage_bytes);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, row);
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], (tap * p.k_chunks + kc) * BK, n0);
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + stage * L::stage_bytes);
+                    const uint64_t da = make_smem_desc<BK>(sa);
+                    const uint64_t db = make_smem_desc<BK>(sa + L::a_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                    if (it == k_iters - 1) umma_commit(&tmem_full[as]);   // accumulator complete
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;               // row of the tile handled by this thread
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m = (tile / p.num_n_tiles) * kBlockM + r;
+            const int n0 = (tile % p.num_n_tiles) * BN;
+            // decode the pixel and decide whether the row is a real output
+            bool valid = m < p.m_total;
+            int img = 0, h = 0, w = 0;
+            if (valid) {
+                img = m / p.dom_plane;
+                const int rem = m - img * p.dom_plane;
+                const int y = rem / p.dom_w;
+                h = y - p.dom_off;
+                w = rem - y * p.dom_w - p.dom_off;
+                valid = (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+            }
+            const __nv_bfloat16* res_row = nullptr;
+            if (valid && p.res != nullptr) {
+                const long long rr = ((long long)img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
+                res_row = p.res + rr * p.res_pitch + p.res_choff + n0;
+            }
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld_32x32(taddr + c0, acc);
+                tmem_ld_wait();
+                if (valid) {
+                    float v[32];
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+                        v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+                        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+                        v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+                    }
+                    if (p.leaky) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                    }
+                    if (res_row != nullptr) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(res_row + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 t = __ldg(r4 + j);
+                            const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[8 * j + 2 * e + 0] += __uint_as_float(u[e] << 16);
+                                v[8 * j + 2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        const OutDesc& od = p.out[o];
+                        if (od.kind == OUT_NONE) continue;
+                        if (od.kind == OUT_HEAD_F32) {
+                            float* dst = reinterpret_cast<float*>(od.ptr) + (((long long)img * p.H + h) * p.W + w) * od.c_real;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + c0 + j < od.c_real) dst[n0 + c0 + j] = v[j];
+                            continue;
+                        }
+                        uint4 pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            pk[j].x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            pk[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            pk[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            pk[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        }
+                        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(od.ptr) + od.choff + n0 + c0;
+                        if (od.kind == OUT_PADDED) {
+                            const long long row = ((long long)img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
+                            uint4* d = reinterpret_cast<uint4*>(base + row * od.pitch);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) d[j] = pk[j];
+                        } else if (od.kind == OUT_PHASE) {
+                            const int hp = h + 1, wp = w + 1;
+                            const int ph = ((hp & 1) << 1) | (wp & 1);
+                            const int pw = (p.W >> 1) + 1;
+                            const long long plane = (long long)((p.H >> 1) + 1) * pw;
+                            const long long row = ((long long)ph * od.nmax + img) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
+                            uint4* d = reinterpret_cast<uint4*>(base + row * od.pitch);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) d[j] = pk[j];
+                        } else {   // OUT_UP2_PADDED
+                            const int W2 = 2 * p.W + 2;
+                            const long long row0 = ((long long)img * (2 * p.H + 2) + (2 * h + 1)) * W2 + (2 * w + 1);
+#pragma unroll
+                            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 2; ++dx) {
+                                    uint4* d = reinterpret_cast<uint4*>(base + (row0 + (long long)dy * W2 + dx) * od.pitch);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) d[j] = pk[j];
+                                }
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above): hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace fvy

@@ -1,0 +1,957 @@
+// libfvy.so — C ABI (include/fvy.h) over the sm_100a kernels.  Host-side plan, weight folding,
+// buffer arena, TMA tensor maps, launches.  No torch types, no CPU fallback.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fvy.h"
+#include "conv_igemm_sm100.cuh"
+#include "fvy_plan.h"
+#include "postproc_kernels.cuh"
+
+namespace fvy {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(FVY_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ TMA encode
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous, row pitch `pitch_elems`), box = box_cols x box_rows,
+// swizzle = box_cols * 2 bytes (64 or 128).  Out-of-bounds elements read as zero.
+static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t box_cols,
+                        uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (cols=%llu rows=%llu pitch=%llu box=%ux%u)",
+                                       (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems, box_cols, box_rows);
+    return FVY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+// Stem operand: im2col of the 3x3 / pad 1 / stride 1 window of the RGB input, K index = (r*3+s)*3 + c,
+// padded 27 -> 32 (one 64-byte swizzle row per pixel).  yolov3_detect.py:221 (conv_0), :205 (ZeroPadding2D(1)).
+template <typename T>
+__global__ void stem_im2col_kernel(const T* __restrict__ img, int batch, int H, int W, __nv_bfloat16* __restrict__ out) {
+    const long long total = (long long)batch * H * W;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(pix % W);
+        const long long t = pix / W;
+        const int h = (int)(t % H);
+        const long long n = t / H;
+        __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int hh = h + r - 1, ww = w + s - 1;
+                const bool in = (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+                const T* src = img + ((n * H + (in ? hh : 0)) * W + (in ? ww : 0)) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = __float2bfloat16_rn(in ? (float)src[c] : 0.f);
+            }
+#pragma unroll
+        for (int k = 27; k < 32; ++k) v[k] = __float2bfloat16_rn(0.f);
+        uint4* d = reinterpret_cast<uint4*>(out + pix * 32);
+        const uint4* s4 = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = s4[j];
+    }
+}
+
+// Debug / parity aid: stored activation -> dense NHWC fp32.
+__global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float* __restrict__ dst) {
+    const long long total = (long long)batch * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const long long n = t / H;
+        float v;
+        if (od.kind == OUT_HEAD_F32) {
+            v = reinterpret_cast<const float*>(od.ptr)[((n * H + h) * W + w) * od.c_real + c];
+        } else {
+            long long row;
+            if (od.kind == OUT_PADDED) row = (n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+            else if (od.kind == OUT_PHASE) {
+                const int hp = h + 1, wp = w + 1, ph = ((hp & 1) << 1) | (wp & 1), pw = (W >> 1) + 1;
+                const long long plane = (long long)((H >> 1) + 1) * pw;
+                row = ((long long)ph * od.nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
+            } else row = (n * (2 * H + 2) + (2 * h + 1)) * (2 * W + 2) + (2 * w + 1);
+            v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(od.ptr)[row * od.pitch + od.choff + c]);
+        }
+        dst[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ handle
+struct Layer {
+    ConvSpec s;
+    int Hin, Win, Hout, Wout;
+    int BN, BK, stages, num_n_tiles, cout_pad, cin_pad, taps, occ;
+    size_t smem_bytes;
+    __nv_bfloat16* w = nullptr;   // [cout_pad][taps * cin_pad]
+    float* bias = nullptr;        // [cout_pad]
+    CUtensorMap tmap_a, tmap_b;
+    ConvParams p;                 // m_total / num_m_tiles filled per call
+    OutDesc primary;              // where fvy_layer_output reads from
+    size_t stream_off;            // offset of this layer in the Darknet stream
+};
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+};
+
+}  // namespace fvy
+
+using namespace fvy;
+
+struct fvy_handle {
+    fvy_config cfg;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<Layer> layers;
+    std::vector<void*> allocs;
+    bool weights_loaded = false;
+    long long launches = 0;
+    long long weight_count = 0;
+    // forward
+    void* d_input = nullptr; size_t input_bytes = 0;       // staging for host images
+    __nv_bfloat16* d_stem = nullptr;                        // im2col operand
+    float* d_logits[3] = {nullptr, nullptr, nullptr};
+    int gh[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, head_c = 0;
+    // post
+    int cap = 0, capP = 0, words = 0, np2max = 0, smem_keys = 0;
+    double* d_nbox = nullptr;
+    int* d_ibox = nullptr; float* d_obj = nullptr; float* d_cls = nullptr; int* d_cand = nullptr; int* d_counts = nullptr;
+    int* d_status = nullptr; int* d_image_hw = nullptr;
+    int* d_order = nullptr; int4* d_sbox = nullptr; unsigned long long* d_mask = nullptr; unsigned long long* d_gkeys = nullptr;
+    int* d_kept = nullptr; int* d_kept_counts = nullptr;
+    FvyDet* d_dets = nullptr; int* d_det_counts = nullptr; int dets_cap = 0;
+    float last_fwd_ms = 0.f, last_post_ms = 0.f;
+};
+
+namespace fvy {
+
+static int dev_alloc(fvy_handle* h, void** p, size_t bytes, bool zero) {
+    CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    h->allocs.push_back(*p);
+    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, h->stream));
+    return FVY_OK;
+}
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static uint16_t f32_to_bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+template <int BN, int BK>
+static int launch_conv_t(fvy_handle* h, Layer& L, int grid) {
+    auto kern = conv_igemm_kernel<BN, BK>;   // max dynamic smem was raised in query_occ_t at plan time
+    kern<<<grid, kThreads, L.smem_bytes, h->stream>>>(L.tmap_a, L.tmap_b, L.p, L.stages);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    return FVY_OK;
+}
+
+template <int BN, int BK>
+static int query_occ_t(size_t smem, int* occ) {
+    auto kern = conv_igemm_kernel<BN, BK>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem));
+    return FVY_OK;
+}
+
+#define FVY_DISPATCH(BNv, BKv, CALL)                                                  \
+    do {                                                                              \
+        if (BKv == 64) {                                                              \
+            switch (BNv) {                                                            \
+                case 32: return CALL(32, 64); case 64: return CALL(64, 64);           \
+                case 128: return CALL(128, 64); case 256: return CALL(256, 64);       \
+            }                                                                         \
+        } else {                                                                      \
+            switch (BNv) {                                                            \
+                case 32: return CALL(32, 32); case 64: return CALL(64, 32);           \
+                case 128: return CALL(128, 32); case 256: return CALL(256, 32);       \
+            }                                                                         \
+        }                                                                             \
+        return fail(FVY_E_INVALID, "no kernel instance for tile N=%d K=%d", BNv, BKv); \
+    } while (0)
+
+static int launch_conv(fvy_handle* h, Layer& L, int grid) {
+#define CALL(bn, bk) launch_conv_t<bn, bk>(h, L, grid)
+    FVY_DISPATCH(L.BN, L.BK, CALL);
+#undef CALL
+}
+static int query_occ(int BN, int BK, size_t smem, int* occ) {
+#define CALL(bn, bk) query_occ_t<bn, bk>(smem, occ)
+    FVY_DISPATCH(BN, BK, CALL);
+#undef CALL
+}
+
+struct TensorBufs { __nv_bfloat16* padded = nullptr; __nv_bfloat16* phase = nullptr; };
+
+static int build_plan(fvy_handle* h) {
+    const fvy_config& c = h->cfg;
+    std::vector<ConvSpec> specs = c.head == FVY_HEAD_YOLO3 ? yolo3_table(c.nb_class) : fd6_table(c.bb_info_c_size);
+    const int nmax = c.max_batch;
+    // which stored forms does each producer need?
+    std::map<int, bool> need_padded, need_phase;
+    for (const ConvSpec& s : specs) {
+        if (s.src >= 0) { if (s.k == 3 && s.stride == 2) need_phase[s.src] = true; else need_padded[s.src] = true; }
+        if (s.res >= 0) need_padded[s.res] = true;
+    }
+    std::map<int, const ConvSpec*> by_idx;
+    for (const ConvSpec& s : specs) by_idx[s.idx] = &s;
+    std::map<int, TensorBufs> bufs;
+    auto HW = [&](int level, int* H, int* W) { *H = c.net_h >> level; *W = c.net_w >> level; };
+    // concat buffers (yolo3 only): A = [up(conv_84) 256 | skip_61 512] at level 4, B = [up(conv_96) 128 | skip_36 256] at level 3
+    __nv_bfloat16 *catA = nullptr, *catB = nullptr;
+    if (c.head == FVY_HEAD_YOLO3) {
+        int H, W;
+        HW(4, &H, &W);
+        if (int e = dev_alloc(h, (void**)&catA, (size_t)nmax * (H + 2) * (W + 2) * 768 * 2, true)) return e;
+        HW(3, &H, &W);
+        if (int e = dev_alloc(h, (void**)&catB, (size_t)nmax * (H + 2) * (W + 2) * 384 * 2, true)) return e;
+    }
+    // stem operand
+    if (int e = dev_alloc(h, (void**)&h->d_stem, (size_t)nmax * c.net_h * c.net_w * 32 * 2, false)) return e;
+    // activation buffers
+    for (const ConvSpec& s : specs) {
+        int H, W;
+        HW(s.level, &H, &W);
+        TensorBufs tb;
+        if (need_padded.count(s.idx))
+            if (int e = dev_alloc(h, (void**)&tb.padded, (size_t)nmax * (H + 2) * (W + 2) * s.cout * 2, true)) return e;
+        if (need_phase.count(s.idx))
+            if (int e = dev_alloc(h, (void**)&tb.phase, (size_t)4 * nmax * (H / 2 + 1) * (W / 2 + 1) * s.cout * 2, true)) return e;
+        bufs[s.idx] = tb;
+    }
+    // heads
+    int nh = 0;
+    for (const ConvSpec& s : specs)
+        if (!s.bn) {
+            int H, W;
+            HW(s.level, &H, &W);
+            if (nh >= 3) return fail(FVY_E_INVALID, "more than 3 heads");
+            h->gh[nh] = H; h->gw[nh] = W; h->head_c = s.cout;
+            if (int e = dev_alloc(h, (void**)&h->d_logits[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
+            ++nh;
+        }
+    const int bn_cap = c.tile_n_max > 0 ? c.tile_n_max : 128;
+    size_t stream_off = 0;
+    int head_i = 0;
+    for (const ConvSpec& s : specs) {
+        Layer L;
+        L.s = s;
+        HW(s.level, &L.Hout, &L.Wout);
+        L.Hin = L.Hout * s.stride; L.Win = L.Wout * s.stride;
+        L.stream_off = stream_off;
+        stream_off += (size_t)(s.bn ? 4 : 1) * s.cout + (size_t)s.cout * s.cin * s.k * s.k;
+        const bool stem = s.src == -1;
+        L.taps = stem ? 1 : s.k * s.k;
+        L.cin_pad = stem ? 32 : s.cin;
+        L.BK = (L.cin_pad % 64 == 0) ? 64 : 32;
+        if (L.cin_pad % L.BK) return fail(FVY_E_INVALID, "conv_%d: Cin %d not a multiple of %d", s.idx, s.cin, L.BK);
+        L.cout_pad = (s.cout + 31) / 32 * 32;
+        L.BN = 32;
+        for (int bn : {256, 128, 64, 32})
+            if (bn <= bn_cap && L.cout_pad % bn == 0) { L.BN = bn; break; }
+        L.num_n_tiles = L.cout_pad / L.BN;
+        const size_t stage_bytes = (size_t)(kBlockM + L.BN) * L.BK * 2;
+        const size_t budget = (L.BN >= 128) ? (232448 - 2048) : (100 * 1024);
+        L.stages = (int)std::min<size_t>(kMaxStages, std::max<size_t>(2, budget / stage_bytes));
+        L.smem_bytes = 2048 + (size_t)L.stages * stage_bytes;
+        if (int e = query_occ(L.BN, L.BK, L.smem_bytes, &L.occ)) return e;
+        L.occ = std::max(1, std::min(L.occ, 512 / std::max(32, 2 * L.BN)));
+        // operands
+        const size_t kdim = (size_t)L.taps * L.cin_pad;
+        if (int e = dev_alloc(h, (void**)&L.w, (size_t)L.cout_pad * kdim * 2, true)) return e;
+        if (int e = dev_alloc(h, (void**)&L.bias, (size_t)L.cout_pad * 4, true)) return e;
+        if (int e = make_tmap_2d(&L.tmap_b, L.w, kdim, L.cout_pad, kdim, L.BK, L.BN)) return e;
+        ConvParams& p = L.p;
+        memset(&p, 0, sizeof(p));
+        p.num_taps = L.taps;
+        p.k_chunks = L.cin_pad / L.BK;
+        p.a_choff = 0;
+        p.H = L.Hout; p.W = L.Wout;
+        p.leaky = s.leaky ? 1 : 0;
+        p.bias = L.bias;
+        p.num_n_tiles = L.num_n_tiles;
+        const void* a_base = nullptr;
+        uint64_t a_rows = 0, a_pitch = 0;
+        if (stem) {
+            a_base = h->d_stem; a_rows = (uint64_t)nmax * L.Hin * L.Win; a_pitch = 32;
+            p.dom_plane = L.Hin * L.Win; p.dom_w = L.Win; p.dom_off = 0; p.tap_off[0] = 0;
+        } else if (s.stride == 2) {
+            const int Ho = L.Hout, Wo = L.Wout;
+            const long long plane = (long long)(Ho + 1) * (Wo + 1);
+            a_base = bufs[s.src].phase; a_rows = (uint64_t)(4 * nmax * plane); a_pitch = s.cin;
+            p.dom_plane = (int)plane; p.dom_w = Wo + 1; p.dom_off = 0;
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q)
+                    p.tap_off[r * 3 + q] = (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + (r >> 1) * (Wo + 1) + (q >> 1));
+        } else {
+            const int H = L.Hin, W = L.Win;
+            if (s.src == -2) { a_base = catA; a_pitch = 768; }
+            else if (s.src == -3) { a_base = catB; a_pitch = 384; }
+            else { a_base = bufs[s.src].padded; a_pitch = s.cin; }
+            a_rows = (uint64_t)nmax * (H + 2) * (W + 2);
+            p.dom_plane = (H + 2) * (W + 2); p.dom_w = W + 2; p.dom_off = 1;
+            if (s.k == 1) p.tap_off[0] = 0;
+            else
+                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < 3; ++q) p.tap_off[r * 3 + q] = (r - 1) * (W + 2) + (q - 1);
+        }
+        if (a_base == nullptr) return fail(FVY_E_INVALID, "conv_%d: input buffer missing", s.idx);
+        if (int e = make_tmap_2d(&L.tmap_a, a_base, a_pitch, a_rows, a_pitch, L.BK, kBlockM)) return e;
+        if (s.res >= 0) {
+            p.res = bufs[s.res].padded; p.res_pitch = by_idx[s.res]->cout; p.res_choff = 0;
+            if (!p.res) return fail(FVY_E_INVALID, "conv_%d: residual buffer missing", s.idx);
+        }
+        // outputs
+        int no = 0;
+        auto add_out = [&](void* ptr, int kind, int pitch, int choff, int c_real) {
+            OutDesc od; od.ptr = ptr; od.kind = kind; od.pitch = pitch; od.choff = choff; od.nmax = nmax; od.c_real = c_real;
+            p.out[no++] = od;
+        };
+        if (!s.bn) {
+            add_out(h->d_logits[head_i++], OUT_HEAD_F32, s.cout, 0, s.cout);
+        } else {
+            if (bufs[s.idx].padded) add_out(bufs[s.idx].padded, OUT_PADDED, s.cout, 0, s.cout);
+            if (bufs[s.idx].phase) add_out(bufs[s.idx].phase, OUT_PHASE, s.cout, 0, s.cout);
+            if (c.head == FVY_HEAD_YOLO3) {
+                if (s.idx == 60) add_out(catA, OUT_PADDED, 768, 256, s.cout);
+                if (s.idx == 35) add_out(catB, OUT_PADDED, 384, 128, s.cout);
+                if (s.idx == 84) add_out(catA, OUT_UP2_PADDED, 768, 0, s.cout);
+                if (s.idx == 96) add_out(catB, OUT_UP2_PADDED, 384, 0, s.cout);
+            }
+        }
+        if (no == 0) return fail(FVY_E_INVALID, "conv_%d has no consumer", s.idx);
+        if (no > 2) return fail(FVY_E_INVALID, "conv_%d has more than two stored forms", s.idx);
+        L.primary = p.out[0];
+        h->layers.push_back(L);
+    }
+    h->weight_count = (long long)stream_off;
+    return FVY_OK;
+}
+
+static int total_cands(const fvy_handle* h) {
+    if (h->cfg.head == FVY_HEAD_FD6) return (h->cfg.net_h / 32) * (h->cfg.net_w / 32);
+    int t = 0;
+    for (int lvl : {32, 16, 8}) t += 3 * (h->cfg.net_h / lvl) * (h->cfg.net_w / lvl);
+    return t;
+}
+
+static int build_post(fvy_handle* h) {
+    const fvy_config& c = h->cfg;
+    const int B = c.max_batch;
+    if (c.head == FVY_HEAD_NONE || c.head == FVY_HEAD_YOLO3) {
+        int i = 0;
+        for (int lvl : {32, 16, 8}) { h->gh[i] = c.net_h / lvl; h->gw[i] = c.net_w / lvl; ++i; }
+        h->head_c = 3 * (5 + c.nb_class);
+    }
+    if (c.head == FVY_HEAD_NONE) {   // post-processing-only handle still stages logits it is given
+        for (int i = 0; i < 3; ++i)
+            if (int e = dev_alloc(h, (void**)&h->d_logits[i], (size_t)B * h->gh[i] * h->gw[i] * h->head_c * 4, true)) return e;
+    }
+    h->cap = c.max_cands > 0 ? c.max_cands : total_cands(h);
+    h->capP = (h->cap + 63) / 64 * 64;
+    h->words = h->capP / 64;
+    h->np2max = 64;
+    while (h->np2max < h->cap) h->np2max <<= 1;
+    h->smem_keys = std::min(h->np2max, 16384);
+    const int nc = std::max(1, c.nb_class);
+    const size_t n = (size_t)B * h->cap;
+    if (int e = dev_alloc(h, (void**)&h->d_nbox, n * 4 * 8, false)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_ibox, n * 16, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_obj, n * 4, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_cls, n * nc * 4, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_cand, n * 4, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_counts, (size_t)B * 4, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_status, 16, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_image_hw, (size_t)B * 8, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_order, (size_t)B * h->capP * 4, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_sbox, (size_t)B * h->capP * 16, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_mask, (size_t)B * h->capP * h->words * 8, false)) return e;
+    if (h->np2max > h->smem_keys)
+        if (int e = dev_alloc(h, (void**)&h->d_gkeys, (size_t)B * h->np2max * 8, false)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_kept, n * 4, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_kept_counts, (size_t)B * 4, true)) return e;
+    h->dets_cap = h->cap;
+    if (int e = dev_alloc(h, (void**)&h->d_dets, n * sizeof(FvyDet), true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_det_counts, (size_t)B * 4, true)) return e;
+    CUDA_TRY(cudaFuncSetAttribute(sort_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_keys * 8));
+    return FVY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+static int stage_input(fvy_handle* h, const void* images, int dtype, int batch, const void** dev_images) {
+    const size_t es = dtype == FVY_F64 ? 8 : 4;
+    const size_t bytes = (size_t)batch * h->cfg.net_h * h->cfg.net_w * 3 * es;
+    if (is_device_ptr(images)) { *dev_images = images; return FVY_OK; }
+    if (h->input_bytes < bytes) {
+        if (h->d_input) cudaFree(h->d_input);
+        h->d_input = nullptr; h->input_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->d_input, bytes));
+        h->input_bytes = bytes;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_input, images, bytes, cudaMemcpyHostToDevice, h->stream));
+    *dev_images = h->d_input;
+    return FVY_OK;
+}
+
+static int run_layers(fvy_handle* h, int batch, int first, int last) {
+    for (int i = first; i < last; ++i) {
+        Layer& L = h->layers[i];
+        L.p.m_total = batch * L.p.dom_plane;
+        L.p.num_m_tiles = (L.p.m_total + kBlockM - 1) / kBlockM;
+        const int tiles = L.p.num_m_tiles * L.p.num_n_tiles;
+        const int grid = std::min(tiles, h->num_sms * L.occ);
+        if (int e = launch_conv(h, L, grid)) return e;
+    }
+    return FVY_OK;
+}
+
+static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int batch) {
+    if (!h->weights_loaded) return fail(FVY_E_STATE, "fvy_forward before fvy_load_weights");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (dtype != FVY_F32 && dtype != FVY_F64) return fail(FVY_E_INVALID, "dtype %d", dtype);
+    const void* dimg = nullptr;
+    if (int e = stage_input(h, images, dtype, batch, &dimg)) return e;
+    const long long pix = (long long)batch * h->cfg.net_h * h->cfg.net_w;
+    const int blocks = (int)std::min<long long>((pix + 255) / 256, (long long)h->num_sms * 16);
+    if (dtype == FVY_F32)
+        stem_im2col_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
+    else
+        stem_im2col_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    return run_layers(h, batch, 0, (int)h->layers.size());
+}
+
+static int copy_out(fvy_handle* h, const void* dev, void* dst, size_t bytes) {
+    if (!dst) return FVY_OK;
+    CUDA_TRY(cudaMemcpyAsync(dst, dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    return FVY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ post
+static int check_pp(const fvy_handle* h, const fvy_post_params* pp) {
+    if (!pp) return fail(FVY_E_INVALID, "fvy_post_params is NULL");
+    if (pp->arith != FVY_ARITH_F64 && pp->arith != FVY_ARITH_F32) return fail(FVY_E_INVALID, "arith %d", pp->arith);
+    (void)h;
+    return FVY_OK;
+}
+
+// logits given by the caller (host or device) or resident; returns device pointers
+static int resolve_logits(fvy_handle* h, const float* o0, const float* o1, const float* o2, int batch, const float* dev[3]) {
+    const float* in[3] = {o0, o1, o2};
+    const int nheads = h->cfg.head == FVY_HEAD_FD6 ? 1 : 3;
+    for (int i = 0; i < nheads; ++i) {
+        if (in[i] == nullptr) { dev[i] = h->d_logits[i]; continue; }
+        if (is_device_ptr(in[i])) { dev[i] = in[i]; continue; }
+        const size_t bytes = (size_t)batch * h->gh[i] * h->gw[i] * h->head_c * 4;
+        CUDA_TRY(cudaMemcpyAsync(h->d_logits[i], in[i], bytes, cudaMemcpyHostToDevice, h->stream));
+        dev[i] = h->d_logits[i];
+    }
+    return FVY_OK;
+}
+
+static int upload_image_hw(fvy_handle* h, const int* image_hw, int batch, const int** dev) {
+    if (!image_hw) { *dev = nullptr; return FVY_OK; }
+    if (is_device_ptr(image_hw)) { *dev = image_hw; return FVY_OK; }
+    CUDA_TRY(cudaMemcpyAsync(h->d_image_hw, image_hw, (size_t)batch * 8, cudaMemcpyHostToDevice, h->stream));
+    *dev = h->d_image_hw;
+    return FVY_OK;
+}
+
+static int decode_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy_post_params* pp, const int* d_hw, bool want_nbox) {
+    CUDA_TRY(cudaMemsetAsync(h->d_status, 0, 4, h->stream));
+    if (h->cfg.head == FVY_HEAD_FD6) {
+        DecodeFd6Args a;
+        a.cands = dev[0]; a.grid = h->gh[0]; a.image_size = h->cfg.net_h; a.cell_px = h->cfg.net_h / 13;
+        a.face_conf_th = pp->obj_thresh; a.arith = pp->arith; a.cap = h->cap;
+        a.ibox = h->d_ibox; a.objness = h->d_obj; a.score = h->d_cls; a.cand = h->d_cand; a.counts = h->d_counts;
+        decode_fd6_kernel<<<batch, 512, 0, h->stream>>>(a);
+    } else {
+        DecodeArgs a;
+        for (int i = 0; i < 3; ++i) { a.out[i] = dev[i]; a.gh[i] = h->gh[i]; a.gw[i] = h->gw[i]; }
+        a.nb_class = h->cfg.nb_class;
+        memcpy(a.anchors, pp->anchors, sizeof(a.anchors));
+        a.anchor_mask = pp->anchor_mask; a.obj_thresh = pp->obj_thresh;
+        a.net_h = h->cfg.net_h; a.net_w = h->cfg.net_w; a.arith = pp->arith;
+        a.image_hw = d_hw; a.cap = h->cap;
+        a.nbox = want_nbox ? h->d_nbox : nullptr; a.ibox = h->d_ibox; a.objness = h->d_obj; a.classes = h->d_cls;
+        a.cand = h->d_cand; a.counts = h->d_counts; a.status = h->d_status;
+        decode_yolo_kernel<<<batch, 1024, 0, h->stream>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    return FVY_OK;
+}
+
+// NMS over device-resident segments (ibox/classes with stride `seg_stride`, counts on device)
+static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int* d_counts, int batch, int seg_stride, int nb_class,
+                       double th) {
+    for (int c = 0; c < nb_class; ++c) {
+        SortArgs s;
+        s.ibox = d_ibox; s.classes = d_cls; s.counts = d_counts; s.seg_stride = seg_stride; s.nb_class = nb_class; s.cls = c;
+        s.capP = h->capP; s.descending = 1; s.order = h->d_order; s.sbox = h->d_sbox; s.gkeys = h->d_gkeys;
+        s.smem_keys = h->smem_keys; s.np2max = h->np2max;
+        sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->stream>>>(s);
+        CUDA_TRY(cudaGetLastError());
+        MaskArgs m;
+        m.sbox = h->d_sbox; m.counts = d_counts; m.seg_stride = seg_stride; m.batch = batch; m.capP = h->capP; m.words = h->words;
+        m.th = th; m.mask = h->d_mask;
+        nms_mask_kernel<<<h->num_sms * 16, 64, 0, h->stream>>>(m);
+        CUDA_TRY(cudaGetLastError());
+        SweepArgs w;
+        w.mask = h->d_mask; w.order = h->d_order; w.counts = d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
+        w.nb_class = nb_class; w.cls = c; w.classes = d_cls;
+        nms_sweep_kernel<<<batch, 512, (size_t)h->words * 8, h->stream>>>(w);
+        CUDA_TRY(cudaGetLastError());
+        h->launches += 3;
+    }
+    return FVY_OK;
+}
+
+static int post_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy_post_params* pp, const int* d_hw, int max_out) {
+    if (int e = decode_enqueue(h, dev, batch, pp, d_hw, false)) return e;
+    const int nc = h->cfg.head == FVY_HEAD_FD6 ? 1 : h->cfg.nb_class;
+    if (int e = nms_enqueue(h, h->d_ibox, h->d_cls, h->d_counts, batch, h->cap, nc, pp->nms_thresh)) return e;
+    AssembleArgs a;
+    a.ibox = h->d_ibox; a.objness = h->d_obj; a.classes = h->d_cls; a.cand = h->d_cand; a.counts = h->d_counts;
+    a.seg_stride = h->cap; a.nb_class = nc; a.max_out = max_out;
+    a.limit = pp->num_cands > 0 ? std::min(pp->num_cands, max_out) : max_out;
+    a.kept_idx = nullptr; a.kept_counts = nullptr; a.dets = h->d_dets; a.det_counts = h->d_det_counts;
+    if (h->cfg.head == FVY_HEAD_FD6) {
+        SortArgs s;
+        s.ibox = h->d_ibox; s.classes = h->d_cls; s.counts = h->d_counts; s.seg_stride = h->cap; s.nb_class = 1; s.cls = 0;
+        s.capP = h->capP; s.descending = 0; s.order = h->d_order; s.sbox = nullptr; s.gkeys = h->d_gkeys;
+        s.smem_keys = h->smem_keys; s.np2max = h->np2max;
+        sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->stream>>>(s);
+        CUDA_TRY(cudaGetLastError());
+        assemble_fd6_kernel<<<batch, 512, 0, h->stream>>>(a, h->d_order, h->capP);
+        h->launches += 2;
+    } else {
+        assemble_yolo_kernel<<<batch, 1024, 0, h->stream>>>(a);
+        ++h->launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FVY_OK;
+}
+
+static int check_post_status(fvy_handle* h, int batch, const int* counts_host) {
+    int st = 0;
+    CUDA_TRY(cudaMemcpy(&st, h->d_status, 4, cudaMemcpyDeviceToHost));
+    if (st & 1) return fail(FVY_E_RANGE, "decoded coordinate outside +-2^30");
+    if (counts_host)
+        for (int b = 0; b < batch; ++b)
+            if (counts_host[b] > h->cap) return fail(FVY_E_CAPACITY, "image %d: %d candidates exceed capacity %d", b, counts_host[b], h->cap);
+    return FVY_OK;
+}
+
+}  // namespace fvy
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char* fvy_last_error(void) { return g_err; }
+const char* fvy_version(void) { return "fvy 0.1 (sm_100a: tcgen05/TMEM/TMA implicit-GEMM conv, bitmask NMS)"; }
+
+void fvy_destroy(fvy_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->d_input) cudaFree(h->d_input);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fvy_create(const fvy_config* cfg, fvy_handle** out) {
+    if (!cfg || !out) return fail(FVY_E_INVALID, "NULL argument");
+    *out = nullptr;
+    if (cfg->head != FVY_HEAD_YOLO3 && cfg->head != FVY_HEAD_FD6 && cfg->head != FVY_HEAD_NONE) return fail(FVY_E_INVALID, "head %d", cfg->head);
+    if (cfg->net_h <= 0 || cfg->net_w <= 0 || cfg->net_h % 32 || cfg->net_w % 32) return fail(FVY_E_INVALID, "net size %dx%d must be a positive multiple of 32", cfg->net_h, cfg->net_w);
+    if (cfg->max_batch < 1 || cfg->max_batch > 1024) return fail(FVY_E_INVALID, "max_batch %d outside [1, 1024]", cfg->max_batch);
+    if (cfg->head != FVY_HEAD_FD6 && (cfg->nb_class < 1 || cfg->nb_class > 80)) return fail(FVY_E_INVALID, "nb_class %d outside [1, 80]", cfg->nb_class);
+    if (cfg->head == FVY_HEAD_FD6 && cfg->bb_info_c_size != 6) return fail(FVY_E_INVALID, "bb_info_c_size must be 6 (FaceDetector.detect reads channels 0..5)");
+    if (cfg->tile_n_max != 0 && cfg->tile_n_max != 32 && cfg->tile_n_max != 64 && cfg->tile_n_max != 128 && cfg->tile_n_max != 256)
+        return fail(FVY_E_INVALID, "tile_n_max %d", cfg->tile_n_max);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(FVY_E_CUDA, "no CUDA device (there is no CPU fallback)"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FVY_E_INVALID, "device %d of %d", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(FVY_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    fvy_handle* h = new fvy_handle();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    int e = FVY_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { e = fail(FVY_E_CUDA, "cudaStreamCreate failed"); break; }
+        bool ok = true;
+        for (auto& ev : h->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+        if (!ok) { e = fail(FVY_E_CUDA, "cudaEventCreate failed"); break; }
+        if (cfg->head != FVY_HEAD_NONE && (e = build_plan(h))) break;
+        if ((e = build_post(h))) break;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { e = fail(FVY_E_CUDA, "sync after create failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    if (e) { fvy_destroy(h); return e; }
+    *out = h;
+    return FVY_OK;
+}
+
+long long fvy_weight_count(const fvy_handle* h) { return h ? h->weight_count : 0; }
+
+int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats) {
+    if (!h || !stream) return fail(FVY_E_INVALID, "NULL argument");
+    if (h->cfg.head == FVY_HEAD_NONE) return fail(FVY_E_STATE, "handle has no network");
+    if ((long long)n_floats != h->weight_count) return fail(FVY_E_INVALID, "weight stream has %zu floats, network needs %lld", n_floats, h->weight_count);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    std::vector<uint16_t> wbuf;
+    std::vector<float> bbuf;
+    for (Layer& L : h->layers) {
+        const ConvSpec& s = L.s;
+        const float* p = stream + L.stream_off;
+        const float *beta = nullptr, *gamma = nullptr, *mean = nullptr, *var = nullptr, *bias = nullptr;
+        if (s.bn) { beta = p; gamma = p + s.cout; mean = p + 2 * s.cout; var = p + 3 * s.cout; p += 4 * s.cout; }   // yolov3_detect.py:97-101
+        else { bias = p; p += s.cout; }                                                                              // :108-109
+        const float* kern = p;   // (Cout, Cin, kh, kw)  :112, :117
+        const size_t kdim = (size_t)L.taps * L.cin_pad;
+        wbuf.assign((size_t)L.cout_pad * kdim, 0);
+        bbuf.assign(L.cout_pad, 0.f);
+        const bool stem = s.src == -1;
+        for (int o = 0; o < s.cout; ++o) {
+            float scale = 1.f;
+            if (s.bn) {
+                scale = gamma[o] / sqrtf(var[o] + 0.001f);          // BatchNormalization(epsilon=0.001) :212, folded in fp32
+                bbuf[o] = beta[o] - mean[o] * scale;
+            } else bbuf[o] = bias[o];
+            for (int ci = 0; ci < s.cin; ++ci)
+                for (int r = 0; r < s.k; ++r)
+                    for (int q = 0; q < s.k; ++q) {
+                        const float v = kern[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q] * scale;
+                        const size_t kk = stem ? (size_t)(r * 3 + q) * 3 + ci : (size_t)(r * s.k + q) * L.cin_pad + ci;
+                        wbuf[(size_t)o * kdim + kk] = f32_to_bf16_rn(v);
+                    }
+        }
+        CUDA_TRY(cudaMemcpyAsync(L.w, wbuf.data(), wbuf.size() * 2, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(L.bias, bbuf.data(), bbuf.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->weights_loaded = true;
+    return FVY_OK;
+}
+
+int fvy_forward(fvy_handle* h, const void* images, int dtype, int batch, float* out0, float* out1, float* out2) {
+    if (!h || !images) return fail(FVY_E_INVALID, "NULL argument");
+    if (h->cfg.head == FVY_HEAD_NONE) return fail(FVY_E_STATE, "handle has no network");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    if (int e = forward_enqueue(h, images, dtype, batch)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    float* outs[3] = {out0, out1, out2};
+    const int nheads = h->cfg.head == FVY_HEAD_FD6 ? 1 : 3;
+    for (int i = 0; i < nheads; ++i)
+        if (int e = copy_out(h, h->d_logits[i], outs[i], (size_t)batch * h->gh[i] * h->gw[i] * h->head_c * 4)) return e;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(&h->last_fwd_ms, h->ev[0], h->ev[1]));
+    return FVY_OK;
+}
+
+int fvy_decode(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch, const fvy_post_params* pp,
+               const int* image_hw, int cap, double* nbox, int32_t* ibox, float* objness, float* classes, int32_t* cand,
+               int32_t* counts) {
+    if (!h) return fail(FVY_E_INVALID, "NULL handle");
+    if (int e = check_pp(h, pp)) return e;
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (cap != h->cap) return fail(FVY_E_INVALID, "cap %d must equal the handle's candidate capacity %d", cap, h->cap);
+    if (ibox && !image_hw && h->cfg.head != FVY_HEAD_FD6) return fail(FVY_E_INVALID, "ibox needs image_hw");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const float* dev[3] = {nullptr, nullptr, nullptr};
+    if (int e = resolve_logits(h, out0, out1, out2, batch, dev)) return e;
+    const int* d_hw = nullptr;
+    if (int e = upload_image_hw(h, image_hw, batch, &d_hw)) return e;
+    if (int e = decode_enqueue(h, dev, batch, pp, d_hw, nbox != nullptr)) return e;
+    const int nc = h->cfg.head == FVY_HEAD_FD6 ? 1 : h->cfg.nb_class;
+    const size_t n = (size_t)batch * h->cap;
+    if (int e = copy_out(h, h->d_nbox, nbox, n * 32)) return e;
+    if (int e = copy_out(h, h->d_ibox, ibox, n * 16)) return e;
+    if (int e = copy_out(h, h->d_obj, objness, n * 4)) return e;
+    if (int e = copy_out(h, h->d_cls, classes, n * nc * 4)) return e;
+    if (int e = copy_out(h, h->d_cand, cand, n * 4)) return e;
+    std::vector<int> hc(batch);
+    CUDA_TRY(cudaMemcpyAsync(hc.data(), h->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (counts) {
+        if (is_device_ptr(counts)) CUDA_TRY(cudaMemcpy(counts, h->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToDevice));
+        else memcpy(counts, hc.data(), (size_t)batch * 4);
+    }
+    return check_post_status(h, batch, hc.data());
+}
+
+int fvy_correct_boxes(fvy_handle* h, const double* nbox, int n, int image_h, int image_w, int net_h, int net_w, int arith,
+                      int32_t* ibox) {
+    if (!h || !nbox || !ibox) return fail(FVY_E_INVALID, "NULL argument");
+    if (n < 0 || (size_t)n > (size_t)h->cfg.max_batch * h->cap) return fail(FVY_E_INVALID, "n %d exceeds scratch capacity", n);
+    if (n == 0) return FVY_OK;
+    if (image_h <= 0 || image_w <= 0 || net_h <= 0 || net_w <= 0) return fail(FVY_E_INVALID, "non-positive size");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemsetAsync(h->d_status, 0, 4, h->stream));
+    const double* src = nbox;
+    if (!is_device_ptr(nbox)) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_nbox, nbox, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+        src = h->d_nbox;
+    }
+    correct_boxes_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(src, n, image_h, image_w, net_h, net_w, arith, h->d_ibox, h->d_status);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    if (int e = copy_out(h, h->d_ibox, ibox, (size_t)n * 16)) return e;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_post_status(h, 0, nullptr);
+}
+
+int fvy_nms(fvy_handle* h, const int32_t* ibox, const int32_t* counts, int batch, int seg_stride, int nb_class, double nms_thresh,
+            float* classes, int32_t* kept_idx, int32_t* kept_counts) {
+    if (!h || !ibox || !counts || !classes) return fail(FVY_E_INVALID, "NULL argument");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (seg_stride < 1 || seg_stride > h->cap) return fail(FVY_E_INVALID, "seg_stride %d outside [1, %d]", seg_stride, h->cap);
+    if (nb_class < 1 || nb_class > std::max(1, h->cfg.nb_class)) return fail(FVY_E_INVALID, "nb_class %d exceeds the handle's %d", nb_class, h->cfg.nb_class);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)batch * seg_stride;
+    const bool dev_in = is_device_ptr(ibox);
+    if (dev_in != is_device_ptr(classes) || dev_in != is_device_ptr(counts)) return fail(FVY_E_INVALID, "ibox/classes/counts must all be host or all be device pointers");
+    const int* d_ibox = ibox; float* d_cls = classes; const int* d_counts = counts;
+    if (!dev_in) {
+        for (int b = 0; b < batch; ++b)
+            if (counts[b] < 0 || counts[b] > seg_stride) return fail(FVY_E_INVALID, "counts[%d] = %d outside [0, %d]", b, counts[b], seg_stride);
+        CUDA_TRY(cudaMemcpyAsync(h->d_ibox, ibox, n * 16, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_cls, classes, n * nb_class * 4, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_counts, counts, (size_t)batch * 4, cudaMemcpyHostToDevice, h->stream));
+        d_ibox = h->d_ibox; d_cls = h->d_cls; d_counts = h->d_counts;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    if (int e = nms_enqueue(h, d_ibox, d_cls, d_counts, batch, seg_stride, nb_class, nms_thresh)) return e;
+    if (kept_idx || kept_counts) {
+        AssembleArgs a;
+        a.ibox = d_ibox; a.objness = nullptr; a.classes = d_cls; a.cand = nullptr; a.counts = d_counts;
+        a.seg_stride = seg_stride; a.nb_class = nb_class; a.max_out = 0; a.limit = 0;
+        a.kept_idx = h->d_kept; a.kept_counts = h->d_kept_counts; a.dets = nullptr; a.det_counts = nullptr;
+        assemble_yolo_kernel<<<batch, 1024, 0, h->stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        ++h->launches;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+    if (!dev_in) if (int e = copy_out(h, d_cls, classes, n * nb_class * 4)) return e;
+    if (int e = copy_out(h, h->d_kept, kept_idx, n * 4)) return e;
+    if (int e = copy_out(h, h->d_kept_counts, kept_counts, (size_t)batch * 4)) return e;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(&h->last_post_ms, h->ev[2], h->ev[3]));
+    return FVY_OK;
+}
+
+int fvy_bbox_iou(fvy_handle* h, const int32_t* a, const int32_t* b, int n, double* out) {
+    if (!h || !a || !b || !out) return fail(FVY_E_INVALID, "NULL argument");
+    if (n < 0 || (size_t)n * 2 > (size_t)h->cfg.max_batch * h->cap) return fail(FVY_E_INVALID, "n %d exceeds scratch capacity", n);
+    if (n == 0) return FVY_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int4* da = reinterpret_cast<int4*>(h->d_ibox);
+    int4* db = da + n;
+    double* dout = h->d_nbox;
+    CUDA_TRY(cudaMemcpyAsync(da, a, (size_t)n * 16, cudaMemcpyDefault, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(db, b, (size_t)n * 16, cudaMemcpyDefault, h->stream));
+    bbox_iou_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(da, db, n, dout);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDefault, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FVY_OK;
+}
+
+static int postprocess_common(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch,
+                              const fvy_post_params* pp, const int* image_hw, int max_out, fvy_det* dets, int32_t* det_counts,
+                              bool sync) {
+    if (int e = check_pp(h, pp)) return e;
+    if (h->cfg.head == FVY_HEAD_NONE && (!out0 || !out1 || !out2)) return fail(FVY_E_INVALID, "post-processing-only handle needs all three logit tensors");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (max_out < 1 || max_out > h->dets_cap) return fail(FVY_E_INVALID, "max_out %d outside [1, %d]", max_out, h->dets_cap);
+    if (!dets || !det_counts) return fail(FVY_E_INVALID, "NULL output");
+    if (!image_hw && h->cfg.head != FVY_HEAD_FD6) return fail(FVY_E_INVALID, "image_hw is required (correct_yolo_boxes needs the image size)");
+    const float* dev[3] = {nullptr, nullptr, nullptr};
+    if (int e = resolve_logits(h, out0, out1, out2, batch, dev)) return e;
+    const int* d_hw = nullptr;
+    if (int e = upload_image_hw(h, image_hw, batch, &d_hw)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    if (int e = post_enqueue(h, dev, batch, pp, d_hw, max_out)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+    if (int e = copy_out(h, h->d_dets, dets, (size_t)batch * max_out * sizeof(FvyDet))) return e;
+    if (int e = copy_out(h, h->d_det_counts, det_counts, (size_t)batch * 4)) return e;
+    if (!sync) return FVY_OK;
+    std::vector<int> hc(batch);
+    CUDA_TRY(cudaMemcpyAsync(hc.data(), h->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(&h->last_post_ms, h->ev[2], h->ev[3]));
+    return check_post_status(h, batch, hc.data());
+}
+
+int fvy_postprocess(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch, const fvy_post_params* pp,
+                    const int* image_hw, int max_out, fvy_det* dets, int32_t* det_counts) {
+    if (!h) return fail(FVY_E_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    return postprocess_common(h, out0, out1, out2, batch, pp, image_hw, max_out, dets, det_counts, true);
+}
+
+static int detect_common(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp, const int* image_hw,
+                         int max_out, fvy_det* dets, int32_t* det_counts, bool sync) {
+    if (!h || !images) return fail(FVY_E_INVALID, "NULL argument");
+    if (h->cfg.head == FVY_HEAD_NONE) return fail(FVY_E_STATE, "handle has no network");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    if (int e = forward_enqueue(h, images, dtype, batch)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    if (int e = postprocess_common(h, nullptr, nullptr, nullptr, batch, pp, image_hw, max_out, dets, det_counts, sync)) return e;
+    if (sync) CUDA_TRY(cudaEventElapsedTime(&h->last_fwd_ms, h->ev[0], h->ev[1]));
+    return FVY_OK;
+}
+
+int fvy_detect(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp, const int* image_hw, int max_out,
+               fvy_det* dets, int32_t* det_counts) {
+    return detect_common(h, images, dtype, batch, pp, image_hw, max_out, dets, det_counts, true);
+}
+
+int fvy_detect_async(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp, const int* image_hw,
+                     int max_out, fvy_det* dets, int32_t* det_counts) {
+    return detect_common(h, images, dtype, batch, pp, image_hw, max_out, dets, det_counts, false);
+}
+
+int fvy_sync(fvy_handle* h) {
+    if (!h) return fail(FVY_E_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FVY_OK;
+}
+
+int fvy_num_layers(const fvy_handle* h) { return h ? (int)h->layers.size() : 0; }
+
+int fvy_layer_info(const fvy_handle* h, int layer, int* info) {
+    if (!h || !info || layer < 0 || layer >= (int)h->layers.size()) return fail(FVY_E_INVALID, "bad layer %d", layer);
+    const Layer& L = h->layers[layer];
+    const int m_total = h->cfg.max_batch * L.p.dom_plane;
+    const int tiles = ((m_total + kBlockM - 1) / kBlockM) * L.num_n_tiles;
+    const int v[12] = {L.s.idx, L.s.cin, L.s.cout, L.s.k, L.s.stride, L.Hout, L.Wout, L.BN, L.BK, L.stages,
+                       std::min(tiles, h->num_sms * L.occ), tiles};
+    memcpy(info, v, sizeof(v));
+    return FVY_OK;
+}
+
+int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host) {
+    if (!h || !dst_host || layer < 0 || layer >= (int)h->layers.size()) return fail(FVY_E_INVALID, "bad argument");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d", batch);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const Layer& L = h->layers[layer];
+    const size_t n = (size_t)batch * L.Hout * L.Wout * L.s.cout;
+    float* tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&tmp, n * 4));
+    unpack_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(L.primary, batch, L.Hout, L.Wout, L.s.cout, tmp);
+    cudaError_t e1 = cudaGetLastError();
+    cudaError_t e2 = cudaMemcpyAsync(dst_host, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(FVY_E_CUDA, "layer_output failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return FVY_OK;
+}
+
+long long fvy_launch_count(const fvy_handle* h) { return h ? h->launches : 0; }
+
+int fvy_last_timing(const fvy_handle* h, float* forward_ms, float* post_ms) {
+    if (!h) return fail(FVY_E_INVALID, "NULL handle");
+    if (forward_ms) *forward_ms = h->last_fwd_ms;
+    if (post_ms) *post_ms = h->last_post_ms;
+    return FVY_OK;
+}
+
+int fvy_profile_layers(fvy_handle* h, int batch, int iters, float* ms) {
+    if (!h || !ms) return fail(FVY_E_INVALID, "NULL argument");
+    if (!h->weights_loaded) return fail(FVY_E_STATE, "weights not loaded");
+    if (batch < 1 || batch > h->cfg.max_batch || iters < 1) return fail(FVY_E_INVALID, "bad batch/iters");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (size_t i = 0; i < h->layers.size(); ++i) {
+        if (int e = run_layers(h, batch, (int)i, (int)i + 1)) return e;   // warm
+        CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+        for (int it = 0; it < iters; ++it)
+            if (int e = run_layers(h, batch, (int)i, (int)i + 1)) return e;
+        CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+        ms[i] = t / iters;
+    }
+    return FVY_OK;
+}
+
+void* fvy_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void fvy_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

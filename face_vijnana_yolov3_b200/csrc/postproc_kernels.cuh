@@ -1,0 +1,563 @@
+// Post-processing kernels: anchor decode (+ letterbox correction), deterministic score sort,
+// bitmask-IoU, greedy sweep, detection assembly.  HBM-bound integer / byte work.
+//
+// Reference semantics restated on the device (paths under /root/reference/src/space/):
+//   decode_netout            yolov3_detect.py:335-387      correct_yolo_boxes   :389-404
+//   _interval_overlap        :165-178                      bbox_iou             :183-194
+//   do_nms / do_nms_v2       :426-458                      BoundBox.get_score   :151-155
+//   FaceDetector.detect      face_detection.py:899-947
+//
+// Exactness rules: every float/double operation that the reference performs as a separate
+// rounded operation is an explicit IEEE intrinsic (__fadd_rn, __ddiv_rn, ...) so that no FMA
+// contraction can change a result; exp() is evaluated in double and rounded once to float.
+// IoU is int64 arithmetic followed by one correctly rounded double divide, exactly the
+// reference's `float(intersect) / union`.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fvy {
+
+constexpr int kCoordLimit = (1 << 30) - 1;
+
+// ---------------------------------------------------------------- small helpers
+__device__ __forceinline__ float exp_cr_f32(float x) { return (float)exp((double)x); }
+// _sigmoid on a float32 array: 1. / (1. + np.exp(-x))   (yolov3_detect.py:180-181)
+__device__ __forceinline__ float sigmoid_ref(float x) {
+    const float e = exp_cr_f32(-x);
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+}
+
+// Exclusive block scan of a 0/1 flag; returns this thread's offset, total through *total (same for all threads).
+// blockDim.x must be a multiple of 32 and <= 1024.  `ws` = 33 ints of shared memory.
+__device__ __forceinline__ int block_scan_flag(bool flag, int* ws, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();                    // protect ws from the previous call
+    if (lane == 0) ws[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < nwarps ? ws[lane] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        ws[lane] = incl - v;
+        if (lane == 31) ws[32] = incl;
+    }
+    __syncthreads();
+    *total = ws[32];
+    return ws[warp] + within;
+}
+
+__device__ __forceinline__ int trunc_to_i32(double v, int* range_flag) {
+    // Python int(): truncation toward zero, unbounded.  Here: |v| must stay below 2^30.
+    if (!(v > -(double)kCoordLimit && v < (double)kCoordLimit)) { *range_flag = 1; return v < 0 ? -kCoordLimit : kCoordLimit; }
+    return (int)v;
+}
+
+// ---------------------------------------------------------------- yolo3 decode
+struct DecodeArgs {
+    const float* out[3];     // (B, gh, gw, C) fp32 logits per scale
+    int gh[3], gw[3];
+    int nb_class;
+    int anchors[18];
+    unsigned anchor_mask;    // bit 3*scale + b
+    double obj_thresh;
+    int net_h, net_w;
+    int arith;               // 0 = f64, 1 = f32
+    const int* image_hw;     // [B][2] or nullptr
+    int cap;                 // slot size per image
+    double* nbox;            // [B][cap][4] or nullptr
+    int* ibox;               // [B][cap][4] or nullptr
+    float* objness;          // [B][cap] or nullptr
+    float* classes;          // [B][cap][nb_class] or nullptr
+    int* cand;               // [B][cap] or nullptr
+    int* counts;             // [B]
+    int* status;             // [0] |= 1 range error
+};
+
+struct LetterboxConst { double x_off, x_scale, y_off, y_scale; int image_h, image_w; };
+
+// correct_yolo_boxes prologue (yolov3_detect.py:390-399), incl. the `new_h = net_w` else-branch.
+__device__ __forceinline__ LetterboxConst letterbox_const(int image_h, int image_w, int net_h, int net_w) {
+    double new_w, new_h;
+    if (__ddiv_rn((double)net_w, (double)image_w) < __ddiv_rn((double)net_h, (double)image_h)) {
+        new_w = (double)net_w;
+        new_h = __ddiv_rn((double)((long long)image_h * net_w), (double)image_w);
+    } else {
+        new_h = (double)net_w;
+        new_w = __ddiv_rn((double)((long long)image_w * net_h), (double)image_h);
+    }
+    LetterboxConst c;
+    c.x_off = __ddiv_rn(__ddiv_rn(__dsub_rn((double)net_w, new_w), 2.0), (double)net_w);
+    c.x_scale = __ddiv_rn(new_w, (double)net_w);
+    c.y_off = __ddiv_rn(__ddiv_rn(__dsub_rn((double)net_h, new_h), 2.0), (double)net_h);
+    c.y_scale = __ddiv_rn(new_h, (double)net_h);
+    c.image_h = image_h; c.image_w = image_w;
+    return c;
+}
+
+// int((v - offset) / scale * image_dim)   (yolov3_detect.py:401-404)
+__device__ __forceinline__ int correct_coord(double v, double off, double scale, int dim, int arith, int* range_flag) {
+    if (arith == 0) {
+        const double t = __dmul_rn(__ddiv_rn(__dsub_rn(v, off), scale), (double)dim);
+        return trunc_to_i32(t, range_flag);
+    }
+    const float t = __fmul_rn(__fdiv_rn(__fsub_rn((float)v, (float)off), (float)scale), (float)dim);
+    return trunc_to_i32((double)t, range_flag);
+}
+
+__global__ void __launch_bounds__(1024) decode_yolo_kernel(const DecodeArgs a) {
+    __shared__ int ws[33];
+    __shared__ LetterboxConst lb;
+    const int img = blockIdx.x;
+    const int ch = 5 + a.nb_class;
+    const int C = 3 * ch;
+    const int n0 = 3 * a.gh[0] * a.gw[0], n1 = n0 + 3 * a.gh[1] * a.gw[1], n2 = n1 + 3 * a.gh[2] * a.gw[2];
+    if (threadIdx.x == 0 && a.image_hw != nullptr)
+        lb = letterbox_const(a.image_hw[2 * img], a.image_hw[2 * img + 1], a.net_h, a.net_w);
+    __syncthreads();
+    int base = 0;
+    int range_flag = 0;
+    for (int start = 0; start < n2; start += blockDim.x) {
+        const int g = start + threadIdx.x;
+        bool pass = false;
+        const float* t = nullptr;
+        int s = 0, cell = 0, b = 0;
+        float obj = 0.f;
+        if (g < n2) {
+            s = g < n0 ? 0 : (g < n1 ? 1 : 2);
+            const int local = g - (s == 0 ? 0 : (s == 1 ? n0 : n1));
+            cell = local / 3; b = local - 3 * cell;
+            if ((a.anchor_mask >> (3 * s + b)) & 1u) {                                  // :354-362
+                t = a.out[s] + ((size_t)img * a.gh[s] * a.gw[s] + cell) * C + b * ch;
+                obj = sigmoid_ref(__ldg(t + 4));                                        // :344
+                const bool below = a.arith == 0 ? ((double)obj < a.obj_thresh) : (obj < (float)a.obj_thresh);
+                pass = !below;                                                          // :368
+            }
+        }
+        int total;
+        const int pos = base + block_scan_flag(pass, ws, &total);
+        if (pass && pos < a.cap) {
+            const int gw = a.gw[s], gh = a.gh[s];
+            const int row = cell / gw, col = cell - row * gw;                           // :349-350
+            const float sx = sigmoid_ref(__ldg(t + 0)), sy = sigmoid_ref(__ldg(t + 1)); // :343
+            const float ew = exp_cr_f32(__ldg(t + 2)), eh = exp_cr_f32(__ldg(t + 3));   // :375-376
+            const int aw = a.anchors[6 * s + 2 * b], ah = a.anchors[6 * s + 2 * b + 1];
+            double x0, y0, x1, y1;
+            if (a.arith == 0) {
+                const double x = __ddiv_rn(__dadd_rn((double)col, (double)sx), (double)gw);   // :373
+                const double y = __ddiv_rn(__dadd_rn((double)row, (double)sy), (double)gh);   // :374
+                const double w = __ddiv_rn(__dmul_rn((double)aw, (double)ew), (double)a.net_w);   // :375
+                const double h = __ddiv_rn(__dmul_rn((double)ah, (double)eh), (double)a.net_h);   // :376
+                const double hw = __ddiv_rn(w, 2.0), hh = __ddiv_rn(h, 2.0);
+                x0 = __dsub_rn(x, hw); y0 = __dsub_rn(y, hh); x1 = __dadd_rn(x, hw); y1 = __dadd_rn(y, hh);   // :383
+            } else {
+                const float x = __fdiv_rn(__fadd_rn((float)col, sx), (float)gw);
+                const float y = __fdiv_rn(__fadd_rn((float)row, sy), (float)gh);
+                const float w = __fdiv_rn(__fmul_rn((float)aw, ew), (float)a.net_w);
+                const float h = __fdiv_rn(__fmul_rn((float)ah, eh), (float)a.net_h);
+                const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+                x0 = __fsub_rn(x, hw); y0 = __fsub_rn(y, hh); x1 = __fadd_rn(x, hw); y1 = __fadd_rn(y, hh);
+            }
+            const size_t o = (size_t)img * a.cap + pos;
+            if (a.nbox) { double* d = a.nbox + 4 * o; d[0] = x0; d[1] = y0; d[2] = x1; d[3] = y1; }
+            if (a.ibox && a.image_hw) {
+                int4 q;
+                q.x = correct_coord(x0, lb.x_off, lb.x_scale, lb.image_w, a.arith, &range_flag);
+                q.y = correct_coord(y0, lb.y_off, lb.y_scale, lb.image_h, a.arith, &range_flag);
+                q.z = correct_coord(x1, lb.x_off, lb.x_scale, lb.image_w, a.arith, &range_flag);
+                q.w = correct_coord(y1, lb.y_off, lb.y_scale, lb.image_h, a.arith, &range_flag);
+                reinterpret_cast<int4*>(a.ibox)[o] = q;
+            }
+            if (a.objness) a.objness[o] = obj;
+            if (a.classes)
+                for (int c = 0; c < a.nb_class; ++c) a.classes[o * a.nb_class + c] = sigmoid_ref(__ldg(t + 5 + c));   // :344
+            if (a.cand) a.cand[o] = g;
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) a.counts[img] = base;
+    if (range_flag) atomicOr(a.status, 1);
+}
+
+__global__ void correct_boxes_kernel(const double* nbox, int n, int image_h, int image_w, int net_h, int net_w, int arith,
+                                     int* ibox, int* status) {
+    const LetterboxConst lb = letterbox_const(image_h, image_w, net_h, net_w);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int rf = 0;
+    int4 q;
+    q.x = correct_coord(nbox[4 * i + 0], lb.x_off, lb.x_scale, image_w, arith, &rf);
+    q.y = correct_coord(nbox[4 * i + 1], lb.y_off, lb.y_scale, image_h, arith, &rf);
+    q.z = correct_coord(nbox[4 * i + 2], lb.x_off, lb.x_scale, image_w, arith, &rf);
+    q.w = correct_coord(nbox[4 * i + 3], lb.y_off, lb.y_scale, image_h, arith, &rf);
+    reinterpret_cast<int4*>(ibox)[i] = q;
+    if (rf) atomicOr(status, 1);
+}
+
+// ---------------------------------------------------------------- fd6 decode (FaceDetector.detect, face_detection.py:900-932)
+struct DecodeFd6Args {
+    const float* cands;   // (B, g, g, 6) raw linear outputs
+    int grid;             // g = net/32
+    int image_size;       // nn_arch.image_size
+    int cell_px;          // image_size // 13  (face_detection.py:325)
+    double face_conf_th;
+    int arith;
+    int cap;
+    int* ibox; float* objness; float* score; int* cand; int* counts;
+};
+
+__global__ void __launch_bounds__(512) decode_fd6_kernel(const DecodeFd6Args a) {
+    __shared__ int ws[33];
+    const int img = blockIdx.x;
+    const int ncell = a.grid * a.grid;
+    int base = 0;
+    for (int start = 0; start < ncell; start += blockDim.x) {
+        const int g = start + threadIdx.x;
+        bool pass = false;
+        float obj = 0.f, sc = 0.f;
+        const float* t = nullptr;
+        if (g < ncell) {
+            t = a.cands + ((size_t)img * ncell + g) * 6;
+            obj = sigmoid_ref(__ldg(t + 0));                               // :904
+            sc = __fmul_rn(obj, sigmoid_ref(__ldg(t + 5)));                // :905
+            const bool ge = a.arith == 0 ? ((double)sc >= a.face_conf_th) : (sc >= (float)a.face_conf_th);
+            pass = obj > 0.f && ge;                                        // :909
+        }
+        int total;
+        const int pos = base + block_scan_flag(pass, ws, &total);
+        if (pass && pos < a.cap) {
+            const int i = g / a.grid, j = g - i * a.grid;
+            const float r1 = __ldg(t + 1), r2 = __ldg(t + 2), r3 = __ldg(t + 3), r4 = __ldg(t + 4);
+            const double bx = r1 > 0.f ? (double)r1 : 0.0, by = r2 > 0.f ? (double)r2 : 0.0;   // :912-913
+            const double bw = r3 > 0.f ? (double)r3 : 0.0, bh = r4 > 0.f ? (double)r4 : 0.0;   // :914-915
+            const double lim = (double)kCoordLimit;
+            double tx = __dmul_rn(bx, (double)a.cell_px); tx = tx < lim ? tx : lim;
+            double ty = __dmul_rn(by, (double)a.cell_px); ty = ty < lim ? ty : lim;
+            int px = (int)tx; px = (px < a.cell_px - 1 ? px : a.cell_px - 1) + a.cell_px * j;   // :919
+            int py = (int)ty; py = (py < a.cell_px - 1 ? py : a.cell_px - 1) + a.cell_px * i;   // :920
+            double pw = __dmul_rn(bw, (double)a.image_size); pw = pw < (double)a.image_size ? pw : (double)a.image_size;   // :921
+            double ph = __dmul_rn(bh, (double)a.image_size); ph = ph < (double)a.image_size ? ph : (double)a.image_size;   // :922
+            const int hw = (int)__ddiv_rn(pw, 2.0), hh = (int)__ddiv_rn(ph, 2.0);
+            int4 q;
+            q.x = max(px - hw, 0); q.y = max(py - hh, 0);                                       // :925-926
+            q.z = min(px + hw, a.image_size - 1); q.w = min(py + hh, a.image_size - 1);         // :927-928
+            const size_t o = (size_t)img * a.cap + pos;
+            reinterpret_cast<int4*>(a.ibox)[o] = q;
+            a.objness[o] = obj; a.score[o] = sc; a.cand[o] = g;
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) a.counts[img] = base;
+}
+
+// ---------------------------------------------------------------- IoU
+// _interval_overlap (yolov3_detect.py:165-178)
+__device__ __forceinline__ long long interval_overlap(long long x1, long long x2, long long x3, long long x4) {
+    if (x3 < x1) {
+        if (x4 < x1) return 0;
+        return (x2 < x4 ? x2 : x4) - x1;
+    }
+    if (x2 < x3) return 0;
+    return (x2 < x4 ? x2 : x4) - x3;
+}
+struct IouParts { long long inter, uni; };
+__device__ __forceinline__ IouParts iou_parts(const int4 a, const int4 b) {
+    const long long iw = interval_overlap(a.x, a.z, b.x, b.z);
+    const long long ih = interval_overlap(a.y, a.w, b.y, b.w);
+    IouParts r;
+    r.inter = iw * ih;                                                     // :187
+    const long long w1 = (long long)a.z - a.x, h1 = (long long)a.w - a.y;
+    const long long w2 = (long long)b.z - b.x, h2 = (long long)b.w - b.y;
+    r.uni = w1 * h1 + w2 * h2 - r.inter;                                   // :192
+    return r;
+}
+// bbox_iou(...) >= thresh  (yolov3_detect.py:194, 443).  union == 0 -> nan -> false.
+__device__ __forceinline__ bool iou_ge(const int4 a, const int4 b, double th, bool zero_ge_th) {
+    const IouParts p = iou_parts(a, b);
+    if (p.uni == 0) return false;
+    if (p.inter == 0) return zero_ge_th;
+    return __ddiv_rn((double)p.inter, (double)p.uni) >= th;
+}
+__global__ void bbox_iou_kernel(const int4* a, const int4* b, int n, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const IouParts p = iou_parts(a[i], b[i]);
+    out[i] = p.uni == 0 ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn((double)p.inter, (double)p.uni);
+}
+
+// ---------------------------------------------------------------- deterministic sort
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending uint order == ascending float order
+}
+
+// Bitonic sort of `np2` 64-bit keys (np2 = power of two) held in shared or global memory.
+__device__ void bitonic_sort_u64(unsigned long long* keys, int np2) {
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = keys[i], b = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct SortArgs {
+    const int* ibox;        // [.. ][4]
+    const float* classes;   // [..][nb_class]
+    const int* counts;      // [B]
+    int seg_stride;         // entries between image segments in ibox/classes
+    int nb_class, cls;      // class being processed
+    int capP;               // scratch stride per image (multiple of 64)
+    int descending;         // 1: score desc (do_nms), 0: score asc (detect's final argsort)
+    int* order;             // [B][capP] sorted candidate indices
+    int4* sbox;             // [B][capP] boxes in sorted order (may be nullptr)
+    unsigned long long* gkeys;   // [B][np2max] global scratch when the keys do not fit in shared memory
+    int smem_keys;          // number of keys that fit in dynamic shared memory
+    int np2max;
+};
+
+// One block per image: order = argsort(-score) with ties by index ascending (yolov3_detect.py:433, 447).
+__global__ void __launch_bounds__(1024) sort_scores_kernel(const SortArgs a) {
+    extern __shared__ unsigned long long skeys[];
+    const int img = blockIdx.x;
+    const int n = min(a.counts[img], a.seg_stride);
+    if (n <= 0) return;
+    int np2 = 64;
+    while (np2 < n) np2 <<= 1;
+    unsigned long long* keys = np2 <= a.smem_keys ? skeys : a.gkeys + (size_t)img * a.np2max;
+    const size_t seg = (size_t)img * a.seg_stride;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < n) {
+            uint32_t o = float_orderable(a.classes[(seg + i) * a.nb_class + a.cls]);
+            if (a.descending) o = ~o;
+            k = ((unsigned long long)o << 32) | (uint32_t)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort_u64(keys, np2);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int idx = (int)(keys[i] & 0xffffffffu);
+        a.order[(size_t)img * a.capP + i] = idx;
+        if (a.sbox) a.sbox[(size_t)img * a.capP + i] = reinterpret_cast<const int4*>(a.ibox)[seg + idx];
+    }
+}
+
+// ---------------------------------------------------------------- bitmask IoU
+struct MaskArgs {
+    const int4* sbox;       // [B][capP]
+    const int* counts;      // [B]
+    int seg_stride;
+    int batch, capP, words; // words = capP / 64
+    double th;
+    unsigned long long* mask;   // [B][capP][words]; only words >= row/64 are written
+};
+
+// Persistent blocks of 64 threads; one 64x64 tile per iteration: thread t owns sorted row r*64+t and
+// produces the 64-bit word of column block c (bit j set <=> IoU(row, c*64+j) >= th and c*64+j > row).
+__global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
+    __shared__ int4 cbox[64];
+    __shared__ int tile_prefix[1025];   // batch <= 1024
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < a.batch; ++b) {
+            tile_prefix[b] = acc;
+            const int n = min(a.counts[b], a.seg_stride);
+            const int nb = (n + 63) >> 6;
+            acc += nb * nb;
+        }
+        tile_prefix[a.batch] = acc;
+    }
+    __syncthreads();
+    const int total = tile_prefix[a.batch];
+    const bool zero_ge = 0.0 >= a.th;
+    int img = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        while (tile_prefix[img + 1] <= t) ++img;          // t is increasing
+        const int n = min(a.counts[img], a.seg_stride);
+        const int nb = (n + 63) >> 6;
+        const int lt = t - tile_prefix[img];
+        const int r = lt / nb, c = lt - r * nb;
+        if (c < r) continue;                               // block-uniform
+        const int4* sb = a.sbox + (size_t)img * a.capP;
+        const int col = c * 64 + threadIdx.x;
+        __syncthreads();
+        cbox[threadIdx.x] = col < n ? sb[col] : make_int4(0, 0, 0, 0);
+        __syncthreads();
+        const int row = r * 64 + threadIdx.x;
+        if (row < n) {
+            const int4 me = sb[row];
+            unsigned long long word = 0;
+            const int jmax = min(64, n - c * 64);
+            for (int j = (c == r ? threadIdx.x + 1 : 0); j < jmax; ++j)
+                if (iou_ge(me, cbox[j], a.th, zero_ge)) word |= 1ull << j;
+            a.mask[((size_t)img * a.capP + row) * a.words + c] = word;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- greedy sweep
+struct SweepArgs {
+    const unsigned long long* mask;
+    const int* order;       // [B][capP]
+    const int* counts;
+    int seg_stride, capP, words;
+    int nb_class, cls;
+    float* classes;         // in/out
+};
+
+// One block per image.  Walks the sorted list in blocks of 64: a single thread resolves the
+// in-block dependencies on the diagonal word, then all threads OR the kept rows into `removed`.
+// Boxes whose score is already 0 never suppress (yolov3_detect.py:438).
+__global__ void __launch_bounds__(512) nms_sweep_kernel(const SweepArgs a) {
+    extern __shared__ unsigned long long removed[];    // [words]
+    __shared__ unsigned long long diag[64];
+    __shared__ unsigned long long alive_w, keep_w;
+    const int img = blockIdx.x;
+    const int n = min(a.counts[img], a.seg_stride);
+    if (n <= 0) return;
+    const int nb = (n + 63) >> 6;
+    const size_t seg = (size_t)img * a.seg_stride;
+    const int* ord = a.order + (size_t)img * a.capP;
+    const unsigned long long* mk = a.mask + (size_t)img * a.capP * a.words;
+    for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
+    __syncthreads();
+    for (int blk = 0; blk < nb; ++blk) {
+        if (threadIdx.x == 0) alive_w = 0;
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int i = blk * 64 + threadIdx.x;
+            unsigned long long d = 0;
+            if (i < n) {
+                d = mk[(size_t)i * a.words + blk];
+                if (a.classes[(seg + ord[i]) * a.nb_class + a.cls] != 0.f) atomicOr(&alive_w, 1ull << threadIdx.x);
+            }
+            diag[threadIdx.x] = d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long cur = removed[blk], keep = 0;
+            const unsigned long long alive = alive_w;
+            for (int b = 0; b < 64; ++b) {
+                if (((alive >> b) & 1ull) && !((cur >> b) & 1ull)) { keep |= 1ull << b; cur |= diag[b]; }
+            }
+            removed[blk] = cur;
+            keep_w = keep;
+        }
+        __syncthreads();
+        const unsigned long long keep = keep_w;
+        for (int w = blk + 1 + threadIdx.x; w < nb; w += blockDim.x) {
+            unsigned long long acc = removed[w];
+            unsigned long long kk = keep;
+            while (kk) {
+                const int b = __ffsll((long long)kk) - 1;
+                kk &= kk - 1;
+                acc |= mk[(size_t)(blk * 64 + b) * a.words + w];
+            }
+            removed[w] = acc;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if ((removed[i >> 6] >> (i & 63)) & 1ull) a.classes[(seg + ord[i]) * a.nb_class + a.cls] = 0.f;   // :444
+}
+
+// ---------------------------------------------------------------- kept list / detection records
+struct FvyDet { int xmin, ymin, xmax, ymax; float objness, score; int label, cand; };
+
+struct AssembleArgs {
+    const int* ibox; const float* objness; const float* classes; const int* cand; const int* counts;
+    int seg_stride, nb_class;
+    int max_out, limit;      // limit = num_cands cap (<= max_out)
+    int* kept_idx;           // [B][seg_stride] or nullptr
+    int* kept_counts;        // [B] or nullptr
+    FvyDet* dets;            // [B][max_out] or nullptr
+    int* det_counts;         // [B] or nullptr
+};
+
+// One block per image: candidates that keep a class score > 0 after NMS, in candidate order.
+__global__ void __launch_bounds__(1024) assemble_yolo_kernel(const AssembleArgs a) {
+    __shared__ int ws[33];
+    const int img = blockIdx.x;
+    const int n = min(a.counts[img], a.seg_stride);
+    const size_t seg = (size_t)img * a.seg_stride;
+    int base = 0;
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        bool keep = false; float best = 0.f; int label = 0;
+        if (i < n) {
+            const float* c = a.classes + (seg + i) * a.nb_class;
+            best = c[0];
+            for (int k = 1; k < a.nb_class; ++k) if (c[k] > best) { best = c[k]; label = k; }   // np.argmax: first maximum
+            for (int k = 0; k < a.nb_class; ++k) keep |= c[k] > 0.f;
+        }
+        int total;
+        const int pos = base + block_scan_flag(keep, ws, &total);
+        if (keep) {
+            if (a.kept_idx) a.kept_idx[seg + pos] = i;
+            if (a.dets && pos < a.limit) {
+                const int4 q = reinterpret_cast<const int4*>(a.ibox)[seg + i];
+                FvyDet d;
+                d.xmin = q.x; d.ymin = q.y; d.xmax = q.z; d.ymax = q.w;
+                d.objness = a.objness ? a.objness[seg + i] : 0.f;
+                d.score = best < 1.0f ? best : 1.0f;                  // get_score clips to 1.0 (:155)
+                d.label = label; d.cand = a.cand ? a.cand[seg + i] : i;
+                a.dets[(size_t)img * a.max_out + pos] = d;
+            }
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) {
+        if (a.kept_counts) a.kept_counts[img] = base;
+        if (a.det_counts) a.det_counts[img] = min(base, a.limit);
+    }
+}
+
+// fd6 tail (face_detection.py:942-947): survivors with get_score() > 0, ascending by score (ties: index
+// ascending), first num_cands.  `order` = argsort ascending over ALL candidates (sort_scores_kernel with
+// descending = 0 after NMS zeroing); zero scores sort first and are skipped.
+__global__ void __launch_bounds__(512) assemble_fd6_kernel(const AssembleArgs a, const int* order, int capP) {
+    __shared__ int ws[33];
+    const int img = blockIdx.x;
+    const int n = min(a.counts[img], a.seg_stride);
+    const size_t seg = (size_t)img * a.seg_stride;
+    int base = 0;
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int p = start + threadIdx.x;
+        bool keep = false; int i = 0; float sc = 0.f;
+        if (p < n) {
+            i = order[(size_t)img * capP + p];
+            sc = a.classes[seg + i];
+            sc = sc < 1.0f ? sc : 1.0f;
+            keep = sc > 0.f;
+        }
+        int total;
+        const int pos = base + block_scan_flag(keep, ws, &total);
+        if (keep && pos < a.limit) {
+            const int4 q = reinterpret_cast<const int4*>(a.ibox)[seg + i];
+            FvyDet d;
+            d.xmin = q.x; d.ymin = q.y; d.xmax = q.z; d.ymax = q.w;
+            d.objness = a.objness[seg + i]; d.score = sc; d.label = 0; d.cand = a.cand[seg + i];
+            a.dets[(size_t)img * a.max_out + pos] = d;
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) a.det_counts[img] = min(base, a.limit);
+}
+
+}  // namespace fvy

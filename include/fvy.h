@@ -1,0 +1,171 @@
+/* fvy.h — C ABI of the B200-native face-detection hot path (libfvy.so).
+ *
+ * The reference (tonandr/face_vijnana_yolov3) is pure Python with no FFI of its own: the boundary
+ * of its hot path is `Model.predict` plus the host functions that follow it.  Each entry point
+ * below cites the reference interface it replaces (paths under /root/reference/).  The Python
+ * drop-ins in face_vijnana_yolov3_b200/space/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch types.
+ *   - Every function returns 0 (FVY_OK) or a negative fvy_status; the message is available from
+ *     fvy_last_error() (thread-local).  No C++ exception crosses the ABI.
+ *   - Data pointers may be HOST or DEVICE pointers (queried with cudaPointerGetAttributes);
+ *     host buffers are staged through pinned memory owned by the handle.  The caller owns every
+ *     pointer it passes; the handle owns weights, activation arena, tensor maps and scratch.
+ *   - A handle is bound to one device and one stream and is not re-entrant; distinct handles are
+ *     independent (8 GPUs = 8 handles, one process or thread each).
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with FVY_E_CUDA.
+ */
+#ifndef FVY_H_
+#define FVY_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fvy_handle fvy_handle;
+
+typedef enum {
+    FVY_OK = 0,
+    FVY_E_INVALID = -1,   /* bad argument */
+    FVY_E_CUDA = -2,      /* CUDA runtime / driver error, or no device */
+    FVY_E_STATE = -3,     /* e.g. forward before load_weights */
+    FVY_E_CAPACITY = -4,  /* more candidates than the configured capacity */
+    FVY_E_RANGE = -5      /* decoded coordinate outside +-2^30 (reference: unbounded Python int) */
+} fvy_status;
+
+enum { FVY_HEAD_YOLO3 = 0, FVY_HEAD_FD6 = 1, FVY_HEAD_NONE = 2 };   /* NONE: post-processing only */
+enum { FVY_F32 = 0, FVY_F64 = 1 };                                 /* dtype of the image tensor */
+enum { FVY_ARITH_F64 = 0, FVY_ARITH_F32 = 1 };                     /* decode scalar arithmetic (see fvy_decode) */
+
+/* The fork's anchor mask in decode_netout (src/space/yolov3_detect.py:354-362): bit (3*scale+b). */
+#define FVY_ANCHOR_MASK_REFERENCE 0x0AAu
+#define FVY_ANCHOR_MASK_ALL 0x1FFu
+
+typedef struct {
+    int device;          /* CUDA device ordinal */
+    int net_h, net_w;    /* network input size, multiples of 32 (416 / 608) */
+    int head;            /* FVY_HEAD_* */
+    int nb_class;        /* yolo3 heads: C = 3*(5+nb_class) (yolov3_detect.py:278,294,308 hard-code 80) */
+    int bb_info_c_size;  /* fd6 head channels (face_vijnana_yolov3.json:27 -> 6) */
+    int max_batch;       /* images per forward call */
+    int max_cands;       /* candidate capacity per image for decode/NMS; 0 = every cell x anchor */
+    int tile_n_max;      /* 0 = default; upper bound on the GEMM N tile (tuning knob) */
+    int flags;           /* reserved, 0 */
+} fvy_config;
+
+/* One detection, 32 bytes.  Mirrors the fields of the reference's BoundBox that survive the hot
+ * path (src/space/yolov3_detect.py:126-145): xmin,ymin,xmax,ymax,objness, get_label(), get_score(). */
+typedef struct {
+    int32_t xmin, ymin, xmax, ymax;
+    float objness;
+    float score;   /* classes[label] after NMS */
+    int32_t label; /* argmax class */
+    int32_t cand;  /* candidate index in reference order: yolo3 = offset(scale) + (row*gw+col)*3+b (all-anchor
+                      numbering); fd6 = row*13+col */
+} fvy_det;
+
+typedef struct {
+    double obj_thresh;        /* decode_netout obj_thresh (yolov3_detect.py:335,368) / hps.face_conf_th (face_detection.py:909) */
+    double nms_thresh;        /* do_nms nms_thresh (yolov3_detect.py:426,443) / hps.nms_iou_th (face_detection.py:939) */
+    int num_cands;            /* fd6: hps.num_cands (face_detection.py:946-947); yolo3: cap on returned boxes, 0 = max_out */
+    unsigned anchor_mask;     /* yolo3: FVY_ANCHOR_MASK_* */
+    int anchors[18];          /* yolo3: 9 (w,h) pairs, scale 0 (stride 32) first (yolov3_detect.py:558-560) */
+    int arith;                /* FVY_ARITH_* */
+} fvy_post_params;
+
+const char* fvy_last_error(void);
+const char* fvy_version(void);
+
+/* Lifetime.  Replaces model construction: make_yolov3_model() (yolov3_detect.py:217-311) /
+ * FaceDetector.__init__ + YOLOV3Base (face_detection.py:312-382, 384-600). */
+int fvy_create(const fvy_config* cfg, fvy_handle** out);
+void fvy_destroy(fvy_handle* h);
+
+/* Weight ingest.  Replaces WeightReader.load_weights (yolov3_detect.py:90-121): `stream` is the
+ * float32 payload of a Darknet .weights file (header stripped) in the order that function reads
+ * it; for FVY_HEAD_FD6 the 3x3 head's bias[c] + kernel[c][1024][3][3] follow conv_73.  Folds
+ * BatchNorm (eps = 1e-3) in fp32, rounds once to bf16, packs K-major GEMM operands. HOST pointer. */
+int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats);
+/* Number of floats fvy_load_weights expects (= parameter count: 61 576 342 for yolo3, nb_class 1). */
+long long fvy_weight_count(const fvy_handle* h);
+
+/* Forward.  Replaces Model.predict (yolov3_detect.py:593, face_detection.py:899).
+ *   images: (batch, net_h, net_w, 3) NHWC, dtype FVY_F32 / FVY_F64, values in [0,1].
+ *   out0/out1/out2: yolo3 -> (batch, H/32, W/32, C), (batch, H/16, W/16, C), (batch, H/8, W/8, C) fp32;
+ *                   fd6   -> out0 = (batch, H/32, W/32, bb_info_c_size), out1 = out2 = NULL.
+ *   Any out pointer may be NULL: the logits then stay in the handle for fvy_postprocess. */
+int fvy_forward(fvy_handle* h, const void* images, int dtype, int batch, float* out0, float* out1, float* out2);
+
+/* Decode, yolo3.  Replaces decode_netout over the three scales (yolov3_detect.py:335-387, loop at
+ * :596-598) and, when image_hw != NULL, correct_yolo_boxes (:389-404).
+ *   out0..2: logits as produced by fvy_forward (NULL = use the handle's resident logits).
+ *   image_hw: batch x {image_h, image_w} or NULL.
+ *   Outputs (each may be NULL), per image b a slot of `cap` = capacity entries:
+ *     nbox  [batch][cap][4] double  xmin,ymin,xmax,ymax normalised to the net (BoundBox floats)
+ *     ibox  [batch][cap][4] int32   after correct_yolo_boxes (needs image_hw)
+ *     objness [batch][cap], classes [batch][cap][nb_class] float, cand [batch][cap] int32
+ *     counts [batch] int32
+ *   arith: FVY_ARITH_F64 = scalar math in double (NumPy 1.x promotion, the reference's pinned
+ *   environment); FVY_ARITH_F32 = float (NumPy >= 2).  sigmoid/exp are float32 array ops in both. */
+int fvy_decode(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch,
+               const fvy_post_params* pp, const int* image_hw, int cap, double* nbox, int32_t* ibox, float* objness,
+               float* classes, int32_t* cand, int32_t* counts);
+
+/* correct_yolo_boxes / correct_yolo_boxes_v2 on its own (yolov3_detect.py:389-424): n boxes of one image. */
+int fvy_correct_boxes(fvy_handle* h, const double* nbox, int n, int image_h, int image_w, int net_h, int net_w,
+                      int arith, int32_t* ibox);
+
+/* Greedy per-class NMS.  Replaces do_nms / do_nms_v2 (yolov3_detect.py:426-458) with bbox_iou
+ * (:183-194) on integer boxes.  Segment b holds counts[b] boxes starting at entry b*seg_stride.
+ *   ibox    [..][4] int32;  classes [..][nb_class] float, IN/OUT: suppressed scores set to 0.
+ *   kept_idx (optional) [batch][seg_stride] int32: indices (within the segment, ascending) whose
+ *   score for class 0..nb_class-1 is still > 0 for at least one class; kept_counts [batch].
+ * Order: score descending, ties by index ascending (the reference's argsort leaves ties undefined). */
+int fvy_nms(fvy_handle* h, const int32_t* ibox, const int32_t* counts, int batch, int seg_stride, int nb_class,
+            double nms_thresh, float* classes, int32_t* kept_idx, int32_t* kept_counts);
+
+/* Pairwise IoU of integer boxes, float(intersect)/union as an IEEE double (bbox_iou, :183-194);
+ * union == 0 -> NaN.  a, b: [n][4] int32, out[n]. */
+int fvy_bbox_iou(fvy_handle* h, const int32_t* a, const int32_t* b, int n, double* out);
+
+/* Post-processing of resident (or given) logits into detections.
+ *   yolo3: decode -> correct_yolo_boxes -> do_nms -> boxes with a surviving class score, candidate order.
+ *   fd6:   FaceDetector.detect after predict (face_detection.py:900-947): sigmoid, threshold, box math,
+ *          do_nms_v2, score > 0, ascending by score, first num_cands.
+ *   dets [batch][max_out], det_counts [batch]. */
+int fvy_postprocess(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch,
+                    const fvy_post_params* pp, const int* image_hw, int max_out, fvy_det* dets, int32_t* det_counts);
+
+/* forward + postprocess in one call (yolov3_detect._main_ :593-604 / FaceDetector.detect :899-947). */
+int fvy_detect(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp, const int* image_hw,
+               int max_out, fvy_det* dets, int32_t* det_counts);
+
+/* Introspection for tests / bench: */
+int fvy_num_layers(const fvy_handle* h);
+/* info[0..11] = idx, cin, cout, k, stride, H_out, W_out, tile_n, tile_k, stages, grid, num_tiles */
+int fvy_layer_info(const fvy_handle* h, int layer, int* info12);
+/* Copies layer `layer`'s stored output for `batch` images into dst as dense NHWC float32 (debug / layer-wise parity). */
+int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host);
+/* Kernels launched by this handle since creation (bench.py reports gpu_launches from it). */
+long long fvy_launch_count(const fvy_handle* h);
+/* Device-time of the last fvy_forward / fvy_postprocess call in ms (CUDA events on the handle's stream). */
+int fvy_last_timing(const fvy_handle* h, float* forward_ms, float* post_ms);
+/* Per-layer device time of one forward (synchronises between layers; profiling aid). ms[num_layers]. */
+int fvy_profile_layers(fvy_handle* h, int batch, int iters, float* ms);
+/* Blocks until all work queued on the handle's stream is done. */
+int fvy_sync(fvy_handle* h);
+/* Async variants for pipelined serving: enqueue only; results valid after fvy_sync. Host buffers must be pinned. */
+int fvy_detect_async(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp,
+                     const int* image_hw, int max_out, fvy_det* dets, int32_t* det_counts);
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+void* fvy_host_alloc(size_t bytes);
+void fvy_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVY_H_ */
