@@ -40,7 +40,7 @@ class FvyPostParams(C.Structure):
 # every symbol include/fvy.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_load_weights", "fvy_weight_count", "fvy_forward",
            "fvy_decode", "fvy_correct_boxes", "fvy_nms", "fvy_bbox_iou", "fvy_postprocess", "fvy_detect", "fvy_num_layers",
-           "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_sync",
+           "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
            "fvy_detect_async", "fvy_host_alloc", "fvy_host_free"]
 
 _lib = None
@@ -83,6 +83,9 @@ def load():
     L.fvy_launch_count.restype = C.c_longlong; L.fvy_launch_count.argtypes = [H]
     L.fvy_last_timing.restype = C.c_int; L.fvy_last_timing.argtypes = [H, fp, fp]
     L.fvy_profile_layers.restype = C.c_int; L.fvy_profile_layers.argtypes = [H, C.c_int, C.c_int, vp]
+    L.fvy_run_layer.restype = C.c_int; L.fvy_run_layer.argtypes = [H, C.c_int, C.c_int, C.c_int, fp]
+    L.fvy_timer_start.restype = C.c_int; L.fvy_timer_start.argtypes = [H]
+    L.fvy_timer_stop.restype = C.c_int; L.fvy_timer_stop.argtypes = [H, fp]
     L.fvy_sync.restype = C.c_int; L.fvy_sync.argtypes = [H]
     L.fvy_host_alloc.restype = C.c_void_p; L.fvy_host_alloc.argtypes = [C.c_size_t]
     L.fvy_host_free.restype = None; L.fvy_host_free.argtypes = [C.c_void_p]

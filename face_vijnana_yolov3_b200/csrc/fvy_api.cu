@@ -152,7 +152,7 @@ struct fvy_handle {
     fvy_config cfg;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<Layer> layers;
     std::vector<void*> allocs;
     bool weights_loaded = false;
@@ -944,6 +944,38 @@ int fvy_profile_layers(fvy_handle* h, int batch, int iters, float* ms) {
         CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
         ms[i] = t / iters;
     }
+    return FVY_OK;
+}
+
+int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
+    if (!h || !ms) return fail(FVY_E_INVALID, "NULL argument");
+    if (!h->weights_loaded) return fail(FVY_E_STATE, "weights not loaded");
+    if (layer < 0 || layer >= (int)h->layers.size() || batch < 1 || batch > h->cfg.max_batch || iters < 1) return fail(FVY_E_INVALID, "bad layer/batch/iters");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int e = run_layers(h, batch, layer, layer + 1)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    for (int it = 0; it < iters; ++it)
+        if (int e = run_layers(h, batch, layer, layer + 1)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+    *ms = t / iters;
+    return FVY_OK;
+}
+
+int fvy_timer_start(fvy_handle* h) {
+    if (!h) return fail(FVY_E_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+    return FVY_OK;
+}
+int fvy_timer_stop(fvy_handle* h, float* ms) {
+    if (!h || !ms) return fail(FVY_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->ev[4], h->ev[5]));
     return FVY_OK;
 }
 

@@ -203,6 +203,14 @@ class Engine:
         self._keep = (images, hw, dets, counts, pp)   # keep buffers alive for async use
         return dets, counts
 
+    def timer_start(self):
+        L.check(self.lib.fvy_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        L.check(self.lib.fvy_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def sync(self):
         L.check(self.lib.fvy_sync(self._h))
 
@@ -236,6 +244,11 @@ class Engine:
         ms = np.zeros(self.lib.fvy_num_layers(self._h), np.float32)
         L.check(self.lib.fvy_profile_layers(self._h, batch, iters, _ptr(ms)))
         return ms
+
+    def run_layer(self, layer: int, batch: int, iters: int = 3) -> float:
+        ms = C.c_float()
+        L.check(self.lib.fvy_run_layer(self._h, layer, batch, iters, C.byref(ms)))
+        return ms.value
 
     def macs_per_image(self) -> int:
         return arch.macs(arch.table(self.head, self.nb_class), self.net_h, self.net_w)

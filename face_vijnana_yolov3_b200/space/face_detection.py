@@ -1,0 +1,225 @@
+"""Drop-in for the reference's ``src/space/face_detection.py`` FaceDetector, backed by libfvy.so.
+
+    FaceDetector(conf)                      reference :312-382   (conf = face_vijnana_yolov3.json['fd_conf'])
+      .detect(image) -> [BoundBox]          reference :885-949   (predict + decode + do_nms_v2 + select, one GPU call)
+      .detect_batch(images) -> [[BoundBox]] additive: the same per image, batched
+      .evaluate() / .test()                 reference :632-781 / :783-883  (host image loop kept; per-image detect on the GPU)
+      .train()                              reference :602-630   (SURVEY 8 f-1 "next": not built this round)
+    main()                                  reference :951-985
+
+The model is the reference's: Darknet-53 base conv_0..conv_73 (:384-600) + Conv2D(6, 3x3, same, linear)
+(:348-352) -> (B,13,13,6) ``[obj, bx, by, bw, bh, cls]``.  Keras .h5 files cannot be read here (no h5py);
+weights come from a Darknet ``yolov3.weights`` file (backbone) and/or a flat ``face_detector.fvyw`` stream
+(``FaceDetector.save_weights``), else Keras-default random initialisation as in the reference's untrained model.
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import platform
+import time
+
+import numpy as np
+
+from .. import _lib as L
+from .. import arch, synth
+from ..engine import Engine, post_params
+from .yolov3_detect import BoundBox, WeightReader
+
+DEBUG = True
+
+
+class FaceDetector(object):
+    """Face detector to use yolov3 (same constants as the reference, :66-73)."""
+
+    MODEL_PATH = 'face_detector.h5'
+    WEIGHTS_PATH = 'face_detector.fvyw'
+    CELL_SIZE = 13
+
+    def __init__(self, conf, device=0, max_batch=None):
+        self.conf = conf
+        self.raw_data_path = self.conf.get('raw_data_path')
+        self.hps = self.conf['hps']
+        self.nn_arch = self.conf['nn_arch']
+        self.model_loading = self.conf.get('model_loading', False)
+        self.cell_image_size = self.nn_arch['image_size'] // self.CELL_SIZE      # :325
+        if self.nn_arch['image_size'] % 32:
+            raise ValueError("nn_arch.image_size must be a multiple of 32")
+        self.device = device
+        self.max_batch = int(max_batch or 1)
+        self.specs = arch.fd6_table(self.nn_arch['bb_info_c_size'])
+        self._stream = self._initial_stream()
+        self._engine = None
+
+    # ------------------------------------------------------------------ weights
+    def _initial_stream(self) -> np.ndarray:
+        n = arch.n_params(self.specs)
+        if self.model_loading:
+            if os.path.exists(self.WEIGHTS_PATH):
+                s = np.fromfile(self.WEIGHTS_PATH, dtype='<f4')
+                if s.size != n:
+                    raise ValueError(f"{self.WEIGHTS_PATH} holds {s.size} floats, model needs {n}")
+                return s
+            raise FileNotFoundError(f"model_loading is set but {self.WEIGHTS_PATH} does not exist "
+                                    f"({self.MODEL_PATH} is a Keras HDF5 file; h5py is not available in this build)")
+        stream = synth.darknet_stream(self.specs, 0, synth.INIT_KERAS_DEFAULT)   # Keras default init of the untrained model
+        if os.path.exists('yolov3.weights'):                                     # YOLOV3Base, :398-402
+            wr = WeightReader('yolov3.weights')
+            n_base = arch.n_params([c for c in self.specs if c.idx <= 73])
+            stream[:n_base] = wr.read_bytes(n_base)
+        return stream
+
+    def save_weights(self, path=None):
+        np.asarray(self._stream, '<f4').tofile(path or self.WEIGHTS_PATH)
+
+    def set_weight_stream(self, stream):
+        stream = np.ascontiguousarray(stream, np.float32)
+        if stream.size != arch.n_params(self.specs):
+            raise ValueError("wrong weight stream length")
+        self._stream = stream
+        if self._engine is not None:
+            self._engine.load_weights(stream)
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            s = self.nn_arch['image_size']
+            self._engine = Engine(s, s, head=L.HEAD_FD6, max_batch=self.max_batch, device=self.device,
+                                  bb_info_c_size=self.nn_arch['bb_info_c_size'])
+            self._engine.load_weights(self._stream)
+        return self._engine
+
+    def _pp(self):
+        return post_params(obj_thresh=self.hps['face_conf_th'], nms_thresh=self.hps['nms_iou_th'],
+                           num_cands=self.hps['num_cands'], arith=L.ARITH_F64)
+
+    # ------------------------------------------------------------------ detect (:885-949)
+    @staticmethod
+    def _to_boxes(dets, n):
+        out = []
+        for d in dets[:n]:
+            sc = np.float32(d['score'])
+            out.append(BoundBox(np.int64(d['xmin']), np.int64(d['ymin']), np.int64(d['xmax']), np.int64(d['ymax']),
+                                objness=np.float32(d['objness']), classes=[sc]))
+        return out
+
+    def detect(self, image):
+        """image: (1, S, S, 3) float in [0,1] -> face candidate BoundBoxes, ascending score, <= num_cands."""
+        image = np.ascontiguousarray(image)
+        if image.dtype not in (np.float32, np.float64):
+            image = image.astype(np.float64)
+        if image.shape[0] != 1:
+            raise ValueError("detect takes one image (1,S,S,3); use detect_batch for more")
+        dets, counts = self.engine.detect(image, pp=self._pp())
+        return self._to_boxes(dets[0], int(counts[0]))
+
+    def detect_batch(self, images):
+        images = np.ascontiguousarray(images)
+        if images.dtype not in (np.float32, np.float64):
+            images = images.astype(np.float64)
+        if images.shape[0] > self.max_batch:
+            self.max_batch = int(images.shape[0])
+            if self._engine is not None:
+                self._engine.close()
+                self._engine = None
+        dets, counts = self.engine.detect(images, pp=self._pp())
+        return [self._to_boxes(dets[b], int(counts[b])) for b in range(images.shape[0])]
+
+    # ------------------------------------------------------------------ host image loop (:645-735, :788-883)
+    def _letterbox(self, image):
+        import cv2 as cv
+        S = self.nn_arch['image_size']
+        w, h = image.shape[1], image.shape[0]
+        pad_t = pad_b = pad_l = pad_r = 0
+        if w >= h:
+            w_p, h_p = S, int(h / w * S)
+            pad = S - h_p
+            pad_t, pad_b = pad // 2, pad // 2 + (pad % 2)
+            image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC)
+            image = cv.copyMakeBorder(image, pad_t, pad_b, 0, 0, cv.BORDER_CONSTANT, value=[0, 0, 0])
+        else:
+            h_p, w_p = S, int(w / h * S)
+            pad = S - w_p
+            pad_l, pad_r = pad // 2, pad // 2 + (pad % 2)
+            image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC)
+            image = cv.copyMakeBorder(image, 0, 0, pad_l, pad_r, cv.BORDER_CONSTANT, value=[0, 0, 0])
+        return image[np.newaxis, :], (w, h, pad_t, pad_l)
+
+    def _unletterbox(self, boxes, geom):
+        S = self.nn_arch['image_size']
+        w, h, pad_t, pad_l = geom
+        for box in boxes:
+            if w >= h:
+                box.xmin = np.min([box.xmin * w / S, w])
+                box.xmax = np.min([box.xmax * w / S, w])
+                box.ymin = np.min([np.max([box.ymin - pad_t, 0]) * w / S, h])
+                box.ymax = np.min([np.max([box.ymax - pad_t, 0]) * w / S, h])
+            else:
+                box.xmin = np.min([np.max([box.xmin - pad_l, 0]) * h / S, w])
+                box.xmax = np.min([np.max([box.xmax - pad_l, 0]) * h / S, w])
+                box.ymin = np.min([box.ymin * h / S, h])
+                box.ymax = np.min([box.ymax * h / S, h])
+
+    def _run_files(self, draw_dir=None):
+        import cv2 as cv
+        test_path = self.conf['test_path']
+        output_file_path = self.conf['output_file_path']
+        file_names = glob.glob(os.path.join(test_path, '*.jpg'))
+        with open(output_file_path, 'w') as f:
+            for count1, file_name in enumerate(file_names, 1):
+                if DEBUG:
+                    print(count1, '/', len(file_names), file_name)
+                image_o = cv.imread(file_name, cv.IMREAD_COLOR)[:, :, ::-1]   # RGB like skimage.io.imread
+                image, geom = self._letterbox(image_o / 255)
+                boxes = self.detect(image)
+                self._unletterbox(boxes, geom)
+                base = file_name.split('\\')[-1] if platform.system() == 'Windows' else file_name.split('/')[-1]
+                for count, box in enumerate(boxes, 1):
+                    if count > 60:                                                # :729, :870
+                        break
+                    f.write(base + ',' + str(box.xmin) + ',' + str(box.ymin) + ',')
+                    f.write(str(box.xmax - box.xmin) + ',' + str(box.ymax - box.ymin) + ',' + str(box.get_score()) + '\n')
+                if draw_dir is not None and len(boxes) > 0:
+                    canvas = np.ascontiguousarray(image_o[:, :, ::-1])
+                    for box in boxes:
+                        cv.rectangle(canvas, (int(box.xmin), int(box.ymin)), (int(box.xmax), int(box.ymax)), (0, 255, 0), 2)
+                    cv.imwrite(os.path.join(draw_dir, base[:-4] + '_detected.jpg'), canvas)
+
+    def evaluate(self):
+        """Detect on every ``test_path/*.jpg``, write ``output_file_path`` CSV and ``results/*_detected.jpg``."""
+        import shutil
+        res = os.path.join(self.conf['test_path'], 'results')
+        if os.path.isdir(res):
+            shutil.rmtree(res)
+        os.mkdir(res)
+        self._run_files(draw_dir=res)
+
+    def test(self):
+        """Detect on every ``test_path/*.jpg`` and write the ``file,x,y,w,h,score`` CSV (<= 60 rows per file)."""
+        self._run_files(draw_dir=None)
+
+    def train(self):
+        raise NotImplementedError("FaceDetector.train (fit_generator + multi_gpu_model, face_detection.py:602-630) is the "
+                                  "'next' row f-1 of SURVEY section 8 and is not part of this build round")
+
+
+def main():
+    """Same dispatch as the reference (:951-985): reads face_vijnana_yolov3.json['fd_conf']."""
+    name = "face_vijnana_yolov3_win.json" if platform.system() == 'Windows' else "face_vijnana_yolov3.json"
+    with open(name, 'r') as f:
+        conf = json.load(f)['fd_conf']
+    fd = FaceDetector(conf)
+    ts = time.time()
+    if conf['mode'] == 'train':
+        fd.train()
+    elif conf['mode'] == 'evaluate':
+        fd.evaluate()
+    elif conf['mode'] == 'test':
+        fd.test()
+    te = time.time()
+    print('Elasped time: {0:f}s'.format(te - ts))
+
+
+if __name__ == '__main__':
+    main()

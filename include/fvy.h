@@ -156,6 +156,12 @@ long long fvy_launch_count(const fvy_handle* h);
 int fvy_last_timing(const fvy_handle* h, float* forward_ms, float* post_ms);
 /* Per-layer device time of one forward (synchronises between layers; profiling aid). ms[num_layers]. */
 int fvy_profile_layers(fvy_handle* h, int batch, int iters, float* ms);
+/* Runs one conv layer (1 warm-up + iters timed launches) on the activations of the last forward; *ms = mean device time. */
+int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms);
+/* Device stopwatch on the handle's stream (CUDA events): start records an event; stop records another,
+ * synchronises the stream and returns the elapsed milliseconds.  bench.py brackets its K timed steps with it. */
+int fvy_timer_start(fvy_handle* h);
+int fvy_timer_stop(fvy_handle* h, float* ms);
 /* Blocks until all work queued on the handle's stream is done. */
 int fvy_sync(fvy_handle* h);
 /* Async variants for pipelined serving: enqueue only; results valid after fvy_sync. Host buffers must be pinned. */

@@ -1,0 +1,318 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle on
+the same seeded inputs and against the committed reference vectors.
+
+Tolerances
+  * head logits: relative L2 <= 1e-2 vs the fp32 oracle (BASELINE.json north_star, bf16 storage) on the
+    reference's random initialisation (Keras default).  The BN-exercising set is an extra stress: its
+    bf16 EMULATION already sits at ~1.1e-2 on one head, so it is held to 1.5e-2 and, layer by layer,
+    to the emulation.
+  * decode / IoU / NMS: bit-exact (integers, fp32 scores, kept indices and order).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from face_vijnana_yolov3_b200 import _lib as L, arch, synth
+from face_vijnana_yolov3_b200.engine import Engine, post_params
+from oracle import darknet_ref as D, postproc as P
+
+HEAD_TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def yolo_engine():
+    eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=3)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def post_engine():
+    eng = Engine(416, 416, head=L.HEAD_NONE, nb_class=1, max_batch=4)
+    yield eng
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ forward
+def test_forward_heads_match_oracle_keras_default(yolo_engine):
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(2, 416, 416, 0)
+    yolo_engine.load_weights(stream)
+    outs = yolo_engine.forward(x)
+    ref = D.forward(stream, x, 1)
+    assert [o.shape for o in outs] == [(2, 13, 13, 18), (2, 26, 26, 18), (2, 52, 52, 18)]
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) <= HEAD_TOL
+    # batch independence: image 1 alone gives the same logits as image 1 inside the batch of 2
+    single = yolo_engine.forward(x[1:2])
+    for o, s in zip(outs, single):
+        assert np.array_equal(o[1], s[0])
+    # float64 input (the reference feeds image/255. as float64) is cast to float32 first
+    o64 = yolo_engine.forward(x[:1].astype(np.float64))
+    for o, s in zip(outs, o64):
+        assert np.array_equal(o[0], s[0])
+
+
+def test_forward_layerwise_bn_exercising(yolo_engine):
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_BN_EXERCISING)
+    x = synth.images(1, 416, 416, 5)
+    yolo_engine.load_weights(stream)
+    outs = yolo_engine.forward(x)
+    taps = {}
+    emu = D.forward(stream, x, 1, emulate_bf16=True, taps=taps)
+    ref = D.forward(stream, x, 1)
+    for li, info in enumerate(yolo_engine.layer_infos()):
+        got = yolo_engine.layer_output(li, 1)
+        exp = taps[info["idx"]].permute(0, 2, 3, 1).numpy()
+        assert rel_l2(got, exp) <= 2e-2, f"conv_{info['idx']}"
+        if li < 4:                                  # before bf16 rounding noise accumulates the match is ~1e-4
+            assert rel_l2(got, exp) <= 1e-3, f"conv_{info['idx']}"
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) <= 1.5e-2
+
+
+def test_forward_fd6_matches_oracle():
+    specs = arch.fd6_table()
+    stream = synth.darknet_stream(specs, 1, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(2, 416, 416, 2)
+    eng = Engine(416, 416, head=L.HEAD_FD6, max_batch=2)
+    eng.load_weights(stream)
+    out = eng.forward(x)[0]
+    ref = D.forward(stream, x, fd6=True)
+    assert out.shape == (2, 13, 13, 6) and rel_l2(out, ref) <= HEAD_TOL
+    eng.close()
+
+
+def test_forward_608():
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(1, 608, 608, 4)
+    eng = Engine(608, 608, nb_class=1, max_batch=1)
+    eng.load_weights(stream)
+    outs = eng.forward(x)
+    ref = D.forward(stream, x, 1)
+    assert [o.shape for o in outs] == [(1, 19, 19, 18), (1, 38, 38, 18), (1, 76, 76, 18)]
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) <= HEAD_TOL
+    eng.close()
+
+
+def test_forward_requires_weights_and_valid_batch():
+    eng = Engine(416, 416, nb_class=1, max_batch=1)
+    with pytest.raises(L.FvyError):
+        eng.forward(synth.images(1, 416, 416, 0))
+    eng.load_weights(synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT))
+    with pytest.raises(ValueError):
+        eng.forward(synth.images(2, 416, 416, 0))
+    with pytest.raises(ValueError):
+        eng.load_weights(np.zeros(10, np.float32))
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ decode / NMS
+@pytest.mark.parametrize("arith", [L.ARITH_F64, L.ARITH_F32])
+@pytest.mark.parametrize("mask", [L.ANCHOR_MASK_REFERENCE, L.ANCHOR_MASK_ALL])
+def test_decode_bit_exact_vs_oracle(post_engine, arith, mask):
+    outs = synth.head_logits(3, 416, 416, 1, seed=9)
+    hw = np.array([[360, 640], [416, 416], [1000, 750]], np.int32)
+    pp = post_params(0.5, 0.45, anchor_mask=mask, arith=arith)
+    d = post_engine.decode(outs, pp=pp, image_hw=hw)
+    masks = [(mask >> (3 * s)) & 7 for s in range(3)]
+    for b in range(3):
+        o = P.decode_image([t[b] for t in outs], anchor_masks=masks, obj_thresh=0.5, arith=arith)
+        ib = P.correct_yolo_boxes(o["box"], hw[b, 0], hw[b, 1], 416, 416, arith)
+        n = int(d["counts"][b])
+        assert n == len(o["cell"])
+        assert np.array_equal(d["nbox"][b, :n], o["box"])
+        assert np.array_equal(d["ibox"][b, :n], ib)
+        assert np.array_equal(d["objness"][b, :n], o["objness"])
+        assert np.array_equal(d["classes"][b, :n], o["classes"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_post_against_reference_vectors(post_engine, golden_dir, tag):
+    """Vectors produced by the reference's own decode_netout / correct_yolo_boxes / do_nms."""
+    g = np.load(os.path.join(golden_dir, f"post_yolo3_{tag}.npz"))
+    outs = [g["out0"][None], g["out1"][None], g["out2"][None]]
+    pp = post_params(float(g["obj_thresh"]), float(g["nms_thresh"]), arith=L.ARITH_F32)
+    d = post_engine.decode(outs, pp=pp, image_hw=g["image_hw"][None])
+    n = int(d["counts"][0])
+    assert n == g["ibox"].shape[0]
+    assert (d["ibox"][0, :n] != g["ibox"]).mean() <= 1e-3            # NumPy's float32 exp is a few ulp off correctly rounded
+    assert np.abs(d["classes"][0, :n] - g["classes_before"]).max() <= 1e-6
+    # NMS on the REFERENCE's candidates: kept set and order bit-exact
+    S = post_engine.cap
+    ib = np.zeros((1, S, 4), np.int32); ib[0, :n] = g["ibox"]
+    cl = np.zeros((1, S, 1), np.float32); cl[0, :n] = g["classes_before"]
+    out, kept, kc = post_engine.nms(ib, cl, np.array([n], np.int32), float(g["nms_thresh"]))
+    assert np.array_equal(out[0, :n], g["classes_after"])
+    assert np.array_equal(kept[0, :kc[0]], np.nonzero(g["classes_after"][:, 0] > 0)[0])
+
+
+def test_iou_known_answers(post_engine, golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "iou_cases.json")))
+    a = np.array([c["a"] for c in cases], np.int32); b = np.array([c["b"] for c in cases], np.int32)
+    v = post_engine.bbox_iou(a, b)
+    for c, x in zip(cases, v):
+        if c["iou"] is None:
+            assert np.isnan(x)
+        else:
+            assert x == c["iou"]
+
+
+def test_nms_stress_crowd_10k():
+    """BASELINE config 5: ~10k candidates per image, all 9 anchors, crowd boxes, nms 0.5."""
+    B = 2
+    outs = synth.head_logits(B, 416, 416, 1, seed=4, crowd=True, obj_bias=6.0)
+    eng = Engine(416, 416, head=L.HEAD_NONE, nb_class=1, max_batch=B)
+    pp = post_params(0.5, 0.5, anchor_mask=L.ANCHOR_MASK_ALL, num_cands=60)
+    hw = np.array([[416, 416]] * B, np.int32)
+    d = eng.decode(outs, pp=pp, image_hw=hw, want_nbox=False)
+    assert d["counts"].min() > 10000
+    dets, counts = eng.postprocess(outs, pp=pp, image_hw=hw, max_out=eng.cap)
+    for b in range(B):
+        n = int(d["counts"][b])
+        cls = P.do_nms(d["ibox"][b, :n], d["classes"][b, :n], 0.5)
+        keep = np.nonzero(cls[:, 0] > 0)[0][:60]
+        assert int(counts[b]) == len(keep)
+        got = dets[b, :len(keep)]
+        assert np.array_equal(got["cand"], d["cand"][b, keep])
+        assert np.array_equal(got["score"], cls[keep, 0])
+    # idempotence: NMS of the survivors removes nothing more
+    cls1, _, _ = eng.nms(d["ibox"], d["classes"], d["counts"], 0.5, want_kept=False)
+    cls2, _, _ = eng.nms(d["ibox"], cls1, d["counts"], 0.5, want_kept=False)
+    assert np.array_equal(cls1, cls2)
+    eng.close()
+
+
+def test_nms_edge_cases(post_engine):
+    S = post_engine.cap
+    ib = np.zeros((3, S, 4), np.int32); cl = np.zeros((3, S, 1), np.float32)
+    # image 0: empty; image 1: identical boxes + a zero-score box + zero-area boxes (union 0 -> nan -> kept);
+    # image 2: chain a>b>c where a suppresses b but b (suppressed) must not suppress c
+    ib[1, :5] = [[0, 0, 10, 10], [0, 0, 10, 10], [0, 0, 10, 10], [5, 5, 5, 5], [5, 5, 5, 5]]
+    cl[1, :5, 0] = [0.5, 0.9, 0.0, 0.3, 0.2]
+    ib[2, :3] = [[0, 0, 10, 10], [4, 0, 14, 10], [8, 0, 18, 10]]
+    cl[2, :3, 0] = [0.9, 0.8, 0.7]
+    counts = np.array([0, 5, 3], np.int32)
+    out, kept, kc = post_engine.nms(ib, cl, counts, 0.4)
+    ref1 = P.do_nms(ib[1, :5], cl[1, :5], 0.4); ref2 = P.do_nms(ib[2, :3], cl[2, :3], 0.4)
+    assert kc[0] == 0
+    assert np.array_equal(out[1, :5], ref1) and list(out[1, :5, 0]) == [0.0, np.float32(0.9), 0.0, np.float32(0.3), np.float32(0.2)]
+    assert np.array_equal(out[2, :3], ref2) and list(kept[2, :kc[2]]) == [0, 2]
+    # ties: (score desc, index asc) is the framework's documented rule
+    ib[1, :2] = [[0, 0, 10, 10], [1, 0, 11, 10]]; cl[1, :2, 0] = [0.5, 0.5]
+    out, kept, kc = post_engine.nms(ib, cl, np.array([0, 2, 0], np.int32), 0.4)
+    assert list(out[1, :2, 0]) == [np.float32(0.5), 0.0]
+
+
+def test_multiclass_nms():
+    eng = Engine(416, 416, head=L.HEAD_NONE, nb_class=3, max_batch=1)
+    rng = np.random.default_rng(0)
+    n = 300
+    xy = rng.integers(0, 300, (n, 2)); wh = rng.integers(10, 120, (n, 2))
+    ibx = np.concatenate([xy, xy + wh], 1).astype(np.int32)
+    cls = rng.random((n, 3)).astype(np.float32)
+    S = eng.cap
+    ib = np.zeros((1, S, 4), np.int32); ib[0, :n] = ibx
+    cl = np.zeros((1, S, 3), np.float32); cl[0, :n] = cls
+    out, kept, kc = eng.nms(ib, cl, np.array([n], np.int32), 0.45)
+    ref = P.do_nms(ibx, cls, 0.45)
+    assert np.array_equal(out[0, :n], ref)
+    assert np.array_equal(kept[0, :kc[0]], np.nonzero((ref > 0).any(1))[0])
+    eng.close()
+
+
+def test_fd6_detect_against_reference_vectors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "post_fd6.npz"))
+    hps = json.loads(str(g["hps"]))
+    eng = Engine(416, 416, head=L.HEAD_FD6, max_batch=4)
+    for k in range(4):
+        pp = post_params(hps[k]["face_conf_th"], hps[k]["nms_iou_th"], num_cands=hps[k]["num_cands"], arith=L.ARITH_F64)
+        dets, counts = eng.postprocess([g["maps"][k][None]], pp=pp, max_out=169)
+        n = int(counts[0])
+        got = dets[0, :n]
+        assert np.array_equal(np.stack([got["xmin"], got["ymin"], got["xmax"], got["ymax"]], 1), g[f"ibox{k}"]), k
+        assert np.abs(got["score"] - g[f"score{k}"]).max() <= 1e-6
+        ib, sc, cell = P.fd6_detect(g["maps"][k], 416, hps[k]["face_conf_th"], hps[k]["nms_iou_th"], hps[k]["num_cands"])
+        assert np.array_equal(got["score"], sc) and np.array_equal(got["cand"], cell)      # bit-exact vs the oracle
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ whole path + drop-ins
+def test_detect_end_to_end_matches_oracle_on_gpu_logits(yolo_engine):
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(3, 416, 416, 7)
+    yolo_engine.load_weights(stream)
+    hw = np.array([[416, 416], [300, 400], [720, 1280]], np.int32)
+    pp = post_params(0.5, 0.45)
+    dets, counts = yolo_engine.detect(x, pp=pp, image_hw=hw)
+    outs = yolo_engine.forward(x)
+    for b in range(3):
+        d = P.decode_image([o[b] for o in outs], obj_thresh=0.5)
+        ib = P.correct_yolo_boxes(d["box"], hw[b, 0], hw[b, 1], 416, 416)
+        cls = P.do_nms(ib, d["classes"], 0.45)
+        keep = np.nonzero(cls[:, 0] > 0)[0]
+        n = int(counts[b])
+        assert n == len(keep)
+        got = dets[b, :n]
+        assert np.array_equal(np.stack([got["xmin"], got["ymin"], got["xmax"], got["ymax"]], 1), ib[keep])
+        assert np.array_equal(got["score"], cls[keep, 0]) and np.array_equal(got["objness"], d["objness"][keep])
+
+
+def test_dropin_functions_and_facedetector():
+    from face_vijnana_yolov3_b200.space import yolov3_detect as yd
+    from face_vijnana_yolov3_b200.space.face_detection import FaceDetector
+    outs = synth.head_logits(1, 416, 416, 1, seed=12)
+    anchors = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]
+    boxes = []
+    for i in range(3):
+        boxes += yd.decode_netout(outs[i][0], anchors[i], i, 0.5, 416, 416)
+    d = P.decode_image([o[0] for o in outs])
+    assert len(boxes) == len(d["cell"]) and isinstance(boxes[0].xmin, np.float64)
+    assert np.array_equal(np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes]), d["box"])
+    yd.correct_yolo_boxes(boxes, 360, 640, 416, 416)
+    ib = P.correct_yolo_boxes(d["box"], 360, 640, 416, 416)
+    assert all(isinstance(b.xmin, int) for b in boxes[:5])
+    assert np.array_equal(np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes]), ib)
+    yd.do_nms(boxes, 0.45)
+    cls = P.do_nms(ib, d["classes"], 0.45)
+    assert np.array_equal(np.array([b.classes[0] for b in boxes], np.float32), cls[:, 0])
+    assert yd.bbox_iou(yd.BoundBox(0, 0, 10, 10), yd.BoundBox(5, 5, 15, 15)) == 25 / 175
+    with pytest.raises(ZeroDivisionError):
+        yd.bbox_iou(yd.BoundBox(1, 1, 1, 1), yd.BoundBox(5, 5, 5, 5))
+    # make_yolov3_model().predict on a small input, 255-channel heads like the reference
+    m = yd.make_yolov3_model()
+    y = m.predict(synth.images(1, 64, 64, 0))
+    assert [t.shape for t in y] == [(1, 2, 2, 255), (1, 4, 4, 255), (1, 8, 8, 255)]
+    # FaceDetector.detect: ascending scores, <= num_cands, equals the oracle on the same 13x13x6 map
+    conf = {"mode": "test", "raw_data_path": "", "test_path": "", "output_file_path": "", "multi_gpu": False, "num_gpus": 1,
+            "yolov3_base_model_load": False, "hps": {"face_conf_th": 0.2, "nms_iou_th": 0.5, "num_cands": 60},
+            "nn_arch": {"image_size": 416, "bb_info_c_size": 6}, "model_loading": False}
+    fd = FaceDetector(conf)
+    stream = synth.darknet_stream(arch.fd6_table(), 3, synth.INIT_BN_EXERCISING)
+    fd.set_weight_stream(stream)
+    img = synth.images(1, 416, 416, 8).astype(np.float64)
+    boxes = fd.detect(img)
+    raw = fd.engine.forward(img)[0]
+    ib, sc, cell = P.fd6_detect(raw[0], 416, 0.2, 0.5, 60)
+    assert len(boxes) == len(sc) <= 60
+    assert np.array_equal(np.array([b.classes[0] for b in boxes], np.float32), sc)
+    assert all(boxes[i].get_score() <= boxes[i + 1].get_score() for i in range(len(boxes) - 1))
+    assert isinstance(boxes[0].xmin, np.int64) if boxes else True
+
+
+def test_capacity_error():
+    eng = Engine(416, 416, head=L.HEAD_NONE, nb_class=1, max_batch=1, max_cands=100)
+    outs = synth.head_logits(1, 416, 416, 1, seed=1)
+    with pytest.raises(L.FvyError):
+        eng.decode(outs, pp=post_params(0.5, 0.45), image_hw=np.array([[416, 416]], np.int32))
+    eng.close()

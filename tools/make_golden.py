@@ -1,0 +1,129 @@
+"""Generate tests/golden/* by running the REAL reference in the build container.
+
+/root/reference does not exist on the GPU box, so the outputs of its own functions are committed
+as small fixtures (this script is their provenance):
+
+  darknet53_summary.json  conv/bnorm/add rows of the Keras summary() dump the reference ships in
+                          analysis/face_recog_analysis.ipynb:1431-1868 (+ the param totals).
+  post_yolo3_*.npz        reference decode_netout -> correct_yolo_boxes -> do_nms on seeded logits
+                          (src/space/yolov3_detect.py:335-444), executed with this container's NumPy
+                          (>= 2, i.e. float32 scalar arithmetic = FVY_ARITH_F32).
+  post_fd6.npz            reference FaceDetector.detect (src/space/face_detection.py:885-949) on seeded
+                          (1,13,13,6) maps through a fake model.predict.
+  iou_cases.json          bbox_iou / _interval_overlap known answers computed by the reference code.
+
+usage: python tools/make_golden.py
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from face_vijnana_yolov3_b200 import synth   # noqa: E402
+from oracle import ref_loader as R            # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+ANCHORS = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]
+
+
+def summary_fixture():
+    path = "/root/reference/analysis/face_recog_analysis.ipynb"
+    lines = open(path).read().split("\n")[1425:1875]
+    rows = []
+    pat = re.compile(r'"(\w+) \((\w+)\)\s+\(None, (\d+), (\d+), (\d+)\)?\s+(\d+)')
+    for ln in lines:
+        m = pat.search(ln)
+        if m and m.group(2) in ("Conv2D", "BatchNormalization", "Add"):
+            rows.append([m.group(1), m.group(2), int(m.group(3)), int(m.group(4)), int(m.group(5)), int(m.group(6))])
+    tot = [int(re.search(r"([\d,]+)", ln.split(":")[1]).group(1).replace(",", "")) for ln in lines if "params:" in ln][:3]
+    json.dump({"source": "analysis/face_recog_analysis.ipynb:1431-1868", "rows": rows, "total": tot[0], "trainable": tot[1],
+               "non_trainable": tot[2]}, open(os.path.join(OUT, "darknet53_summary.json"), "w"))
+    print("summary rows", len(rows), tot)
+
+
+def post_yolo3(tag, seed, image_hw, obj_thresh, nms_thresh, nb_class=1, all_anchors=False):
+    Y = R.load_yolov3_detect()
+    outs = synth.head_logits(1, 416, 416, nb_class, seed=seed)
+    boxes = []
+    src = Y.decode_netout
+    for i in range(3):
+        boxes += src(outs[i][0].copy(), ANCHORS[i], i, obj_thresh, 416, 416)
+    nbox = np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes], np.float64)
+    objn = np.array([b.objness for b in boxes], np.float32)
+    cls0 = np.array([np.array(b.classes, np.float32) for b in boxes], np.float32).reshape(len(boxes), nb_class)
+    Y.correct_yolo_boxes(boxes, image_hw[0], image_hw[1], 416, 416)
+    ibox = np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes], np.int64)
+    Y.do_nms(boxes, nms_thresh)
+    cls1 = np.array([np.array(b.classes, np.float32) for b in boxes], np.float32).reshape(len(boxes), nb_class)
+    np.savez_compressed(os.path.join(OUT, f"post_yolo3_{tag}.npz"), out0=outs[0][0], out1=outs[1][0], out2=outs[2][0],
+                        nbox=nbox, objness=objn, classes_before=cls0, ibox=ibox, classes_after=cls1,
+                        image_hw=np.array(image_hw, np.int32), obj_thresh=obj_thresh, nms_thresh=nms_thresh,
+                        numpy_version=np.__version__)
+    print(tag, "cands", len(boxes), "kept", int((cls1 > 0).any(1).sum()))
+
+
+def post_fd6():
+    rng = np.random.default_rng(11)
+    maps, res = [], []
+    hps = {"face_conf_th": 0.5, "nms_iou_th": 0.5, "num_cands": 60}
+    for k in range(4):
+        m = rng.standard_normal((1, 13, 13, 6)).astype(np.float32)
+        m[..., 0] += 1.5; m[..., 5] += 1.5
+        m[..., 1:3] = rng.uniform(-0.2, 1.2, m[..., 1:3].shape)
+        m[..., 3:5] = rng.uniform(-0.05, 0.5, m[..., 3:5].shape) * (1 + 2 * (k % 2))
+        if k == 3:
+            hps = {"face_conf_th": 0.3, "nms_iou_th": 0.3, "num_cands": 10}
+        fd = R.make_ref_face_detector(hps, 416, predict_fn=lambda image, m=m: m.copy())
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            boxes = fd.detect(np.zeros((1, 416, 416, 3)))
+        r = np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes], np.int64).reshape(-1, 4)
+        sc = np.array([b.classes[0] for b in boxes], np.float32)
+        ob = np.array([b.objness for b in boxes], np.float32)
+        maps.append(m[0]); res.append((r, sc, ob, dict(hps)))
+        print("fd6 case", k, "returned", len(boxes))
+    np.savez_compressed(os.path.join(OUT, "post_fd6.npz"), maps=np.stack(maps),
+                        **{f"ibox{k}": res[k][0] for k in range(4)}, **{f"score{k}": res[k][1] for k in range(4)},
+                        **{f"obj{k}": res[k][2] for k in range(4)},
+                        hps=json.dumps([res[k][3] for k in range(4)]))
+
+
+def iou_cases():
+    Y = R.load_yolov3_detect()
+    rng = np.random.default_rng(5)
+    cases = [[0, 0, 10, 10, 5, 5, 15, 15], [0, 0, 10, 10, 10, 10, 20, 20], [0, 0, 10, 10, 0, 0, 10, 10], [0, 0, 10, 10, 2, 2, 4, 4],
+             [-5, -5, 5, 5, 0, 0, 3, 30], [0, 0, 1, 1, 5, 5, 6, 6], [3, 3, 3, 9, 3, 3, 8, 9], [100, 50, 300, 90, 90, 60, 110, 70]]
+    for _ in range(56):
+        a = rng.integers(-50, 400, 4); b = rng.integers(-50, 400, 4)
+        cases.append([int(min(a[0], a[2])), int(min(a[1], a[3])), int(max(a[0], a[2])), int(max(a[1], a[3])),
+                      int(min(b[0], b[2])), int(min(b[1], b[3])), int(max(b[0], b[2])), int(max(b[1], b[3]))])
+    out = []
+    for c in cases:
+        b1, b2 = Y.BoundBox(*c[:4]), Y.BoundBox(*c[4:])
+        try:
+            v = Y.bbox_iou(b1, b2)
+        except ZeroDivisionError:
+            v = None
+        out.append({"a": c[:4], "b": c[4:], "iou": v,
+                    "ow": int(Y._interval_overlap([c[0], c[2]], [c[4], c[6]])), "oh": int(Y._interval_overlap([c[1], c[3]], [c[5], c[7]]))})
+    json.dump(out, open(os.path.join(OUT, "iou_cases.json"), "w"))
+    print("iou cases", len(out))
+
+
+if __name__ == "__main__":
+    if not R.available():
+        raise SystemExit("/root/reference is not available: golden fixtures can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    summary_fixture()
+    post_yolo3("a", seed=21, image_hw=(416, 416), obj_thresh=0.5, nms_thresh=0.45)
+    post_yolo3("b", seed=22, image_hw=(360, 640), obj_thresh=0.6, nms_thresh=0.5)
+    post_yolo3("c", seed=23, image_hw=(500, 375), obj_thresh=0.5, nms_thresh=0.3)
+    post_fd6()
+    iou_cases()
