@@ -21,6 +21,18 @@
 // Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
 // MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
 // Persistent: grid = min(#tiles, #SMs * occupancy); tiles are strided by gridDim.x.
+//
+// Epilogue data path: the accumulator is drained in chunks of 32 channels.  Each chunk is staged in a
+// ring of 8 KB shared-memory buffers laid out exactly as TMA's 64-byte swizzle expects, so that
+//   * the residual chunk arrives by TMA (prefetched `lead` chunks ahead) into the buffer the output
+//     chunk will be written to (in place: each thread reads and rewrites its own 64-byte row),
+//   * stride-1 layers store the chunk with one TMA store per output (rows of the compute domain ARE
+//     rows of the padded output; halo rows are stored as zeros which keeps the padding invariant),
+//   * the other output forms (4-phase, stride-2 remap, 2x up-sample) are written from the staged chunk
+//     with 4 threads per 64-byte row (8 rows per warp instruction instead of 32 scattered 16-byte pieces).
+// Kernels are chained with programmatic dependent launch: the prologue (barrier init, TMEM alloc,
+// tensor-map prefetch) overlaps the previous layer's tail; griddepcontrol.wait precedes the first
+// dependent global access.
 #pragma once
 
 #include <cuda.h>
@@ -46,6 +58,7 @@ struct OutDesc {
     int choff;    // first destination channel
     int nmax;     // batch capacity of the buffer (phase stride)
     int c_real;   // valid channels (heads: 18 / 255 / 6); others: >= BLOCK_N * num_n_tiles
+    int tma;      // 1: stored with TMA (tmap_out[o]); rows of the compute domain coincide with rows of this buffer
 };
 
 struct ConvParams {
@@ -63,6 +76,8 @@ struct ConvParams {
     const float* bias;   // [num_n_tiles * BLOCK_N] fp32
     const __nv_bfloat16* res;   // padded geometry at (H, W), or nullptr
     int res_pitch, res_choff;
+    int nb;              // staging buffers in the epilogue ring (3..8)
+    int lead;            // residual prefetch distance in chunks, 2 <= lead <= nb-1
     OutDesc out[2];
 };
 
@@ -122,6 +137,31 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+
+// smem (swizzled staging chunk) -> global, bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most n of this thread's bulk groups still have to READ their shared-memory source
+__device__ __forceinline__ void bulk_wait_read(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// programmatic dependent launch
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -192,15 +232,25 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 // ----------------------------------------------------------------------------------------------
 constexpr int kBlockM = 128;
 constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
 constexpr int kMaxStages = 8;
+constexpr int kMaxRing = 8;
+constexpr int kChunkBytes = kBlockM * 32 * 2;      // one staged chunk: 128 rows x 32 bf16 = 8 KB
+constexpr int kMaxCout = 1024;
+
+// Shared-memory carve-up (offsets from a 1024-byte aligned base)
+constexpr int kSmemBarriers = 0;                    // full[8] empty[8] tmem_full[2] tmem_empty[2] res_full[8] tmem_ptr
+constexpr int kSmemBias = 1024;                     // kMaxCout floats
+constexpr int kSmemRowIdx = kSmemBias + kMaxCout * 4;        // int rowidx[2 accumulator stages][2 outputs][128]
+constexpr int kSmemRing = kSmemRowIdx + 2 * 2 * kBlockM * 4; // = 7168, 1024-aligned
+static_assert(kSmemRing % 1024 == 0, "staging ring must keep the 512-byte swizzle phase");
 
 template <int BN, int BK>
 struct SmemLayout {
     static constexpr int a_bytes = kBlockM * BK * 2;
     static constexpr int b_bytes = BN * BK * 2;
     static constexpr int stage_bytes = a_bytes + b_bytes;
-    static constexpr int barrier_bytes = 1024;   // full/empty/tmem barriers + tmem ptr, keeps tiles 1024-aligned
-    static constexpr int bytes(int stages) { return barrier_bytes + stages * stage_bytes + 1024 /* alignment slack */; }
+    static constexpr size_t bytes(int stages, int nb) { return 1024 /* alignment slack */ + kSmemRing + (size_t)nb * kChunkBytes + (size_t)stages * stage_bytes; }
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -211,19 +261,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ ConvParams p, const int num_stages) {
+                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out0,
+                  const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ ConvParams p, const int num_stages) {
     using L = SmemLayout<BN, BK>;
     constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages; BN in {32,64,128,256}
     constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN);
+    constexpr int kChunks = BN / 32;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]
-    uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
-    uint64_t* tmem_full = empty_bar + kMaxStages;                        // [2]
-    uint64_t* tmem_empty = tmem_full + 2;                                // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    uint8_t* tiles = smem + L::barrier_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBarriers);   // [kMaxStages]
+    uint64_t* empty_bar = full_bar + kMaxStages;                               // [kMaxStages]
+    uint64_t* tmem_full = empty_bar + kMaxStages;                              // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                                      // [2]
+    uint64_t* res_full = tmem_empty + 2;                                       // [kMaxRing]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + kMaxRing);
+    float* sbias = reinterpret_cast<float*>(smem + kSmemBias);
+    int* srow = reinterpret_cast<int*>(smem + kSmemRowIdx);
+    uint8_t* ring = smem + kSmemRing;
+    uint8_t* tiles = ring + p.nb * kChunkBytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -233,8 +289,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (p.res != nullptr) tma_prefetch_desc(&tmap_res);
+        if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
+        if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
         for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < kMaxRing; ++s) mbar_init(&res_full[s], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -245,6 +305,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Everything above touched no memory written by the previous layer; from here on we do.
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -295,12 +358,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..5, 128 threads) =====================
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;               // row of the tile handled by this thread
+        const int r = q * 32 + lane;               // row of the tile handled by this thread (TMEM lane)
+        const int et = threadIdx.x - 64;           // 0..127
+        const bool issuer = et == 0;
+        const bool has_res = p.res != nullptr;
+        const bool any_tma = p.out[0].tma || p.out[1].tma;
+        const int nb = p.nb, lead = p.lead;
+        const uint32_t swz = (uint32_t)((r >> 1) & 3);          // 64-byte swizzle: 16-byte slot j of row r lives at slot j ^ swz
+        for (int i = et; i < p.num_n_tiles * BN; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
+        named_bar_sync(1, kEpiThreads);
+
+        // residual prefetch cursor (issuer only): runs `lead` chunks ahead of consumption
+        int pf_tile = blockIdx.x, pf_chunk = 0;
+        uint32_t pf_count = 0;
+        auto prefetch_res = [&]() {
+            if (pf_tile >= num_tiles) return;
+            const int buf = pf_count % nb;
+            mbar_expect_tx(&res_full[buf], kChunkBytes);
+            tma_load_2d(ring + buf * kChunkBytes, &tmap_res, &res_full[buf],
+                        p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kBlockM);
+            ++pf_count;
+            if (++pf_chunk == kChunks) { pf_chunk = 0; pf_tile += gridDim.x; }
+        };
+        if (has_res && issuer)
+            for (int i = 0; i < lead; ++i) prefetch_res();
+
+        uint32_t cg = 0;                           // chunks consumed so far by this CTA
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m = (tile / p.num_n_tiles) * kBlockM + r;
+            const int m0 = (tile / p.num_n_tiles) * kBlockM;
+            const int m = m0 + r;
             const int n0 = (tile % p.num_n_tiles) * BN;
             // decode the pixel and decide whether the row is a real output
             bool valid = m < p.m_total;
@@ -313,92 +402,113 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 w = rem - y * p.dom_w - p.dom_off;
                 valid = (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
             }
-            const __nv_bfloat16* res_row = nullptr;
-            if (valid && p.res != nullptr) {
-                const long long rr = ((long long)img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
-                res_row = p.res + rr * p.res_pitch + p.res_choff + n0;
+            // destination row of this pixel for the outputs that are not stored by TMA
+            int* myrow = srow + as * 2 * kBlockM;
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const OutDesc& od = p.out[o];
+                int ridx = -1;
+                if (valid) {
+                    if (od.kind == OUT_PADDED) ridx = (img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
+                    else if (od.kind == OUT_PHASE) {
+                        const int hp = h + 1, wp = w + 1;
+                        const int pw = (p.W >> 1) + 1, plane = ((p.H >> 1) + 1) * pw;
+                        ridx = ((((hp & 1) << 1) | (wp & 1)) * od.nmax + img) * plane + (hp >> 1) * pw + (wp >> 1);
+                    } else if (od.kind == OUT_UP2_PADDED) ridx = (img * (2 * p.H + 2) + (2 * h + 1)) * (2 * p.W + 2) + (2 * w + 1);
+                }
+                myrow[o * kBlockM + r] = ridx;
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c = 0; c < kChunks; ++c, ++cg) {
+                const int c0 = c * 32;
+                const int buf = cg % nb;
+                uint8_t* sbuf = ring + buf * kChunkBytes;
+                uint4* myslot = reinterpret_cast<uint4*>(sbuf + r * 64);
                 uint32_t acc[32];
                 tmem_ld_32x32(taddr + c0, acc);
                 tmem_ld_wait();
-                if (valid) {
-                    float v[32];
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+                float v[32];
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + n0 + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 b = __ldg(b4 + j);
+                        const float4 b = b4[j];
                         v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
                         v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
                         v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
                         v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
                     }
-                    if (p.leaky) {
+                }
+                if (p.leaky) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
-                    }
-                    if (res_row != nullptr) {
-                        const uint4* r4 = reinterpret_cast<const uint4*>(res_row + c0);
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                }
+                if (has_res) {
+                    mbar_wait(&res_full[buf], (cg / nb) & 1);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 t = __ldg(r4 + j);
-                            const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 t = myslot[j ^ swz];
+                        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                v[8 * j + 2 * e + 0] += __uint_as_float(u[e] << 16);
-                                v[8 * j + 2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u);
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            v[8 * j + 2 * e + 0] += __uint_as_float(u[e] << 16);
+                            v[8 * j + 2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u);
                         }
                     }
+                }
+                // fp32 head logits go straight from registers (18 / 255 / 6 valid channels)
 #pragma unroll
-                    for (int o = 0; o < 2; ++o) {
-                        const OutDesc& od = p.out[o];
-                        if (od.kind == OUT_NONE) continue;
-                        if (od.kind == OUT_HEAD_F32) {
-                            float* dst = reinterpret_cast<float*>(od.ptr) + (((long long)img * p.H + h) * p.W + w) * od.c_real;
+                for (int o = 0; o < 2; ++o) {
+                    const OutDesc& od = p.out[o];
+                    if (od.kind == OUT_HEAD_F32 && valid) {
+                        float* dst = reinterpret_cast<float*>(od.ptr) + (((long long)img * p.H + h) * p.W + w) * od.c_real;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (n0 + c0 + j < od.c_real) dst[n0 + c0 + j] = v[j];
-                            continue;
-                        }
-                        uint4 pk[4];
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c0 + j < od.c_real) dst[n0 + c0 + j] = v[j];
+                    }
+                }
+                // stage the bf16 chunk (halo / out-of-image rows as zeros: they ARE the padding of the next layer)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            pk[j].x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            pk[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            pk[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            pk[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        }
-                        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(od.ptr) + od.choff + n0 + c0;
-                        if (od.kind == OUT_PADDED) {
-                            const long long row = ((long long)img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
-                            uint4* d = reinterpret_cast<uint4*>(base + row * od.pitch);
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    pk.x = valid ? pack_bf16x2(v[8 * j + 0], v[8 * j + 1]) : 0u;
+                    pk.y = valid ? pack_bf16x2(v[8 * j + 2], v[8 * j + 3]) : 0u;
+                    pk.z = valid ? pack_bf16x2(v[8 * j + 4], v[8 * j + 5]) : 0u;
+                    pk.w = valid ? pack_bf16x2(v[8 * j + 6], v[8 * j + 7]) : 0u;
+                    myslot[j ^ swz] = pk;
+                }
+                fence_proxy_async();                       // generic-proxy smem writes -> visible to TMA
+                named_bar_sync(1, kEpiThreads);
+                if (issuer) {
+                    if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + c0, m0);
+                    if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + c0, m0);
+                    if (any_tma) bulk_commit();
+                    if (any_tma) bulk_wait_read(nb - lead);   // the buffer of chunk cg + lead - nb has been read
+                    if (has_res) prefetch_res();              // ... so the residual of chunk cg + lead may land in it
+                }
+                // remaining output forms: 4 threads per 64-byte row, 32 rows per pass
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) d[j] = pk[j];
-                        } else if (od.kind == OUT_PHASE) {
-                            const int hp = h + 1, wp = w + 1;
-                            const int ph = ((hp & 1) << 1) | (wp & 1);
-                            const int pw = (p.W >> 1) + 1;
-                            const long long plane = (long long)((p.H >> 1) + 1) * pw;
-                            const long long row = ((long long)ph * od.nmax + img) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
-                            uint4* d = reinterpret_cast<uint4*>(base + row * od.pitch);
+                for (int o = 0; o < 2; ++o) {
+                    const OutDesc& od = p.out[o];
+                    if (od.kind == OUT_NONE || od.kind == OUT_HEAD_F32 || od.tma) continue;
+                    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(od.ptr) + od.choff + n0 + c0 + (et & 3) * 8;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) d[j] = pk[j];
-                        } else {   // OUT_UP2_PADDED
+                    for (int pass = 0; pass < 4; ++pass) {
+                        const int row = pass * 32 + (et >> 2);
+                        const int ridx = myrow[o * kBlockM + row];
+                        if (ridx < 0) continue;
+                        const uint4 t = *reinterpret_cast<const uint4*>(sbuf + row * 64 + (((et & 3) ^ ((row >> 1) & 3)) << 4));
+                        if (od.kind == OUT_UP2_PADDED) {
                             const int W2 = 2 * p.W + 2;
-                            const long long row0 = ((long long)img * (2 * p.H + 2) + (2 * h + 1)) * W2 + (2 * w + 1);
-#pragma unroll
-                            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                                for (int dx = 0; dx < 2; ++dx) {
-                                    uint4* d = reinterpret_cast<uint4*>(base + (row0 + (long long)dy * W2 + dx) * od.pitch);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) d[j] = pk[j];
-                                }
+                            *reinterpret_cast<uint4*>(base + (long long)ridx * od.pitch) = t;
+                            *reinterpret_cast<uint4*>(base + (long long)(ridx + 1) * od.pitch) = t;
+                            *reinterpret_cast<uint4*>(base + (long long)(ridx + W2) * od.pitch) = t;
+                            *reinterpret_cast<uint4*>(base + (long long)(ridx + W2 + 1) * od.pitch) = t;
+                        } else {
+                            *reinterpret_cast<uint4*>(base + (long long)ridx * od.pitch) = t;
                         }
                     }
                 }
@@ -409,6 +519,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (issuer && any_tma) bulk_wait_all();             // smem must outlive the last TMA store
     }
 
     tc_fence_before();

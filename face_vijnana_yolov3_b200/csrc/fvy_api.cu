@@ -134,7 +134,7 @@ struct Layer {
     size_t smem_bytes;
     __nv_bfloat16* w = nullptr;   // [cout_pad][taps * cin_pad]
     float* bias = nullptr;        // [cout_pad]
-    CUtensorMap tmap_a, tmap_b;
+    CUtensorMap tmap_a, tmap_b, tmap_res, tmap_out[2];
     ConvParams p;                 // m_total / num_m_tiles filled per call
     OutDesc primary;              // where fvy_layer_output reads from
     size_t stream_off;            // offset of this layer in the Darknet stream
@@ -156,6 +156,7 @@ struct fvy_handle {
     std::vector<Layer> layers;
     std::vector<void*> allocs;
     bool weights_loaded = false;
+    bool use_pdl = true;
     long long launches = 0;
     long long weight_count = 0;
     // forward
@@ -200,8 +201,14 @@ static uint16_t f32_to_bf16_rn(float f) {
 template <int BN, int BK>
 static int launch_conv_t(fvy_handle* h, Layer& L, int grid) {
     auto kern = conv_igemm_kernel<BN, BK>;   // max dynamic smem was raised in query_occ_t at plan time
-    kern<<<grid, kThreads, L.smem_bytes, h->stream>>>(L.tmap_a, L.tmap_b, L.p, L.stages);
-    CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous layer's tail
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->use_pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.tmap_a, L.tmap_b, L.tmap_res, L.tmap_out[0], L.tmap_out[1], L.p, L.stages));
     ++h->launches;
     return FVY_OK;
 }
@@ -290,7 +297,12 @@ static int build_plan(fvy_handle* h) {
             if (int e = dev_alloc(h, (void**)&h->d_logits[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
             ++nh;
         }
-    const int bn_cap = c.tile_n_max > 0 ? c.tile_n_max : 128;
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    const int bn_cap = c.tile_n_max > 0 ? c.tile_n_max : env_int("FVY_BN", 256);
+    const int bn_res_cap = std::min(bn_cap, env_int("FVY_BN_RES", 256));
+    const int nb_res = env_int("FVY_NB_RES", 6), lead_res = env_int("FVY_LEAD", 4), nb_plain = env_int("FVY_NB", 3);
+    const int stages_cap = env_int("FVY_STAGES", kMaxStages);
+    h->use_pdl = env_int("FVY_PDL", 1) != 0;
     size_t stream_off = 0;
     int head_i = 0;
     for (const ConvSpec& s : specs) {
@@ -306,14 +318,21 @@ static int build_plan(fvy_handle* h) {
         L.BK = (L.cin_pad % 64 == 0) ? 64 : 32;
         if (L.cin_pad % L.BK) return fail(FVY_E_INVALID, "conv_%d: Cin %d not a multiple of %d", s.idx, s.cin, L.BK);
         L.cout_pad = (s.cout + 31) / 32 * 32;
+        if (L.cout_pad > kMaxCout) return fail(FVY_E_INVALID, "conv_%d: Cout %d exceeds %d", s.idx, s.cout, kMaxCout);
+        const bool has_res = s.res >= 0;
+        const int cap_n = has_res ? bn_res_cap : bn_cap;
         L.BN = 32;
         for (int bn : {256, 128, 64, 32})
-            if (bn <= bn_cap && L.cout_pad % bn == 0) { L.BN = bn; break; }
+            if (bn <= cap_n && L.cout_pad % bn == 0) { L.BN = bn; break; }
         L.num_n_tiles = L.cout_pad / L.BN;
         const size_t stage_bytes = (size_t)(kBlockM + L.BN) * L.BK * 2;
-        const size_t budget = (L.BN >= 128) ? (232448 - 2048) : (100 * 1024);
-        L.stages = (int)std::min<size_t>(kMaxStages, std::max<size_t>(2, budget / stage_bytes));
-        L.smem_bytes = 2048 + (size_t)L.stages * stage_bytes;
+        int nb = has_res ? nb_res : nb_plain, lead = has_res ? lead_res : 2;
+        nb = std::max(3, std::min(nb, kMaxRing)); lead = std::max(2, std::min(lead, nb - 1));
+        const size_t fixed = 1024 + kSmemRing + (size_t)nb * kChunkBytes;
+        const size_t budget = (L.BN >= 128) ? (232448 - fixed) : (std::min<size_t>(232448, 112 * 1024) - fixed);
+        L.stages = (int)std::min<size_t>(std::min(kMaxStages, stages_cap), std::max<size_t>(2, budget / stage_bytes));
+        L.smem_bytes = fixed + (size_t)L.stages * stage_bytes;
+        if (L.smem_bytes > 232448) return fail(FVY_E_INVALID, "conv_%d: shared memory plan %zu exceeds 227 KB", s.idx, L.smem_bytes);
         if (int e = query_occ(L.BN, L.BK, L.smem_bytes, &L.occ)) return e;
         L.occ = std::max(1, std::min(L.occ, 512 / std::max(32, 2 * L.BN)));
         // operands
@@ -330,6 +349,7 @@ static int build_plan(fvy_handle* h) {
         p.leaky = s.leaky ? 1 : 0;
         p.bias = L.bias;
         p.num_n_tiles = L.num_n_tiles;
+        p.nb = nb; p.lead = lead;
         const void* a_base = nullptr;
         uint64_t a_rows = 0, a_pitch = 0;
         if (stem) {
@@ -357,15 +377,26 @@ static int build_plan(fvy_handle* h) {
         }
         if (a_base == nullptr) return fail(FVY_E_INVALID, "conv_%d: input buffer missing", s.idx);
         if (int e = make_tmap_2d(&L.tmap_a, a_base, a_pitch, a_rows, a_pitch, L.BK, kBlockM)) return e;
+        L.tmap_res = L.tmap_a; L.tmap_out[0] = L.tmap_a; L.tmap_out[1] = L.tmap_a;   // placeholders for unused maps
+        // rows of the compute domain coincide with rows of a padded (H, W) buffer only for stride-1 convs on a padded input
+        const bool coincident = !stem && s.stride == 1;
+        const uint64_t out_rows = (uint64_t)nmax * (L.Hout + 2) * (L.Wout + 2);
         if (s.res >= 0) {
             p.res = bufs[s.res].padded; p.res_pitch = by_idx[s.res]->cout; p.res_choff = 0;
             if (!p.res) return fail(FVY_E_INVALID, "conv_%d: residual buffer missing", s.idx);
+            if (!coincident) return fail(FVY_E_INVALID, "conv_%d: residual on a non stride-1 layer", s.idx);
+            if (int e = make_tmap_2d(&L.tmap_res, p.res, p.res_pitch, out_rows, p.res_pitch, 32, kBlockM)) return e;
         }
         // outputs
         int no = 0;
+        bool tmap_fail = false;
+        const bool use_tma_store = env_int("FVY_TMA_STORE", 1) != 0;
         auto add_out = [&](void* ptr, int kind, int pitch, int choff, int c_real) {
             OutDesc od; od.ptr = ptr; od.kind = kind; od.pitch = pitch; od.choff = choff; od.nmax = nmax; od.c_real = c_real;
-            p.out[no++] = od;
+            od.tma = (kind == OUT_PADDED && coincident && use_tma_store) ? 1 : 0;
+            if (no < 2 && od.tma && make_tmap_2d(&L.tmap_out[no], ptr, (uint64_t)pitch, out_rows, (uint64_t)pitch, 32, kBlockM)) tmap_fail = true;
+            if (no < 2) p.out[no] = od;
+            ++no;
         };
         if (!s.bn) {
             add_out(h->d_logits[head_i++], OUT_HEAD_F32, s.cout, 0, s.cout);
@@ -379,6 +410,7 @@ static int build_plan(fvy_handle* h) {
                 if (s.idx == 96) add_out(catB, OUT_UP2_PADDED, 384, 0, s.cout);
             }
         }
+        if (tmap_fail) return FVY_E_CUDA;
         if (no == 0) return fail(FVY_E_INVALID, "conv_%d has no consumer", s.idx);
         if (no > 2) return fail(FVY_E_INVALID, "conv_%d has more than two stored forms", s.idx);
         L.primary = p.out[0];
@@ -433,7 +465,8 @@ static int build_post(fvy_handle* h) {
     h->dets_cap = h->cap;
     if (int e = dev_alloc(h, (void**)&h->d_dets, n * sizeof(FvyDet), true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_det_counts, (size_t)B * 4, true)) return e;
-    CUDA_TRY(cudaFuncSetAttribute(sort_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_keys * 8));
+    // a function attribute is per device, not per handle: always raise it to the largest key buffer any handle may use
+    CUDA_TRY(cudaFuncSetAttribute(sort_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     return FVY_OK;
 }
 
