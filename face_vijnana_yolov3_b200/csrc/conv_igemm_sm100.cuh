@@ -18,9 +18,11 @@
 // up-sampled into a channel slice of a concat buffer (:282-283, :298-299), or dense fp32 head
 // logits (:278, :294, :308).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
-// Persistent: grid = min(#tiles, #SMs * occupancy); tiles are strided by gridDim.x.
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue group 0, warps 6..9 = epilogue group 1
+// (TMEM lane quarter = warp_idx & 3).  With two groups, consecutive tiles of a CTA alternate between
+// them (layers with a short K loop are epilogue-bound); accumulators are 2 (BN >= 128) or 4 (BN <= 64)
+// TMEM stages deep.  Persistent: grid = min(#tiles, #SMs); tiles are strided by gridDim.x.
 //
 // Epilogue data path: the accumulator is drained in chunks of 32 channels.  Each chunk is staged in a
 // ring of 8 KB shared-memory buffers laid out exactly as TMA's 64-byte swizzle expects, so that
@@ -76,7 +78,9 @@ struct ConvParams {
     const float* bias;   // [num_n_tiles * BLOCK_N] fp32
     const __nv_bfloat16* res;   // padded geometry at (H, W), or nullptr
     int res_pitch, res_choff;
-    int nb;              // staging buffers in the epilogue ring (3..8)
+    unsigned long long magic_plane, magic_w;   // ceil(2^64 / dom_plane), ceil(2^64 / dom_w): exact division by __umul64hi
+    int epi_groups;      // 1 or 2 epilogue warp groups (2: tiles alternate between them)
+    int nb;              // staging buffers in EACH group's epilogue ring (3..8)
     int lead;            // residual prefetch distance in chunks, 2 <= lead <= nb-1
     OutDesc out[2];
 };
@@ -105,7 +109,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a pipeline bug traps (-> CUDA error at the next sync) instead of hanging the GPU.
+// Bounded wait with back-off.  try_wait suspends the thread in hardware for a short, implementation-defined
+// time; the nanosleep keeps a waiting single-thread role from stealing issue slots of the epilogue warp that
+// shares its scheduler.  A pipeline bug traps (-> CUDA error at the next sync) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     for (uint32_t spin = 0;; ++spin) {
@@ -118,7 +124,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (spin > (1u << 24)) {
+        if (spin > 8) __nanosleep(spin > 64 ? 64 : 20);
+        if (spin > (1u << 23)) {
             printf("fvy: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
             __trap();
         }
@@ -231,18 +238,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 // Kernel
 // ----------------------------------------------------------------------------------------------
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 constexpr int kEpiThreads = 128;
 constexpr int kMaxStages = 8;
 constexpr int kMaxRing = 8;
+constexpr int kMaxAcc = 4;
 constexpr int kChunkBytes = kBlockM * 32 * 2;      // one staged chunk: 128 rows x 32 bf16 = 8 KB
 constexpr int kMaxCout = 1024;
 
 // Shared-memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int kSmemBarriers = 0;                    // full[8] empty[8] tmem_full[2] tmem_empty[2] res_full[8] tmem_ptr
+constexpr int kSmemBarriers = 0;                    // full[8] empty[8] tmem_full[4] tmem_empty[4] res_full[2][8] tmem_ptr
 constexpr int kSmemBias = 1024;                     // kMaxCout floats
-constexpr int kSmemRowIdx = kSmemBias + kMaxCout * 4;        // int rowidx[2 accumulator stages][2 outputs][128]
-constexpr int kSmemRing = kSmemRowIdx + 2 * 2 * kBlockM * 4; // = 7168, 1024-aligned
+constexpr int kSmemRowIdx = kSmemBias + kMaxCout * 4;        // int rowidx[2 groups][2 tile parities][2 outputs][128]
+constexpr int kSmemRing = kSmemRowIdx + 2 * 2 * 2 * kBlockM * 4; // = 9216, 1024-aligned
 static_assert(kSmemRing % 1024 == 0, "staging ring must keep the 512-byte swizzle phase");
 
 template <int BN, int BK>
@@ -250,8 +258,8 @@ struct SmemLayout {
     static constexpr int a_bytes = kBlockM * BK * 2;
     static constexpr int b_bytes = BN * BK * 2;
     static constexpr int stage_bytes = a_bytes + b_bytes;
-    static constexpr size_t bytes(int stages, int nb) { return 1024 /* alignment slack */ + kSmemRing + (size_t)nb * kChunkBytes + (size_t)stages * stage_bytes; }
 };
+__host__ __device__ constexpr int acc_stages(int bn) { return bn <= 64 ? 4 : 2; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -264,7 +272,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out0,
                   const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ ConvParams p, const int num_stages) {
     using L = SmemLayout<BN, BK>;
-    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages; BN in {32,64,128,256}
+    constexpr int kAcc = acc_stages(BN);
+    constexpr uint32_t kTmemCols = kAcc * BN;                      // 128 / 256 / 256 / 512: a power of two >= 32
     constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN);
     constexpr int kChunks = BN / 32;
 
@@ -272,14 +281,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBarriers);   // [kMaxStages]
     uint64_t* empty_bar = full_bar + kMaxStages;                               // [kMaxStages]
-    uint64_t* tmem_full = empty_bar + kMaxStages;                              // [2]
-    uint64_t* tmem_empty = tmem_full + 2;                                      // [2]
-    uint64_t* res_full = tmem_empty + 2;                                       // [kMaxRing]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + kMaxRing);
+    uint64_t* tmem_full = empty_bar + kMaxStages;                              // [kMaxAcc]
+    uint64_t* tmem_empty = tmem_full + kMaxAcc;                                // [kMaxAcc]
+    uint64_t* res_full_all = tmem_empty + kMaxAcc;                             // [2][kMaxRing]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_all + 2 * kMaxRing);
     float* sbias = reinterpret_cast<float*>(smem + kSmemBias);
-    int* srow = reinterpret_cast<int*>(smem + kSmemRowIdx);
-    uint8_t* ring = smem + kSmemRing;
-    uint8_t* tiles = ring + p.nb * kChunkBytes;
+    uint8_t* ring_all = smem + kSmemRing;
+    uint8_t* tiles = ring_all + p.epi_groups * p.nb * kChunkBytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -293,14 +301,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
         if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
         for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
-        for (int s = 0; s < kMaxRing; ++s) mbar_init(&res_full[s], 1);
+        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2 * kMaxRing; ++s) mbar_init(&res_full_all[s], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
         tmem_alloc(tmem_ptr, kTmemCols);
         tmem_relinquish();
     }
+    if (warp >= 2)   // bias is a weight, not an activation of the previous layer: safe before griddepcontrol.wait
+        for (int i = threadIdx.x - 64; i < p.num_n_tiles * BN; i += kThreads - 64) sbias[i] = __ldg(p.bias + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -334,9 +344,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ===================== MMA issuer =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            int as = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+            uint32_t it_tile = 0;                                   // tiles issued by this CTA
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
+                const int as = it_tile % kAcc;
+                mbar_wait(&tmem_empty[as], ((it_tile / kAcc) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int it = 0; it < k_iters; ++it) {
@@ -354,24 +365,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if (it == k_iters - 1) umma_commit(&tmem_full[as]);   // accumulator complete
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
-                if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
-    } else {
-        // ===================== epilogue (warps 2..5, 128 threads) =====================
+    } else if (warp < 2 + 4 * p.epi_groups) {
+        // ===================== epilogue: group g = warps 2+4g .. 5+4g (128 threads) =====================
+        const int g = (warp - 2) >> 2;             // epilogue group
+        const int ng = p.epi_groups;
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;               // row of the tile handled by this thread (TMEM lane)
-        const int et = threadIdx.x - 64;           // 0..127
+        const int et = (threadIdx.x - 64) & (kEpiThreads - 1);   // 0..127 within the group
         const bool issuer = et == 0;
         const bool has_res = p.res != nullptr;
         const bool any_tma = p.out[0].tma || p.out[1].tma;
         const int nb = p.nb, lead = p.lead;
         const uint32_t swz = (uint32_t)((r >> 1) & 3);          // 64-byte swizzle: 16-byte slot j of row r lives at slot j ^ swz
-        for (int i = et; i < p.num_n_tiles * BN; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
-        named_bar_sync(1, kEpiThreads);
+        uint8_t* ring = ring_all + g * nb * kChunkBytes;
+        uint64_t* res_full = res_full_all + g * kMaxRing;
+        int* myrow_base = reinterpret_cast<int*>(smem + kSmemRowIdx) + g * 4 * kBlockM;
+        const int bar_id = 1 + g;
+        const int tile_step = gridDim.x * ng;
+        const int tile_first = blockIdx.x + g * gridDim.x;
 
-        // residual prefetch cursor (issuer only): runs `lead` chunks ahead of consumption
-        int pf_tile = blockIdx.x, pf_chunk = 0;
+        // residual prefetch cursor (issuer only): runs `lead` chunks ahead of this group's consumption
+        int pf_tile = tile_first, pf_chunk = 0;
         uint32_t pf_count = 0;
         auto prefetch_res = [&]() {
             if (pf_tile >= num_tiles) return;
@@ -380,33 +396,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tma_load_2d(ring + buf * kChunkBytes, &tmap_res, &res_full[buf],
                         p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kBlockM);
             ++pf_count;
-            if (++pf_chunk == kChunks) { pf_chunk = 0; pf_tile += gridDim.x; }
+            if (++pf_chunk == kChunks) { pf_chunk = 0; pf_tile += tile_step; }
         };
         if (has_res && issuer)
             for (int i = 0; i < lead; ++i) prefetch_res();
 
-        uint32_t cg = 0;                           // chunks consumed so far by this CTA
-        int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t cg = 0;                           // chunks consumed so far by this group
+        uint32_t it_tile = g;                      // index of the tile in this CTA's sequence (selects the accumulator stage)
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, it_tile += ng) {
+            const int as = it_tile % kAcc;
+            int* myrow = myrow_base + ((it_tile / ng) & 1) * 2 * kBlockM;   // double-buffered: a fast thread may be one tile ahead
             const int m0 = (tile / p.num_n_tiles) * kBlockM;
             const int m = m0 + r;
             const int n0 = (tile % p.num_n_tiles) * BN;
-            // decode the pixel and decide whether the row is a real output
+            // decode the pixel and decide whether the row is a real output (exact division by multiply-high)
             bool valid = m < p.m_total;
             int img = 0, h = 0, w = 0;
             if (valid) {
-                img = m / p.dom_plane;
+                img = (int)__umul64hi((unsigned long long)m, p.magic_plane);
                 const int rem = m - img * p.dom_plane;
-                const int y = rem / p.dom_w;
+                const int y = (int)__umul64hi((unsigned long long)rem, p.magic_w);
                 h = y - p.dom_off;
                 w = rem - y * p.dom_w - p.dom_off;
                 valid = (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
             }
             // destination row of this pixel for the outputs that are not stored by TMA
-            int* myrow = srow + as * 2 * kBlockM;
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
                 const OutDesc& od = p.out[o];
+                if (od.kind == OUT_NONE || od.kind == OUT_HEAD_F32 || od.tma) continue;
                 int ridx = -1;
                 if (valid) {
                     if (od.kind == OUT_PADDED) ridx = (img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
@@ -414,11 +432,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         const int hp = h + 1, wp = w + 1;
                         const int pw = (p.W >> 1) + 1, plane = ((p.H >> 1) + 1) * pw;
                         ridx = ((((hp & 1) << 1) | (wp & 1)) * od.nmax + img) * plane + (hp >> 1) * pw + (wp >> 1);
-                    } else if (od.kind == OUT_UP2_PADDED) ridx = (img * (2 * p.H + 2) + (2 * h + 1)) * (2 * p.W + 2) + (2 * w + 1);
+                    } else ridx = (img * (2 * p.H + 2) + (2 * h + 1)) * (2 * p.W + 2) + (2 * w + 1);   // OUT_UP2_PADDED
                 }
                 myrow[o * kBlockM + r] = ridx;
             }
-            mbar_wait(&tmem_full[as], aphase);
+            mbar_wait(&tmem_full[as], (it_tile / kAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
@@ -442,21 +460,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
                     }
                 }
-                if (p.leaky) {
+                if (p.leaky) {   // LeakyReLU(0.1) == max(v, 0.1 v)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
                 }
                 if (has_res) {
                     mbar_wait(&res_full[buf], (cg / nb) & 1);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 t = myslot[j ^ swz];
-                        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            v[8 * j + 2 * e + 0] += __uint_as_float(u[e] << 16);
-                            v[8 * j + 2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u);
-                        }
+                        v[8 * j + 0] += __uint_as_float(t.x << 16); v[8 * j + 1] += __uint_as_float(t.x & 0xFFFF0000u);
+                        v[8 * j + 2] += __uint_as_float(t.y << 16); v[8 * j + 3] += __uint_as_float(t.y & 0xFFFF0000u);
+                        v[8 * j + 4] += __uint_as_float(t.z << 16); v[8 * j + 5] += __uint_as_float(t.z & 0xFFFF0000u);
+                        v[8 * j + 6] += __uint_as_float(t.w << 16); v[8 * j + 7] += __uint_as_float(t.w & 0xFFFF0000u);
                     }
                 }
                 // fp32 head logits go straight from registers (18 / 255 / 6 valid channels)
@@ -471,23 +487,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                 }
                 // stage the bf16 chunk (halo / out-of-image rows as zeros: they ARE the padding of the next layer)
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 pk;
-                    pk.x = valid ? pack_bf16x2(v[8 * j + 0], v[8 * j + 1]) : 0u;
-                    pk.y = valid ? pack_bf16x2(v[8 * j + 2], v[8 * j + 3]) : 0u;
-                    pk.z = valid ? pack_bf16x2(v[8 * j + 4], v[8 * j + 5]) : 0u;
-                    pk.w = valid ? pack_bf16x2(v[8 * j + 6], v[8 * j + 7]) : 0u;
+                    pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                    pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                    pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                    pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
                     myslot[j ^ swz] = pk;
                 }
-                fence_proxy_async();                       // generic-proxy smem writes -> visible to TMA
-                named_bar_sync(1, kEpiThreads);
+                if (any_tma || has_res) fence_proxy_async();   // generic-proxy smem writes -> visible to TMA
+                named_bar_sync(bar_id, kEpiThreads);
                 if (issuer) {
                     if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + c0, m0);
                     if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + c0, m0);
-                    if (any_tma) bulk_commit();
-                    if (any_tma) bulk_wait_read(nb - lead);   // the buffer of chunk cg + lead - nb has been read
-                    if (has_res) prefetch_res();              // ... so the residual of chunk cg + lead may land in it
+                    if (any_tma) { bulk_commit(); bulk_wait_read(nb - lead); }   // the buffer of chunk cg + lead - nb has been read
+                    if (has_res) prefetch_res();                                 // ... so the residual of chunk cg + lead may land in it
                 }
                 // remaining output forms: 4 threads per 64-byte row, 32 rows per pass
 #pragma unroll
@@ -517,7 +536,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
-            if (++as == 2) { as = 0; aphase ^= 1; }
         }
         if (issuer && any_tma) bulk_wait_all();             // smem must outlive the last TMA store
     }

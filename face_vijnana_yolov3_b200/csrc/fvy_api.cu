@@ -217,6 +217,7 @@ template <int BN, int BK>
 static int query_occ_t(size_t smem, int* occ) {
     auto kern = conv_igemm_kernel<BN, BK>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem));
     return FVY_OK;
 }
@@ -302,6 +303,7 @@ static int build_plan(fvy_handle* h) {
     const int bn_res_cap = std::min(bn_cap, env_int("FVY_BN_RES", 256));
     const int nb_res = env_int("FVY_NB_RES", 6), lead_res = env_int("FVY_LEAD", 4), nb_plain = env_int("FVY_NB", 3);
     const int stages_cap = env_int("FVY_STAGES", kMaxStages);
+    const int groups_kn = env_int("FVY_GROUPS_KN", 40);   // (K iterations x 32-column chunks) at or below which a layer gets two epilogue groups
     h->use_pdl = env_int("FVY_PDL", 1) != 0;
     size_t stream_off = 0;
     int head_i = 0;
@@ -326,15 +328,20 @@ static int build_plan(fvy_handle* h) {
             if (bn <= cap_n && L.cout_pad % bn == 0) { L.BN = bn; break; }
         L.num_n_tiles = L.cout_pad / L.BN;
         const size_t stage_bytes = (size_t)(kBlockM + L.BN) * L.BK * 2;
+        // Layers with a short K loop are epilogue-bound: two epilogue groups alternate tiles.  Deep-K layers keep one
+        // group so that the shared memory goes to the operand pipeline instead of a second staging ring.
+        const int k_iters = L.taps * (L.cin_pad / L.BK);
+        const int groups = env_int("FVY_GROUPS", 0) > 0 ? env_int("FVY_GROUPS", 0) : (k_iters * (L.BN / 32) <= groups_kn ? 2 : 1);
         int nb = has_res ? nb_res : nb_plain, lead = has_res ? lead_res : 2;
+        if (groups == 2 && has_res) { nb = std::min(nb, 4); lead = nb - 1; }
         nb = std::max(3, std::min(nb, kMaxRing)); lead = std::max(2, std::min(lead, nb - 1));
-        const size_t fixed = 1024 + kSmemRing + (size_t)nb * kChunkBytes;
-        const size_t budget = (L.BN >= 128) ? (232448 - fixed) : (std::min<size_t>(232448, 112 * 1024) - fixed);
+        const size_t fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;
+        const size_t budget = 232448 - fixed;
         L.stages = (int)std::min<size_t>(std::min(kMaxStages, stages_cap), std::max<size_t>(2, budget / stage_bytes));
         L.smem_bytes = fixed + (size_t)L.stages * stage_bytes;
         if (L.smem_bytes > 232448) return fail(FVY_E_INVALID, "conv_%d: shared memory plan %zu exceeds 227 KB", s.idx, L.smem_bytes);
         if (int e = query_occ(L.BN, L.BK, L.smem_bytes, &L.occ)) return e;
-        L.occ = std::max(1, std::min(L.occ, 512 / std::max(32, 2 * L.BN)));
+        L.occ = 1;   // 320 threads x ~140 registers: one CTA per SM; latency is hidden inside the CTA (stages, two epilogue groups)
         // operands
         const size_t kdim = (size_t)L.taps * L.cin_pad;
         if (int e = dev_alloc(h, (void**)&L.w, (size_t)L.cout_pad * kdim * 2, true)) return e;
@@ -349,7 +356,7 @@ static int build_plan(fvy_handle* h) {
         p.leaky = s.leaky ? 1 : 0;
         p.bias = L.bias;
         p.num_n_tiles = L.num_n_tiles;
-        p.nb = nb; p.lead = lead;
+        p.nb = nb; p.lead = lead; p.epi_groups = groups;
         const void* a_base = nullptr;
         uint64_t a_rows = 0, a_pitch = 0;
         if (stem) {
@@ -376,6 +383,9 @@ static int build_plan(fvy_handle* h) {
                     for (int q = 0; q < 3; ++q) p.tap_off[r * 3 + q] = (r - 1) * (W + 2) + (q - 1);
         }
         if (a_base == nullptr) return fail(FVY_E_INVALID, "conv_%d: input buffer missing", s.idx);
+        p.magic_plane = ~0ull / (unsigned long long)p.dom_plane + 1ull;
+        p.magic_w = ~0ull / (unsigned long long)p.dom_w + 1ull;
+        if ((long long)nmax * p.dom_plane >= (1ll << 31)) return fail(FVY_E_INVALID, "conv_%d: %d x %d rows overflow int32", s.idx, nmax, p.dom_plane);
         if (int e = make_tmap_2d(&L.tmap_a, a_base, a_pitch, a_rows, a_pitch, L.BK, kBlockM)) return e;
         L.tmap_res = L.tmap_a; L.tmap_out[0] = L.tmap_a; L.tmap_out[1] = L.tmap_a;   // placeholders for unused maps
         // rows of the compute domain coincide with rows of a padded (H, W) buffer only for stride-1 convs on a padded input
