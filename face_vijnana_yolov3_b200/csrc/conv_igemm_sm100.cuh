@@ -112,7 +112,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait with back-off.  try_wait suspends the thread in hardware for a short, implementation-defined
 // time; the nanosleep keeps a waiting single-thread role from stealing issue slots of the epilogue warp that
 // shares its scheduler.  A pipeline bug traps (-> CUDA error at the next sync) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, bool backoff = true) {
     const uint32_t addr = smem_u32(bar);
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
@@ -124,7 +124,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (spin > 8) __nanosleep(spin > 64 ? 64 : 20);
+        if (backoff && spin > 8) __nanosleep(spin > 64 ? 64 : 20);
         if (spin > (1u << 23)) {
             printf("fvy: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
             __trap();
@@ -240,14 +240,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 constexpr int kBlockM = 128;
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 20;
 constexpr int kMaxRing = 8;
 constexpr int kMaxAcc = 4;
 constexpr int kChunkBytes = kBlockM * 32 * 2;      // one staged chunk: 128 rows x 32 bf16 = 8 KB
 constexpr int kMaxCout = 1024;
 
 // Shared-memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int kSmemBarriers = 0;                    // full[8] empty[8] tmem_full[4] tmem_empty[4] res_full[2][8] tmem_ptr
+constexpr int kSmemBarriers = 0;                    // full[20] empty[20] tmem_full[4] tmem_empty[4] res_full[2][8] tmem_ptr (520 B)
 constexpr int kSmemBias = 1024;                     // kMaxCout floats
 constexpr int kSmemRowIdx = kSmemBias + kMaxCout * 4;        // int rowidx[2 groups][2 tile parities][2 outputs][128]
 constexpr int kSmemRing = kSmemRowIdx + 2 * 2 * 2 * kBlockM * 4; // = 9216, 1024-aligned
@@ -329,7 +329,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int tap = 0; tap < p.num_taps; ++tap) {
                     const int row = m0 + p.tap_off[tap];
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_wait(&empty_bar[stage], phase ^ 1, p.epi_groups == 2);
                         uint8_t* sa = tiles + stage * L::stage_bytes;
                         uint8_t* sb = sa + L::a_bytes;
                         mbar_expect_tx(&full_bar[stage], L::stage_bytes);
@@ -347,11 +347,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t it_tile = 0;                                   // tiles issued by this CTA
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
                 const int as = it_tile % kAcc;
-                mbar_wait(&tmem_empty[as], ((it_tile / kAcc) & 1) ^ 1);
+                mbar_wait(&tmem_empty[as], ((it_tile / kAcc) & 1) ^ 1, p.epi_groups == 2);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int it = 0; it < k_iters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(&full_bar[stage], phase, p.epi_groups == 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + stage * L::stage_bytes);
                     const uint64_t da = make_smem_desc<BK>(sa);
