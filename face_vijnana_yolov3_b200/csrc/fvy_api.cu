@@ -604,7 +604,7 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
         SweepArgs w;
         w.mask = h->d_mask; w.order = h->d_order; w.counts = d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
         w.nb_class = nb_class; w.cls = c; w.classes = d_cls;
-        nms_sweep_kernel<<<batch, 512, (size_t)h->words * 8, h->stream>>>(w);
+        nms_sweep_kernel<<<batch, 1024, (size_t)h->words * 8, h->stream>>>(w);
         CUDA_TRY(cudaGetLastError());
         h->launches += 3;
     }

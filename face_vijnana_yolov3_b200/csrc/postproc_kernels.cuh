@@ -285,6 +285,25 @@ __device__ __forceinline__ bool iou_ge(const int4 a, const int4 b, double th, bo
     if (p.inter == 0) return zero_ge_th;
     return __ddiv_rn((double)p.inter, (double)p.uni) >= th;
 }
+// Same decision for WELL-FORMED boxes (xmin <= xmax, ymin <= ymax) with precomputed areas and th > 0, arranged so that
+// the common case costs a handful of 32-bit instructions:
+//   * no strict overlap  => _interval_overlap returns 0 on one axis => intersect == 0 => iou is 0 (or nan) => not >= th;
+//   * otherwise intersect = iw*ih exactly in int64, union = area_a + area_b - intersect, and
+//     fl(intersect/union) >= th is decided by comparing intersect with th*union in double when the two differ by more
+//     than 2 ulp (fl is monotone), and by the correctly rounded divide itself inside that band.
+__device__ __forceinline__ bool iou_ge_fast(const int4 a, long long area_a, const int4 b, long long area_b, double th) {
+    if (a.z <= b.x || b.z <= a.x || a.w <= b.y || b.w <= a.y) return false;
+    const int iw = min(a.z, b.z) - max(a.x, b.x);
+    const int ih = min(a.w, b.w) - max(a.y, b.y);
+    const long long inter = (long long)iw * (long long)ih;
+    const long long uni = area_a + area_b - inter;
+    if (uni == 0) return false;
+    const double x = (double)inter, u = (double)uni;
+    const double t = __dmul_rn(th, u);
+    if (x > __dmul_rn(t, 1.0 + 0x1p-51)) return true;
+    if (x < __dmul_rn(t, 1.0 - 0x1p-51)) return false;
+    return __ddiv_rn(x, u) >= th;
+}
 __global__ void bbox_iou_kernel(const int4* a, const int4* b, int n, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -372,17 +391,18 @@ struct MaskArgs {
 // produces the 64-bit word of column block c (bit j set <=> IoU(row, c*64+j) >= th and c*64+j > row).
 __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
     __shared__ int4 cbox[64];
+    __shared__ long long carea[64];
     __shared__ int tile_prefix[1025];   // batch <= 1024
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < a.batch; ++b) {
-            tile_prefix[b] = acc;
-            const int n = min(a.counts[b], a.seg_stride);
-            const int nb = (n + 63) >> 6;
-            acc += nb * nb;
-        }
-        tile_prefix[a.batch] = acc;
+    __shared__ int all_wellformed;
+    for (int b = threadIdx.x; b < a.batch; b += blockDim.x) {
+        const int n = min(a.counts[b], a.seg_stride);
+        const int nb = (n + 63) >> 6;
+        tile_prefix[b + 1] = nb * nb;
     }
+    if (threadIdx.x == 0) { tile_prefix[0] = 0; all_wellformed = 1; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int b = 0; b < a.batch; ++b) tile_prefix[b + 1] += tile_prefix[b];
     __syncthreads();
     const int total = tile_prefix[a.batch];
     const bool zero_ge = 0.0 >= a.th;
@@ -396,16 +416,28 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
         if (c < r) continue;                               // block-uniform
         const int4* sb = a.sbox + (size_t)img * a.capP;
         const int col = c * 64 + threadIdx.x;
-        __syncthreads();
-        cbox[threadIdx.x] = col < n ? sb[col] : make_int4(0, 0, 0, 0);
-        __syncthreads();
         const int row = r * 64 + threadIdx.x;
+        __syncthreads();
+        const int4 cb = col < n ? sb[col] : make_int4(0, 0, 0, 0);
+        const int4 me = row < n ? sb[row] : make_int4(0, 0, 0, 0);
+        cbox[threadIdx.x] = cb;
+        carea[threadIdx.x] = ((long long)cb.z - cb.x) * ((long long)cb.w - cb.y);
+        all_wellformed = 1;
+        __syncthreads();
+        if (cb.z < cb.x || cb.w < cb.y || me.z < me.x || me.w < me.y) all_wellformed = 0;
+        __syncthreads();
         if (row < n) {
-            const int4 me = sb[row];
             unsigned long long word = 0;
             const int jmax = min(64, n - c * 64);
-            for (int j = (c == r ? threadIdx.x + 1 : 0); j < jmax; ++j)
-                if (iou_ge(me, cbox[j], a.th, zero_ge)) word |= 1ull << j;
+            const int j0 = (c == r ? threadIdx.x + 1 : 0);
+            if (all_wellformed && !zero_ge) {
+                const long long my_area = ((long long)me.z - me.x) * ((long long)me.w - me.y);
+                for (int j = j0; j < jmax; ++j)
+                    if (iou_ge_fast(me, my_area, cbox[j], carea[j], a.th)) word |= 1ull << j;
+            } else {
+                for (int j = j0; j < jmax; ++j)
+                    if (iou_ge(me, cbox[j], a.th, zero_ge)) word |= 1ull << j;
+            }
             a.mask[((size_t)img * a.capP + row) * a.words + c] = word;
         }
     }
@@ -421,10 +453,12 @@ struct SweepArgs {
     float* classes;         // in/out
 };
 
-// One block per image.  Walks the sorted list in blocks of 64: a single thread resolves the
-// in-block dependencies on the diagonal word, then all threads OR the kept rows into `removed`.
-// Boxes whose score is already 0 never suppress (yolov3_detect.py:438).
-__global__ void __launch_bounds__(512) nms_sweep_kernel(const SweepArgs a) {
+// One block per image.  Walks the sorted list in blocks of 64.  Per block: (1) the 64 diagonal words and the
+// "score != 0" bits are fetched in parallel, (2) warp 0 resolves the in-block dependencies with the words held in
+// registers (shuffle broadcast, no memory in the dependent chain), (3) every (kept row, later word) pair is fetched
+// by its own thread and OR-ed into the removed mask with a shared-memory atomic, so a block step costs one memory
+// latency instead of one per kept row.  Boxes whose score is already 0 never suppress (yolov3_detect.py:438).
+__global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
     extern __shared__ unsigned long long removed[];    // [words]
     __shared__ unsigned long long diag[64];
     __shared__ unsigned long long alive_w, keep_w;
@@ -436,40 +470,42 @@ __global__ void __launch_bounds__(512) nms_sweep_kernel(const SweepArgs a) {
     const int* ord = a.order + (size_t)img * a.capP;
     const unsigned long long* mk = a.mask + (size_t)img * a.capP * a.words;
     for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
+    if (threadIdx.x == 0) alive_w = 0;
     __syncthreads();
     for (int blk = 0; blk < nb; ++blk) {
-        if (threadIdx.x == 0) alive_w = 0;
-        __syncthreads();
         if (threadIdx.x < 64) {
             const int i = blk * 64 + threadIdx.x;
             unsigned long long d = 0;
+            bool alive = false;
             if (i < n) {
                 d = mk[(size_t)i * a.words + blk];
-                if (a.classes[(seg + ord[i]) * a.nb_class + a.cls] != 0.f) atomicOr(&alive_w, 1ull << threadIdx.x);
+                alive = a.classes[(seg + ord[i]) * a.nb_class + a.cls] != 0.f;
             }
             diag[threadIdx.x] = d;
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if ((threadIdx.x & 31) == 0) atomicOr(&alive_w, (unsigned long long)bal << (threadIdx.x & 32));
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            const unsigned long long d_lo = diag[threadIdx.x], d_hi = diag[threadIdx.x + 32];
             unsigned long long cur = removed[blk], keep = 0;
             const unsigned long long alive = alive_w;
+#pragma unroll 1
             for (int b = 0; b < 64; ++b) {
-                if (((alive >> b) & 1ull) && !((cur >> b) & 1ull)) { keep |= 1ull << b; cur |= diag[b]; }
+                const unsigned long long db = __shfl_sync(0xffffffffu, b < 32 ? d_lo : d_hi, b & 31);
+                if (((alive >> b) & 1ull) && !((cur >> b) & 1ull)) { keep |= 1ull << b; cur |= db; }
             }
-            removed[blk] = cur;
-            keep_w = keep;
+            if (threadIdx.x == 0) { removed[blk] = cur; keep_w = keep; alive_w = 0; }
         }
         __syncthreads();
         const unsigned long long keep = keep_w;
-        for (int w = blk + 1 + threadIdx.x; w < nb; w += blockDim.x) {
-            unsigned long long acc = removed[w];
-            unsigned long long kk = keep;
-            while (kk) {
-                const int b = __ffsll((long long)kk) - 1;
-                kk &= kk - 1;
-                acc |= mk[(size_t)(blk * 64 + b) * a.words + w];
+        const int later = nb - (blk + 1);
+        for (int idx = threadIdx.x; idx < 64 * later; idx += blockDim.x) {
+            const int b = idx / later, w = blk + 1 + (idx - b * later);
+            if ((keep >> b) & 1ull) {
+                const unsigned long long m = mk[(size_t)(blk * 64 + b) * a.words + w];
+                if (m) atomicOr(&removed[w], m);
             }
-            removed[w] = acc;
         }
         __syncthreads();
     }
