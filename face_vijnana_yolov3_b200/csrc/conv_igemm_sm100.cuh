@@ -80,6 +80,7 @@ struct ConvParams {
     int res_pitch, res_choff;
     unsigned long long magic_plane, magic_w;   // ceil(2^64 / dom_plane), ceil(2^64 / dom_w): exact division by __umul64hi
     int epi_groups;      // 1 or 2 epilogue warp groups (2: tiles alternate between them)
+    int tps;             // taps per operand stage (1, or 3 when k_chunks == 1): fewer barrier round trips per tile
     int nb;              // staging buffers in EACH group's epilogue ring (3..8)
     int lead;            // residual prefetch distance in chunks, 2 <= lead <= nb-1
     OutDesc out[2];
@@ -292,7 +293,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int k_iters = p.num_taps * p.k_chunks;
+    const int k_iters = (p.num_taps / p.tps) * p.k_chunks;   // operand stages per tile
+    const int stage_bytes = p.tps * L::stage_bytes;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -326,15 +328,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.num_n_tiles) * kBlockM;
                 const int n0 = (tile % p.num_n_tiles) * BN;
-                for (int tap = 0; tap < p.num_taps; ++tap) {
-                    const int row = m0 + p.tap_off[tap];
+                for (int tap = 0; tap < p.num_taps; tap += p.tps) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, p.epi_groups == 2);
-                        uint8_t* sa = tiles + stage * L::stage_bytes;
-                        uint8_t* sb = sa + L::a_bytes;
-                        mbar_expect_tx(&full_bar[stage], L::stage_bytes);
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, row);
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], (tap * p.k_chunks + kc) * BK, n0);
+                        uint8_t* sa = tiles + stage * stage_bytes;
+                        uint8_t* sb = sa + p.tps * L::a_bytes;
+                        mbar_expect_tx(&full_bar[stage], stage_bytes);
+                        for (int t = 0; t < p.tps; ++t) {
+                            tma_load_2d(sa + t * L::a_bytes, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, m0 + p.tap_off[tap + t]);
+                            tma_load_2d(sb + t * L::b_bytes, &tmap_b, &full_bar[stage], ((tap + t) * p.k_chunks + kc) * BK, n0);
+                        }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -353,13 +356,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&full_bar[stage], phase, p.epi_groups == 2);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + stage * L::stage_bytes);
-                    const uint64_t da = make_smem_desc<BK>(sa);
-                    const uint64_t db = make_smem_desc<BK>(sa + L::a_bytes);
+                    const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
+                    const uint32_t sb = sa + p.tps * L::a_bytes;
+                    for (int t = 0; t < p.tps; ++t) {
+                        const uint64_t da = make_smem_desc<BK>(sa + t * L::a_bytes);
+                        const uint64_t db = make_smem_desc<BK>(sb + t * L::b_bytes);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | t | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
                     if (it == k_iters - 1) umma_commit(&tmem_full[as]);   // accumulator complete

@@ -160,7 +160,12 @@ struct fvy_handle {
     long long launches = 0;
     long long weight_count = 0;
     // forward
-    void* d_input = nullptr; size_t input_bytes = 0;       // staging for host images
+    // Host images are staged through two device slots on a separate copy stream so that, with the async API, the
+    // H2D copy of call i+1 overlaps the compute of call i; detections leave on a third stream.
+    void* d_input[2] = {nullptr, nullptr}; size_t input_bytes = 0;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_post = nullptr, ev_d2h = nullptr;
+    unsigned stage_slot = 0; int last_slot = -1;
     __nv_bfloat16* d_stem = nullptr;                        // im2col operand
     float* d_logits[3] = {nullptr, nullptr, nullptr};
     int gh[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, head_c = 0;
@@ -327,10 +332,12 @@ static int build_plan(fvy_handle* h) {
         for (int bn : {256, 128, 64, 32})
             if (bn <= cap_n && L.cout_pad % bn == 0) { L.BN = bn; break; }
         L.num_n_tiles = L.cout_pad / L.BN;
-        const size_t stage_bytes = (size_t)(kBlockM + L.BN) * L.BK * 2;
+        int tps = (L.taps == 9 && L.cin_pad == L.BK && env_int("FVY_TPS", 3) == 3) ? 3 : 1;   // one filter row per stage when Cin fits one K chunk
+        if (tps == 3 && (size_t)3 * 3 * (kBlockM + L.BN) * L.BK * 2 > 150 * 1024) tps = 1;              // needs >= 3 such stages next to the epilogue rings
+        const size_t stage_bytes = (size_t)tps * (kBlockM + L.BN) * L.BK * 2;
         // Layers with a short K loop are epilogue-bound: two epilogue groups alternate tiles.  Deep-K layers keep one
         // group so that the shared memory goes to the operand pipeline instead of a second staging ring.
-        const int k_iters = L.taps * (L.cin_pad / L.BK);
+        const int k_iters = (L.taps / tps) * (L.cin_pad / L.BK);
         const int groups = env_int("FVY_GROUPS", 0) > 0 ? env_int("FVY_GROUPS", 0) : (k_iters * (L.BN / 32) <= groups_kn ? 2 : 1);
         int nb = has_res ? nb_res : nb_plain, lead = has_res ? lead_res : 2;
         if (groups == 2 && has_res) { nb = std::min(nb, 4); lead = nb - 1; }
@@ -356,7 +363,7 @@ static int build_plan(fvy_handle* h) {
         p.leaky = s.leaky ? 1 : 0;
         p.bias = L.bias;
         p.num_n_tiles = L.num_n_tiles;
-        p.nb = nb; p.lead = lead; p.epi_groups = groups;
+        p.nb = nb; p.lead = lead; p.epi_groups = groups; p.tps = tps;
         const void* a_base = nullptr;
         uint64_t a_rows = 0, a_pitch = 0;
         if (stem) {
@@ -484,15 +491,26 @@ static int build_post(fvy_handle* h) {
 static int stage_input(fvy_handle* h, const void* images, int dtype, int batch, const void** dev_images) {
     const size_t es = dtype == FVY_F64 ? 8 : 4;
     const size_t bytes = (size_t)batch * h->cfg.net_h * h->cfg.net_w * 3 * es;
+    h->last_slot = -1;
     if (is_device_ptr(images)) { *dev_images = images; return FVY_OK; }
     if (h->input_bytes < bytes) {
-        if (h->d_input) cudaFree(h->d_input);
-        h->d_input = nullptr; h->input_bytes = 0;
-        CUDA_TRY(cudaMalloc(&h->d_input, bytes));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->h2d_stream));
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_input[i]) cudaFree(h->d_input[i]);
+            h->d_input[i] = nullptr;
+        }
+        h->input_bytes = 0;
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMalloc(&h->d_input[i], bytes));
         h->input_bytes = bytes;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_input, images, bytes, cudaMemcpyHostToDevice, h->stream));
-    *dev_images = h->d_input;
+    const int slot = (int)(h->stage_slot++ & 1u);
+    CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, h->ev_consumed[slot], 0));     // the stem of two calls ago has read this slot
+    CUDA_TRY(cudaMemcpyAsync(h->d_input[slot], images, bytes, cudaMemcpyHostToDevice, h->h2d_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_ready[slot], h->h2d_stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_ready[slot], 0));
+    h->last_slot = slot;
+    *dev_images = h->d_input[slot];
     return FVY_OK;
 }
 
@@ -522,6 +540,7 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
         stem_im2col_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
+    if (h->last_slot >= 0) CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream));
     return run_layers(h, batch, 0, (int)h->layers.size());
 }
 
@@ -659,10 +678,15 @@ void fvy_destroy(fvy_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->d_input) cudaFree(h->d_input);
+    for (void* p : h->d_input) if (p) cudaFree(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_ready[0], h->ev_ready[1], h->ev_consumed[0], h->ev_consumed[1], h->ev_post, h->ev_d2h}) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
 }
 
@@ -689,8 +713,11 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
     int e = FVY_OK;
     do {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { e = fail(FVY_E_CUDA, "cudaStreamCreate failed"); break; }
-        bool ok = true;
+        bool ok = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (auto& ev : h->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+        for (cudaEvent_t* ev : {&h->ev_ready[0], &h->ev_ready[1], &h->ev_consumed[0], &h->ev_consumed[1], &h->ev_post, &h->ev_d2h})
+            ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { e = fail(FVY_E_CUDA, "cudaEventCreate failed"); break; }
         if (cfg->head != FVY_HEAD_NONE && (e = build_plan(h))) break;
         if ((e = build_post(h))) break;
@@ -881,15 +908,20 @@ static int postprocess_common(fvy_handle* h, const float* out0, const float* out
     if (int e = resolve_logits(h, out0, out1, out2, batch, dev)) return e;
     const int* d_hw = nullptr;
     if (int e = upload_image_hw(h, image_hw, batch, &d_hw)) return e;
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h, 0));      // the previous call's detections have left the device buffers
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     if (int e = post_enqueue(h, dev, batch, pp, d_hw, max_out)) return e;
     CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-    if (int e = copy_out(h, h->d_dets, dets, (size_t)batch * max_out * sizeof(FvyDet))) return e;
-    if (int e = copy_out(h, h->d_det_counts, det_counts, (size_t)batch * 4)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev_post, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_post, 0));
+    CUDA_TRY(cudaMemcpyAsync(dets, h->d_dets, (size_t)batch * max_out * sizeof(FvyDet), cudaMemcpyDefault, h->d2h_stream));
+    CUDA_TRY(cudaMemcpyAsync(det_counts, h->d_det_counts, (size_t)batch * 4, cudaMemcpyDefault, h->d2h_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_d2h, h->d2h_stream));
     if (!sync) return FVY_OK;
     std::vector<int> hc(batch);
     CUDA_TRY(cudaMemcpyAsync(hc.data(), h->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     CUDA_TRY(cudaEventElapsedTime(&h->last_post_ms, h->ev[2], h->ev[3]));
     return check_post_status(h, batch, hc.data());
 }
@@ -928,6 +960,8 @@ int fvy_sync(fvy_handle* h) {
     if (!h) return fail(FVY_E_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->h2d_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     return FVY_OK;
 }
 
@@ -1016,8 +1050,10 @@ int fvy_timer_start(fvy_handle* h) {
 int fvy_timer_stop(fvy_handle* h, float* ms) {
     if (!h || !ms) return fail(FVY_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h, 0));      // include the last result copy in the measured interval
     CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     CUDA_TRY(cudaEventElapsedTime(ms, h->ev[4], h->ev[5]));
     return FVY_OK;
 }
