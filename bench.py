@@ -147,6 +147,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("FVY_NCCL_DEBUG", "WARN")   # NCCL prints its version banner on stdout otherwise
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, S = args.batch, args.size
     eng = Engine(S, S, head=L.HEAD_YOLO3, nb_class=1, max_batch=B, device=local_rank, tile_n_max=args.tile_n)

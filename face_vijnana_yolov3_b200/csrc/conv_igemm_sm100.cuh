@@ -198,6 +198,57 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster cooperate on one 256-row tile --------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// TMA load issued by either CTA of the pair; the transaction bytes are counted on the LEADER's (rank 0) barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(map_to_cta(smem_u32(bar), 0)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(smem_u32(bar), 0)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows from each CTA's smem] * B[N/2 rows from each CTA's smem]^T, issued by the leader
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread t of the warp gets TMEM lane (base_lane + t), columns [col, col+32).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -267,7 +318,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool CTA2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out0,
@@ -275,8 +326,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     using L = SmemLayout<BN, BK>;
     constexpr int kAcc = acc_stages(BN);
     constexpr uint32_t kTmemCols = kAcc * BN;                      // 128 / 256 / 256 / 512: a power of two >= 32
-    constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN);
+    // CTA2: the pair computes a 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows)
+    constexpr uint32_t kIdesc = make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, BN);
     constexpr int kChunks = BN / 32;
+    constexpr int kABytes = L::a_bytes;
+    constexpr int kBBytes = CTA2 ? L::b_bytes / 2 : L::b_bytes;
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const int cta_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // tiles advance by the number of clusters
+    const int cta_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -292,9 +349,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = (CTA2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;   // CTA2: tiles of 256 rows
     const int k_iters = (p.num_taps / p.tps) * p.k_chunks;   // operand stages per tile
-    const int stage_bytes = p.tps * L::stage_bytes;
+    const int stage_bytes = p.tps * (kABytes + kBBytes);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -303,18 +360,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
         if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
         for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CTA2 ? 8 : 4); }
         for (int s = 0; s < 2 * kMaxRing; ++s) mbar_init(&res_full_all[s], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, kTmemCols);
-        tmem_relinquish();
+        if constexpr (CTA2) { tmem_alloc_pair(tmem_ptr, kTmemCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
     }
     if (warp >= 2)   // bias is a weight, not an activation of the previous layer: safe before griddepcontrol.wait
         for (int i = threadIdx.x - 64; i < p.num_n_tiles * BN; i += kThreads - 64) sbias[i] = __ldg(p.bias + i);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     // Everything above touched no memory written by the previous layer; from here on we do.
@@ -325,18 +383,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.num_n_tiles) * kBlockM;
-                const int n0 = (tile % p.num_n_tiles) * BN;
+            for (int tile = cta_first; tile < num_tiles; tile += cta_step) {
+                const int m0 = (tile / p.num_n_tiles) * (CTA2 ? 2 * kBlockM : kBlockM) + (int)cta_rank * kBlockM;
+                const int n0 = (tile % p.num_n_tiles) * BN + (CTA2 ? (int)cta_rank * (BN / 2) : 0);
                 for (int tap = 0; tap < p.num_taps; tap += p.tps) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, p.epi_groups == 2);
                         uint8_t* sa = tiles + stage * stage_bytes;
-                        uint8_t* sb = sa + p.tps * L::a_bytes;
-                        mbar_expect_tx(&full_bar[stage], stage_bytes);
-                        for (int t = 0; t < p.tps; ++t) {
-                            tma_load_2d(sa + t * L::a_bytes, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, m0 + p.tap_off[tap + t]);
-                            tma_load_2d(sb + t * L::b_bytes, &tmap_b, &full_bar[stage], ((tap + t) * p.k_chunks + kc) * BK, n0);
+                        uint8_t* sb = sa + p.tps * kABytes;
+                        if constexpr (CTA2) {
+                            // one arrival (the leader's) per phase; it expects the bytes of BOTH CTAs, whose loads all signal the leader's barrier
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                            for (int t = 0; t < p.tps; ++t) {
+                                tma_load_2d_pair(sa + t * kABytes, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, m0 + p.tap_off[tap + t]);
+                                tma_load_2d_pair(sb + t * kBBytes, &tmap_b, &full_bar[stage], ((tap + t) * p.k_chunks + kc) * BK, n0);
+                            }
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], stage_bytes);
+                            for (int t = 0; t < p.tps; ++t) {
+                                tma_load_2d(sa + t * kABytes, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, m0 + p.tap_off[tap + t]);
+                                tma_load_2d(sb + t * kBBytes, &tmap_b, &full_bar[stage], ((tap + t) * p.k_chunks + kc) * BK, n0);
+                            }
                         }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
@@ -344,11 +411,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (elect_one()) {
+        // ===================== MMA issuer (CTA2: the leader CTA issues for the pair) =====================
+        if ((!CTA2 || cta_rank == 0) && elect_one()) {
             int stage = 0; uint32_t phase = 0;
             uint32_t it_tile = 0;                                   // tiles issued by this CTA
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
+            for (int tile = cta_first; tile < num_tiles; tile += cta_step, ++it_tile) {
                 const int as = it_tile % kAcc;
                 mbar_wait(&tmem_empty[as], ((it_tile / kAcc) & 1) ^ 1, p.epi_groups == 2);
                 tc_fence_after();
@@ -357,18 +424,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     mbar_wait(&full_bar[stage], phase, p.epi_groups == 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
-                    const uint32_t sb = sa + p.tps * L::a_bytes;
+                    const uint32_t sb = sa + p.tps * kABytes;
                     for (int t = 0; t < p.tps; ++t) {
-                        const uint64_t da = make_smem_desc<BK>(sa + t * L::a_bytes);
-                        const uint64_t db = make_smem_desc<BK>(sb + t * L::b_bytes);
+                        const uint64_t da = make_smem_desc<BK>(sa + t * kABytes);
+                        const uint64_t db = make_smem_desc<BK>(sb + t * kBBytes);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | t | k) != 0);
+                            if constexpr (CTA2) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | t | k) != 0);
+                            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | t | k) != 0);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
-                    if (it == k_iters - 1) umma_commit(&tmem_full[as]);   // accumulator complete
+                    if constexpr (CTA2) {
+                        umma_commit_pair(&empty_bar[stage]);                      // frees the slot in both CTAs
+                        if (it == k_iters - 1) umma_commit_pair(&tmem_full[as]);  // both CTAs' epilogues may drain their half
+                    } else {
+                        umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                        if (it == k_iters - 1) umma_commit(&tmem_full[as]);   // accumulator complete
+                    }
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -389,8 +462,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint64_t* res_full = res_full_all + g * kMaxRing;
         int* myrow_base = reinterpret_cast<int*>(smem + kSmemRowIdx) + g * 4 * kBlockM;
         const int bar_id = 1 + g;
-        const int tile_step = gridDim.x * ng;
-        const int tile_first = blockIdx.x + g * gridDim.x;
+        const int tile_step = cta_step * ng;
+        const int tile_first = cta_first + g * cta_step;
+        constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
+        const int m_rank_off = (int)cta_rank * kBlockM;
 
         // residual prefetch cursor (issuer only): runs `lead` chunks ahead of this group's consumption
         int pf_tile = tile_first, pf_chunk = 0;
@@ -400,7 +475,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int buf = pf_count % nb;
             mbar_expect_tx(&res_full[buf], kChunkBytes);
             tma_load_2d(ring + buf * kChunkBytes, &tmap_res, &res_full[buf],
-                        p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kBlockM);
+                        p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kTileM + m_rank_off);
             ++pf_count;
             if (++pf_chunk == kChunks) { pf_chunk = 0; pf_tile += tile_step; }
         };
@@ -412,7 +487,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int tile = tile_first; tile < num_tiles; tile += tile_step, it_tile += ng) {
             const int as = it_tile % kAcc;
             int* myrow = myrow_base + ((it_tile / ng) & 1) * 2 * kBlockM;   // double-buffered: a fast thread may be one tile ahead
-            const int m0 = (tile / p.num_n_tiles) * kBlockM;
+            const int m0 = (tile / p.num_n_tiles) * kTileM + m_rank_off;
             const int m = m0 + r;
             const int n0 = (tile % p.num_n_tiles) * BN;
             // decode the pixel and decide whether the row is a real output (exact division by multiply-high)
@@ -541,16 +616,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above): hand it back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_leader(&tmem_empty[as]);   // the leader's MMA warp waits for both CTAs' epilogues
+                else mbar_arrive(&tmem_empty[as]);
+            }
         }
         if (issuer && any_tma) bulk_wait_all();             // smem must outlive the last TMA store
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();     // neither CTA frees TMEM / exits while its peer may still signal or read
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (CTA2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 

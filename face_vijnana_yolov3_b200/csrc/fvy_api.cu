@@ -131,6 +131,7 @@ struct Layer {
     ConvSpec s;
     int Hin, Win, Hout, Wout;
     int BN, BK, stages, num_n_tiles, cout_pad, cin_pad, taps, occ;
+    bool cta2 = false;            // CTA pair (cta_group::2): 256-row tiles, each CTA stages half of the B tile
     size_t smem_bytes;
     __nv_bfloat16* w = nullptr;   // [cout_pad][taps * cin_pad]
     float* bias = nullptr;        // [cout_pad]
@@ -203,26 +204,36 @@ static uint16_t f32_to_bf16_rn(float f) {
     return (uint16_t)(u >> 16);
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool CTA2>
 static int launch_conv_t(fvy_handle* h, Layer& L, int grid) {
-    auto kern = conv_igemm_kernel<BN, BK>;   // max dynamic smem was raised in query_occ_t at plan time
+    auto kern = conv_igemm_kernel<BN, BK, CTA2>;   // max dynamic smem was raised in query_occ_t at plan time
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = h->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous layer's tail
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = h->use_pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (h->use_pdl) {   // PDL: prologue overlaps the previous layer's tail
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (CTA2) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.tmap_a, L.tmap_b, L.tmap_res, L.tmap_out[0], L.tmap_out[1], L.p, L.stages));
     ++h->launches;
     return FVY_OK;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool CTA2>
 static int query_occ_t(size_t smem, int* occ) {
-    auto kern = conv_igemm_kernel<BN, BK>;
+    auto kern = conv_igemm_kernel<BN, BK, CTA2>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (CTA2) { *occ = 1; return FVY_OK; }
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem));
     return FVY_OK;
 }
@@ -231,25 +242,27 @@ static int query_occ_t(size_t smem, int* occ) {
     do {                                                                              \
         if (BKv == 64) {                                                              \
             switch (BNv) {                                                            \
-                case 32: return CALL(32, 64); case 64: return CALL(64, 64);           \
-                case 128: return CALL(128, 64); case 256: return CALL(256, 64);       \
+                case 32: return CALL(32, 64, false); case 64: return CALL(64, 64, false);           \
+                case 128: return CALL(128, 64, false); case 256: return CALL(256, 64, false);       \
             }                                                                         \
         } else {                                                                      \
             switch (BNv) {                                                            \
-                case 32: return CALL(32, 32); case 64: return CALL(64, 32);           \
-                case 128: return CALL(128, 32); case 256: return CALL(256, 32);       \
+                case 32: return CALL(32, 32, false); case 64: return CALL(64, 32, false);           \
+                case 128: return CALL(128, 32, false); case 256: return CALL(256, 32, false);       \
             }                                                                         \
         }                                                                             \
         return fail(FVY_E_INVALID, "no kernel instance for tile N=%d K=%d", BNv, BKv); \
     } while (0)
 
 static int launch_conv(fvy_handle* h, Layer& L, int grid) {
-#define CALL(bn, bk) launch_conv_t<bn, bk>(h, L, grid)
+    if (L.cta2) return launch_conv_t<256, 64, true>(h, L, grid);
+#define CALL(bn, bk, c2) launch_conv_t<bn, bk, c2>(h, L, grid)
     FVY_DISPATCH(L.BN, L.BK, CALL);
 #undef CALL
 }
-static int query_occ(int BN, int BK, size_t smem, int* occ) {
-#define CALL(bn, bk) query_occ_t<bn, bk>(smem, occ)
+static int query_occ(int BN, int BK, bool cta2, size_t smem, int* occ) {
+    if (cta2) return query_occ_t<256, 64, true>(smem, occ);
+#define CALL(bn, bk, c2) query_occ_t<bn, bk, c2>(smem, occ)
     FVY_DISPATCH(BN, BK, CALL);
 #undef CALL
 }
@@ -334,7 +347,8 @@ static int build_plan(fvy_handle* h) {
         L.num_n_tiles = L.cout_pad / L.BN;
         int tps = (L.taps == 9 && L.cin_pad == L.BK && env_int("FVY_TPS", 3) == 3) ? 3 : 1;   // one filter row per stage when Cin fits one K chunk
         if (tps == 3 && (size_t)3 * 3 * (kBlockM + L.BN) * L.BK * 2 > 150 * 1024) tps = 1;              // needs >= 3 such stages next to the epilogue rings
-        const size_t stage_bytes = (size_t)tps * (kBlockM + L.BN) * L.BK * 2;
+        L.cta2 = !stem && L.BN == 256 && L.BK == 64 && env_int("FVY_CTA2", 1) != 0;
+        const size_t stage_bytes = (size_t)tps * (kBlockM + (L.cta2 ? L.BN / 2 : L.BN)) * L.BK * 2;
         // Layers with a short K loop are epilogue-bound: two epilogue groups alternate tiles.  Deep-K layers keep one
         // group so that the shared memory goes to the operand pipeline instead of a second staging ring.
         const int k_iters = (L.taps / tps) * (L.cin_pad / L.BK);
@@ -347,13 +361,13 @@ static int build_plan(fvy_handle* h) {
         L.stages = (int)std::min<size_t>(std::min(kMaxStages, stages_cap), std::max<size_t>(2, budget / stage_bytes));
         L.smem_bytes = fixed + (size_t)L.stages * stage_bytes;
         if (L.smem_bytes > 232448) return fail(FVY_E_INVALID, "conv_%d: shared memory plan %zu exceeds 227 KB", s.idx, L.smem_bytes);
-        if (int e = query_occ(L.BN, L.BK, L.smem_bytes, &L.occ)) return e;
+        if (int e = query_occ(L.BN, L.BK, L.cta2, L.smem_bytes, &L.occ)) return e;
         L.occ = 1;   // 320 threads x ~140 registers: one CTA per SM; latency is hidden inside the CTA (stages, two epilogue groups)
         // operands
         const size_t kdim = (size_t)L.taps * L.cin_pad;
         if (int e = dev_alloc(h, (void**)&L.w, (size_t)L.cout_pad * kdim * 2, true)) return e;
         if (int e = dev_alloc(h, (void**)&L.bias, (size_t)L.cout_pad * 4, true)) return e;
-        if (int e = make_tmap_2d(&L.tmap_b, L.w, kdim, L.cout_pad, kdim, L.BK, L.BN)) return e;
+        if (int e = make_tmap_2d(&L.tmap_b, L.w, kdim, L.cout_pad, kdim, L.BK, L.cta2 ? L.BN / 2 : L.BN)) return e;
         ConvParams& p = L.p;
         memset(&p, 0, sizeof(p));
         p.num_taps = L.taps;
@@ -519,8 +533,13 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
         Layer& L = h->layers[i];
         L.p.m_total = batch * L.p.dom_plane;
         L.p.num_m_tiles = (L.p.m_total + kBlockM - 1) / kBlockM;
-        const int tiles = L.p.num_m_tiles * L.p.num_n_tiles;
-        const int grid = std::min(tiles, h->num_sms * L.occ);
+        int grid;
+        if (L.cta2) {
+            const int tiles = ((L.p.num_m_tiles + 1) / 2) * L.p.num_n_tiles;
+            grid = std::min(2 * tiles, h->num_sms & ~1);
+        } else {
+            grid = std::min(L.p.num_m_tiles * L.p.num_n_tiles, h->num_sms * L.occ);
+        }
         if (int e = launch_conv(h, L, grid)) return e;
     }
     return FVY_OK;
