@@ -100,6 +100,114 @@ __global__ void stem_im2col_kernel(const T* __restrict__ img, int batch, int H, 
     }
 }
 
+
+// Fused stem: conv_0 (3x3, pad 1, stride 1, 3 -> 32, BN folded, LeakyReLU(0.1)) straight from the fp32/fp64 image to the
+// bf16 4-phase activation that conv_1 (stride 2) reads.  yolov3_detect.py:221 (conv_0), :205 (ZeroPadding2D(1)), :212-213.
+// K = 27 and N = 32: 1.7 % of the network's FLOPs but its largest activation (11 MB / image), i.e. purely HBM-bound.
+// A tcgen05 tile (128 x 32, K = 32) carries too little math per TMEM / mbarrier round trip (measured 284 us + 156 us for
+// the im2col operand), so this layer keeps everything in registers: each warp owns 16 consecutive pixels of one image
+// row, gathers its A fragment directly from the image (the 3x9 window rows are contiguous in NHWC), runs 8 warp-level
+// bf16 MMAs (m16n8k16, fp32 accumulate), and transposes the result inside each quad so that every lane stores 16
+// contiguous bytes.  Traffic: image read once (L1 catches the window overlap) + output written once.
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax,
+                                                        const __nv_bfloat16* __restrict__ wgt /*[32][32] k-major*/,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*4-phase*/) {
+    const int lane = threadIdx.x & 31, quad = lane & 3, grp = lane >> 2;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // B fragments (weights) and bias stay in registers for the whole kernel
+    uint32_t bfrag[4][2][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(wgt + (j * 8 + grp) * 32 + t * 16 + quad * 2);
+            bfrag[j][t][0] = __ldg(wr);
+            bfrag[j][t][1] = __ldg(wr + 4);
+        }
+    float bia[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bia[j][0] = __ldg(bias + j * 8 + quad * 2); bia[j][1] = __ldg(bias + j * 8 + quad * 2 + 1); }
+    const int tiles_per_row = W >> 4;
+    const long long total_tiles = (long long)batch * H * tiles_per_row;
+    const int pw = (W >> 1) + 1;
+    const long long plane = (long long)((H >> 1) + 1) * pw;
+    for (long long tile = warp_id; tile < total_tiles; tile += warps_total) {
+        const int tx = (int)(tile % tiles_per_row);
+        const long long t2 = tile / tiles_per_row;
+        const int h = (int)(t2 % H);
+        const long long n = t2 / H;
+        const int w0 = tx << 4;
+        // A fragment: rows grp and grp+8 of the tile, k = kstep*16 + quad*2 + {0,1} (+8)
+        uint32_t afrag[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int half = 0; half < 2; ++half)      // k offset 0 / 8
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {       // row grp / grp + 8
+                    const int wpix = w0 + grp + rr * 8;
+                    float v[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = ks * 16 + half * 8 + quad * 2 + e;
+                        float x = 0.f;
+                        if (k < 27) {
+                            const int r = k / 9, j = k - r * 9;          // window row, element (s*3 + c) of the 9 contiguous floats
+                            const int hh = h + r - 1, ww = wpix - 1 + j / 3;
+                            if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
+                                x = (float)__ldg(img + ((n * H + hh) * W + ww) * 3 + (j % 3));
+                        }
+                        v[e] = x;
+                    }
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
+                    afrag[ks][half * 2 + rr] = *reinterpret_cast<uint32_t*>(&pk);
+                }
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+            mma_m16n8k16_bf16(acc[j], afrag[0], bfrag[j][0][0], bfrag[j][0][1]);
+            mma_m16n8k16_bf16(acc[j], afrag[1], bfrag[j][1][0], bfrag[j][1][1]);
+        }
+        // bias + LeakyReLU, pack: word[rr][j] = channels j*8 + quad*2 + {0,1} of row grp + 8*rr
+        uint32_t word[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float a = acc[j][rr * 2 + 0] + bia[j][0], b = acc[j][rr * 2 + 1] + bia[j][1];
+                a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
+                __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
+                word[rr][j] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+        // quad transpose: lane `quad` ends up with the 4 words of n-tile `quad` (channels 8*quad .. 8*quad+7)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int sel = quad ^ i;                     // the word this lane hands to lane (quad ^ i)
+                const uint32_t give = sel == 0 ? word[rr][0] : sel == 1 ? word[rr][1] : sel == 2 ? word[rr][2] : word[rr][3];
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, give, i);   // from lane quad ^ i: its word for n-tile `quad`
+                // `got` holds channels 8*quad + 2*(quad ^ i) + {0,1}
+                if ((quad ^ i) == 0) o[0] = got; else if ((quad ^ i) == 1) o[1] = got; else if ((quad ^ i) == 2) o[2] = got; else o[3] = got;
+            }
+            const int wpix = w0 + grp + rr * 8;
+            const int hp = h + 1, wp = wpix + 1;
+            const long long row = ((long long)((((hp & 1) << 1) | (wp & 1))) * nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
+            *reinterpret_cast<uint4*>(out + row * 32 + quad * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 // Debug / parity aid: stored activation -> dense NHWC fp32.
 __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float* __restrict__ dst) {
     const long long total = (long long)batch * H * W * C;
@@ -158,6 +266,8 @@ struct fvy_handle {
     std::vector<void*> allocs;
     bool weights_loaded = false;
     bool use_pdl = true;
+    bool fused_stem = true;              // conv_0 straight from the image (stem_conv_kernel) instead of im2col + GEMM
+    const void* cur_img = nullptr; int cur_dtype = FVY_F32;   // device image of the current forward (layer 0 re-runs)
     long long launches = 0;
     long long weight_count = 0;
     // forward
@@ -293,7 +403,12 @@ static int build_plan(fvy_handle* h) {
         if (int e = dev_alloc(h, (void**)&catB, (size_t)nmax * (H + 2) * (W + 2) * 384 * 2, true)) return e;
     }
     // stem operand
-    if (int e = dev_alloc(h, (void**)&h->d_stem, (size_t)nmax * c.net_h * c.net_w * 32 * 2, false)) return e;
+    {
+        const char* v = getenv("FVY_FUSED_STEM");
+        h->fused_stem = !(v && *v && atoi(v) == 0);
+    }
+    if (!h->fused_stem)
+        if (int e = dev_alloc(h, (void**)&h->d_stem, (size_t)nmax * c.net_h * c.net_w * 32 * 2, false)) return e;
     // activation buffers
     for (const ConvSpec& s : specs) {
         int H, W;
@@ -321,7 +436,7 @@ static int build_plan(fvy_handle* h) {
     const int bn_res_cap = std::min(bn_cap, env_int("FVY_BN_RES", 256));
     const int nb_res = env_int("FVY_NB_RES", 6), lead_res = env_int("FVY_LEAD", 4), nb_plain = env_int("FVY_NB", 3);
     const int stages_cap = env_int("FVY_STAGES", kMaxStages);
-    const int groups_kn = env_int("FVY_GROUPS_KN", 40);   // (K iterations x 32-column chunks) at or below which a layer gets two epilogue groups
+    const int groups_kn = env_int("FVY_GROUPS_KN", 150);   // (K iterations x 32-column chunks) at or below which a layer gets two epilogue groups
     h->use_pdl = env_int("FVY_PDL", 1) != 0;
     size_t stream_off = 0;
     int head_i = 0;
@@ -381,7 +496,8 @@ static int build_plan(fvy_handle* h) {
         const void* a_base = nullptr;
         uint64_t a_rows = 0, a_pitch = 0;
         if (stem) {
-            a_base = h->d_stem; a_rows = (uint64_t)nmax * L.Hin * L.Win; a_pitch = 32;
+            if (h->fused_stem) { a_base = L.w; a_rows = (uint64_t)L.cout_pad; a_pitch = 32; }   // placeholder map: conv_0 runs in stem_conv_kernel
+            else { a_base = h->d_stem; a_rows = (uint64_t)nmax * L.Hin * L.Win; a_pitch = 32; }
             p.dom_plane = L.Hin * L.Win; p.dom_w = L.Win; p.dom_off = 0; p.tap_off[0] = 0;
         } else if (s.stride == 2) {
             const int Ho = L.Hout, Wo = L.Wout;
@@ -531,6 +647,20 @@ static int stage_input(fvy_handle* h, const void* images, int dtype, int batch, 
 static int run_layers(fvy_handle* h, int batch, int first, int last) {
     for (int i = first; i < last; ++i) {
         Layer& L = h->layers[i];
+        if (L.s.src == -1 && h->fused_stem) {
+            if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
+            const int blocks = h->num_sms * 8;
+            if (h->cur_dtype == FVY_F32)
+                stem_conv_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
+                                                                       L.w, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
+            else
+                stem_conv_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
+                                                                        L.w, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
+            CUDA_TRY(cudaGetLastError());
+            ++h->launches;
+            if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
+            continue;
+        }
         L.p.m_total = batch * L.p.dom_plane;
         L.p.num_m_tiles = (L.p.m_total + kBlockM - 1) / kBlockM;
         int grid;
@@ -551,15 +681,18 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
     if (dtype != FVY_F32 && dtype != FVY_F64) return fail(FVY_E_INVALID, "dtype %d", dtype);
     const void* dimg = nullptr;
     if (int e = stage_input(h, images, dtype, batch, &dimg)) return e;
-    const long long pix = (long long)batch * h->cfg.net_h * h->cfg.net_w;
-    const int blocks = (int)std::min<long long>((pix + 255) / 256, (long long)h->num_sms * 16);
-    if (dtype == FVY_F32)
-        stem_im2col_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
-    else
-        stem_im2col_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
-    CUDA_TRY(cudaGetLastError());
-    ++h->launches;
-    if (h->last_slot >= 0) CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream));
+    h->cur_img = dimg; h->cur_dtype = dtype;
+    if (!h->fused_stem) {
+        const long long pix = (long long)batch * h->cfg.net_h * h->cfg.net_w;
+        const int blocks = (int)std::min<long long>((pix + 255) / 256, (long long)h->num_sms * 16);
+        if (dtype == FVY_F32)
+            stem_im2col_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
+        else
+            stem_im2col_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)dimg, batch, h->cfg.net_h, h->cfg.net_w, h->d_stem);
+        CUDA_TRY(cudaGetLastError());
+        ++h->launches;
+        if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
+    }
     return run_layers(h, batch, 0, (int)h->layers.size());
 }
 
