@@ -119,9 +119,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax,
                                                         const __nv_bfloat16* __restrict__ wgt /*[32][32] k-major*/,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*4-phase*/) {
-    const int lane = threadIdx.x & 31, quad = lane & 3, grp = lane >> 2;
+    __shared__ __align__(16) uint32_t stile[8][16][20];     // per warp: 16 pixels x 32 bf16 (16 words) + 4 words of padding
+    const int lane = threadIdx.x & 31, quad = lane & 3, grp = lane >> 2, wib = threadIdx.x >> 5;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
-    const int warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int warp_id = blockIdx.x * (blockDim.x >> 5) + wib;
     // B fragments (weights) and bias stay in registers for the whole kernel
     uint32_t bfrag[4][2][2];
 #pragma unroll
@@ -136,74 +137,85 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const T* __restrict__ im
 #pragma unroll
     for (int j = 0; j < 4; ++j) { bia[j][0] = __ldg(bias + j * 8 + quad * 2); bia[j][1] = __ldg(bias + j * 8 + quad * 2 + 1); }
     const int tiles_per_row = W >> 4;
-    const long long total_tiles = (long long)batch * H * tiles_per_row;
+    const int total_tiles = batch * H * tiles_per_row;      // < 2^31 (checked on the host)
     const int pw = (W >> 1) + 1;
     const long long plane = (long long)((H >> 1) + 1) * pw;
-    for (long long tile = warp_id; tile < total_tiles; tile += warps_total) {
-        const int tx = (int)(tile % tiles_per_row);
-        const long long t2 = tile / tiles_per_row;
-        const int h = (int)(t2 % H);
-        const long long n = t2 / H;
+    // Per-lane gather table: the 8 K indices this lane feeds (k = ks*16 + half*8 + quad*2 + e) never change, so their
+    // element offsets relative to the centre pixel and their edge sensitivities are computed once.
+    int koff[8];
+    unsigned m_top = 0, m_bot = 0, m_left = 0, m_right = 0, m_none = 0;   // bit i: load i must be skipped at that image edge
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = (i >> 2) * 16 + ((i >> 1) & 1) * 8 + quad * 2 + (i & 1);
+        const int r = k / 9, j = k - r * 9, dx = j / 3 - 1, dr = r - 1, c = j - (j / 3) * 3;
+        koff[i] = k < 27 ? (dr * W + dx) * 3 + c : 0;       // k >= 27: any valid address (the weight row is zero and the value is masked)
+        if (k >= 27) m_none |= 1u << i;
+        if (dr < 0) m_top |= 1u << i;
+        if (dr > 0) m_bot |= 1u << i;
+        if (dx < 0) m_left |= 1u << i;
+        if (dx > 0) m_right |= 1u << i;
+    }
+    for (int tile = warp_id; tile < total_tiles; tile += warps_total) {
+        const int t2 = tile / tiles_per_row;
+        const int tx = tile - t2 * tiles_per_row;
+        const int n = t2 / H;
+        const int h = t2 - n * H;
         const int w0 = tx << 4;
-        // A fragment: rows grp and grp+8 of the tile, k = kstep*16 + quad*2 + {0,1} (+8)
+        // A fragment: rows grp and grp+8 of the tile; register (ks, half*2 + rr) holds k = ks*16 + half*8 + quad*2 + {0,1}
         uint32_t afrag[2][4];
+        const unsigned skip_h = m_none | (h == 0 ? m_top : 0u) | (h == H - 1 ? m_bot : 0u);
+        const T* centre0 = img + ((long long)(n * H + h) * W + w0 + grp) * 3;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+        for (int rr = 0; rr < 2; ++rr) {
+            const int wpix = w0 + grp + rr * 8;
+            const unsigned skip = skip_h | (wpix == 0 ? m_left : 0u) | (wpix == W - 1 ? m_right : 0u);
+            const T* centre = centre0 + rr * 24;
+            float v[8];
+            if (skip == m_none) {       // interior pixel (the common case): unconditional loads
 #pragma unroll
-            for (int half = 0; half < 2; ++half)      // k offset 0 / 8
+                for (int i = 0; i < 8; ++i) v[i] = (float)__ldg(centre + koff[i]);
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {       // row grp / grp + 8
-                    const int wpix = w0 + grp + rr * 8;
-                    float v[2];
+                for (int i = 0; i < 8; ++i) if ((m_none >> i) & 1u) v[i] = 0.f;
+            } else {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = ks * 16 + half * 8 + quad * 2 + e;
-                        float x = 0.f;
-                        if (k < 27) {
-                            const int r = k / 9, j = k - r * 9;          // window row, element (s*3 + c) of the 9 contiguous floats
-                            const int hh = h + r - 1, ww = wpix - 1 + j / 3;
-                            if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
-                                x = (float)__ldg(img + ((n * H + hh) * W + ww) * 3 + (j % 3));
-                        }
-                        v[e] = x;
-                    }
-                    __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
+                for (int i = 0; i < 8; ++i) v[i] = ((skip >> i) & 1u) ? 0.f : (float)__ldg(centre + koff[i]);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(v[ks * 4 + half * 2], v[ks * 4 + half * 2 + 1]);
                     afrag[ks][half * 2 + rr] = *reinterpret_cast<uint32_t*>(&pk);
                 }
+        }
+        // accumulators start at the bias (BN folded): saves the separate add
         float acc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+            acc[j][0] = acc[j][2] = bia[j][0];
+            acc[j][1] = acc[j][3] = bia[j][1];
             mma_m16n8k16_bf16(acc[j], afrag[0], bfrag[j][0][0], bfrag[j][0][1]);
             mma_m16n8k16_bf16(acc[j], afrag[1], bfrag[j][1][0], bfrag[j][1][1]);
         }
-        // bias + LeakyReLU, pack: word[rr][j] = channels j*8 + quad*2 + {0,1} of row grp + 8*rr
-        uint32_t word[2][4];
+        // LeakyReLU, pack, transpose through shared memory: lane (grp, quad) then owns 16 contiguous bytes of pixel grp / grp+8
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-                float a = acc[j][rr * 2 + 0] + bia[j][0], b = acc[j][rr * 2 + 1] + bia[j][1];
+                float a = acc[j][rr * 2 + 0], b = acc[j][rr * 2 + 1];
                 a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
                 __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
-                word[rr][j] = *reinterpret_cast<uint32_t*>(&pk);
+                stile[wib][grp + rr * 8][j * 4 + quad] = *reinterpret_cast<uint32_t*>(&pk);
             }
-        // quad transpose: lane `quad` ends up with the 4 words of n-tile `quad` (channels 8*quad .. 8*quad+7)
+        __syncwarp();
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            uint32_t o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int sel = quad ^ i;                     // the word this lane hands to lane (quad ^ i)
-                const uint32_t give = sel == 0 ? word[rr][0] : sel == 1 ? word[rr][1] : sel == 2 ? word[rr][2] : word[rr][3];
-                const uint32_t got = __shfl_xor_sync(0xffffffffu, give, i);   // from lane quad ^ i: its word for n-tile `quad`
-                // `got` holds channels 8*quad + 2*(quad ^ i) + {0,1}
-                if ((quad ^ i) == 0) o[0] = got; else if ((quad ^ i) == 1) o[1] = got; else if ((quad ^ i) == 2) o[2] = got; else o[3] = got;
-            }
+            const uint4 o = *reinterpret_cast<const uint4*>(&stile[wib][grp + rr * 8][quad * 4]);
             const int wpix = w0 + grp + rr * 8;
             const int hp = h + 1, wp = wpix + 1;
             const long long row = ((long long)((((hp & 1) << 1) | (wp & 1))) * nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
-            *reinterpret_cast<uint4*>(out + row * 32 + quad * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(out + row * 32 + quad * 8) = o;
         }
     }
 }
