@@ -44,7 +44,12 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
+    def mark(self):
+        """Samples read so far are discarded when the summary is made (they precede the load)."""
+        self.first = len(self.rows)
+
     def start(self):
+        self.first = 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,10 +70,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -180,18 +186,25 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput (`value`)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a moment to come up: start it before the warm-up
     for _ in range(args.warmup):
         eng.detect(x_dev, pp=pp, image_hw=hw_dev, max_out=max_out, dets=dets_dev, counts=cnt_dev, sync=False)
     eng.sync()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     launches0 = eng.launch_count
     eng.timer_start()
     for _ in range(args.steps):
         eng.detect(x_dev, pp=pp, image_hw=hw_dev, max_out=max_out, dets=dets_dev, counts=cnt_dev, sync=False)
     ms_total = eng.timer_stop()
     launches = eng.launch_count - launches0
+    # the timed region can be shorter than one nvidia-smi period: keep the same load running (untimed) until a few samples exist
+    t_tail = time.perf_counter()
+    while len(sampler.rows) - sampler.first < 5 and time.perf_counter() - t_tail < 3.0:
+        for _ in range(5):
+            eng.detect(x_dev, pp=pp, image_hw=hw_dev, max_out=max_out, dets=dets_dev, counts=cnt_dev, sync=False)
+        eng.sync()
     barrier()
     clocks = sampler.stop()
     ms_total = max_over_ranks(ms_total)

@@ -67,7 +67,7 @@ struct ConvParams {
     int num_taps;
     int k_chunks;        // K chunks (of BLOCK_K channels) per tap
     int a_choff;         // first channel of the A buffer
-    int tap_off[9];      // row shift per tap
+    int tap_off[9];      // row shift per tap (slab: the shift of the slab's first row = tap (g, 0))
     int m_total;         // rows of the compute domain = batch * dom_plane
     int dom_plane;       // rows per image in the compute domain
     int dom_w;           // row pitch (pixels) of the compute domain
@@ -80,9 +80,19 @@ struct ConvParams {
     int res_pitch, res_choff;
     unsigned long long magic_plane, magic_w;   // ceil(2^64 / dom_plane), ceil(2^64 / dom_w): exact division by __umul64hi
     int epi_groups;      // 1 or 2 epilogue warp groups (2: tiles alternate between them)
-    int tps;             // taps per operand stage (1, or 3 when k_chunks == 1): fewer barrier round trips per tile
-    int nb;              // staging buffers in EACH group's epilogue ring (3..8)
+    int nb;              // staging buffers in EACH group's epilogue ring (2..8)
+    int epi_split;       // 1: both groups drain every tile, split by columns (short drain latency); 0: tiles alternate between the groups
     int lead;            // residual prefetch distance in chunks, 2 <= lead <= nb-1
+    // Operand pipeline: two independent shared-memory rings.  The K loop runs over (filter row g, K chunk kc, column tap t);
+    // an A slot serves a_cover consecutive taps, a B slot b_cover.
+    int gt;              // taps per filter row: 3 (3x3) or 1 (1x1, stem)
+    int a_slab;          // 1: an A slot is ONE box of slab_rows rows; tap t reads it at a row shift of t (stride-1 3x3 convs)
+    int a_cover;         // taps served by one A slot (slab: gt; separate tiles: 1 or gt)
+    int a_stages;
+    int b_cover;         // taps per B slot (1 or gt)
+    int b_stages;
+    int b_resident;      // 1: the B ring holds the whole [BN, K] weight tile of this CTA; loaded once, never released
+    unsigned long long* dbg;   // profiling aid (FVY_DBG): per CTA 8 cycle counters, or nullptr
     OutDesc out[2];
 };
 
@@ -279,6 +289,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     constexpr uint64_t layout = (BK == 64) ? 2 : 4;
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+// The swizzle XOR is a function of the shared-memory ADDRESS bits (measured on B200, profiles/README.md "slab experiment"):
+// a descriptor whose start address lies a few rows into a TMA-written, 1024-byte aligned slab reads exactly the rows
+// start + i * row_bytes with the pattern TMA wrote them in, with the base-offset field left 0 (setting it to
+// (address >> 7) & 7 double-counts the phase and returns garbage).  That is what lets the three column taps of a filter
+// row share one A slab: tap t is the same slab at a start address of t rows further.
+template <int BK>
+__host__ __device__ constexpr int slab_rows() { return BK == 64 ? 136 : 144; }   // 128 + 2, rounded so that the slab is a multiple of 1024 bytes
 
 // Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1),
 // A and B K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -290,19 +307,22 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 // Kernel
 // ----------------------------------------------------------------------------------------------
 constexpr int kBlockM = 128;
-constexpr int kThreads = 320;
+constexpr int kThreads = 416;      // warps: 0 A producer, 1 MMA issuer, 2-5 / 6-9 epilogue groups, 10 B producer, 11 / 12 store warps of the groups
+constexpr int kBProducerWarp = 10;
+constexpr int kStoreWarp0 = 11;
 constexpr int kEpiThreads = 128;
-constexpr int kMaxStages = 20;
+constexpr int kMaxA = 16;       // A ring slots
+constexpr int kMaxB = 32;       // B ring slots
 constexpr int kMaxRing = 8;
 constexpr int kMaxAcc = 4;
 constexpr int kChunkBytes = kBlockM * 32 * 2;      // one staged chunk: 128 rows x 32 bf16 = 8 KB
 constexpr int kMaxCout = 1024;
 
 // Shared-memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int kSmemBarriers = 0;                    // full[20] empty[20] tmem_full[4] tmem_empty[4] res_full[2][8] tmem_ptr (520 B)
-constexpr int kSmemBias = 1024;                     // kMaxCout floats
+constexpr int kSmemBarriers = 0;                    // a_full[16] a_empty[16] b_full[32] b_empty[32] tmem_full[4] tmem_empty[4] res_full[2][8] staged[2][8] buf_free[2][8] tmem_ptr (1220 B)
+constexpr int kSmemBias = 2048;                     // kMaxCout floats
 constexpr int kSmemRowIdx = kSmemBias + kMaxCout * 4;        // int rowidx[2 groups][2 tile parities][2 outputs][128]
-constexpr int kSmemRing = kSmemRowIdx + 2 * 2 * 2 * kBlockM * 4; // = 9216, 1024-aligned
+constexpr int kSmemRing = kSmemRowIdx + 2 * 2 * 2 * kBlockM * 4; // = 10240, 1024-aligned
 static_assert(kSmemRing % 1024 == 0, "staging ring must keep the 512-byte swizzle phase");
 
 template <int BN, int BK>
@@ -318,11 +338,87 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// State handed to the MMA issue loop (one thread per CTA / CTA pair).
+struct MmaCtx {
+    uint64_t *a_full, *a_empty, *b_full, *b_empty, *tmem_full, *tmem_empty;
+    uint64_t desc_hi;
+    uint32_t a_ring16, b_ring16, a_slot16, b_slot16, a_tap16, b_tap16;   // shared-memory addresses / strides in 16-byte units
+    uint32_t tmem_base;
+    int a_stages, b_stages, units, first, step, num_tiles;
+    bool bres, bo;
+    unsigned long long* dbg;
+};
+
+// K loop of one role thread: `units` x GT taps per tile; an A slot serves ACOV taps, a B slot BCOV (compile-time so that the
+// per-tap path is a wait, BK/16 MMAs and a commit with no address arithmetic beyond two adds).
+template <int BN, int BK, bool CTA2, int GT, int ACOV, int BCOV>
+__device__ __forceinline__ void mma_issue(const MmaCtx& c) {
+    constexpr int kAcc = acc_stages(BN);
+    constexpr uint32_t kIdesc = make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, BN);
+    int as_ = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_ph = 0;
+    bool first = true;
+    long long dbg_full = 0, dbg_tmem = 0, dbg_taps = 0;
+    const long long dbg_t0 = c.dbg ? clock64() : 0;
+    for (int tile = c.first; tile < c.num_tiles; tile += c.step) {
+        long long c0 = c.dbg ? clock64() : 0;
+        mbar_wait(&c.tmem_empty[acc], acc_ph ^ 1, c.bo);
+        if (c.dbg) dbg_tmem += clock64() - c0;
+        const uint32_t tmem_d = c.tmem_base + acc * BN;
+        uint32_t accum = 0;
+        uint64_t da0 = 0, db0 = 0;
+#pragma unroll 1
+        for (int u = 0; u < c.units; ++u) {
+#pragma unroll
+            for (int t = 0; t < GT; ++t) {
+                if (c.dbg) c0 = clock64();
+                if (t % ACOV == 0) {
+                    mbar_wait(&c.a_full[as_], aph, c.bo);
+                    da0 = c.desc_hi | (uint64_t)(c.a_ring16 + (uint32_t)as_ * c.a_slot16);
+                }
+                if (t % BCOV == 0) {
+                    if (first || !c.bres) mbar_wait(&c.b_full[bs], bph, c.bo);
+                    db0 = c.desc_hi | (uint64_t)(c.b_ring16 + (uint32_t)bs * c.b_slot16);
+                }
+                if (c.dbg) dbg_full += clock64() - c0;
+                tc_fence_after();
+                const uint64_t da = da0 + (uint32_t)(t % ACOV) * c.a_tap16, db = db0 + (uint32_t)(t % BCOV) * c.b_tap16;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                    if constexpr (CTA2) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, kIdesc, accum);
+                    else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, accum);
+                    accum = 1;
+                }
+                if (t % BCOV == BCOV - 1) {
+                    if (!c.bres) {                          // frees the slot (in both CTAs of a pair) when these MMAs retire
+                        if constexpr (CTA2) umma_commit_pair(&c.b_empty[bs]); else umma_commit(&c.b_empty[bs]);
+                    }
+                    if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
+                }
+                if (t % ACOV == ACOV - 1) {
+                    if constexpr (CTA2) umma_commit_pair(&c.a_empty[as_]); else umma_commit(&c.a_empty[as_]);
+                    if (++as_ == c.a_stages) { as_ = 0; aph ^= 1; }
+                }
+            }
+        }
+        // accumulator complete (CTA2: both CTAs' epilogues may drain their half)
+        if constexpr (CTA2) umma_commit_pair(&c.tmem_full[acc]); else umma_commit(&c.tmem_full[acc]);
+        if (++acc == kAcc) { acc = 0; acc_ph ^= 1; }
+        first = false;
+        dbg_taps += (long long)c.units * GT;
+    }
+    if (c.dbg) {
+        c.dbg[0] = (unsigned long long)(clock64() - dbg_t0); c.dbg[1] = (unsigned long long)dbg_full; c.dbg[2] = (unsigned long long)dbg_tmem;
+        c.dbg[3] = (unsigned long long)dbg_taps;
+    }
+}
+
 template <int BN, int BK, bool CTA2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out0,
-                  const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ ConvParams p, const int num_stages) {
+                  const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ ConvParams p) {
     using L = SmemLayout<BN, BK>;
     constexpr int kAcc = acc_stages(BN);
     constexpr uint32_t kTmemCols = kAcc * BN;                      // 128 / 256 / 256 / 512: a power of two >= 32
@@ -331,27 +427,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr int kChunks = BN / 32;
     constexpr int kABytes = L::a_bytes;
     constexpr int kBBytes = CTA2 ? L::b_bytes / 2 : L::b_bytes;
+    constexpr int kSlabBytes = slab_rows<BK>() * BK * 2;
+    constexpr int kRowBytes = BK * 2;
     const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
     const int cta_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // tiles advance by the number of clusters
     const int cta_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBarriers);   // [kMaxStages]
-    uint64_t* empty_bar = full_bar + kMaxStages;                               // [kMaxStages]
-    uint64_t* tmem_full = empty_bar + kMaxStages;                              // [kMaxAcc]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kSmemBarriers);     // [kMaxA]
+    uint64_t* a_empty = a_full + kMaxA;                                        // [kMaxA]
+    uint64_t* b_full = a_empty + kMaxA;                                        // [kMaxB]
+    uint64_t* b_empty = b_full + kMaxB;                                        // [kMaxB]
+    uint64_t* tmem_full = b_empty + kMaxB;                                     // [kMaxAcc]
     uint64_t* tmem_empty = tmem_full + kMaxAcc;                                // [kMaxAcc]
     uint64_t* res_full_all = tmem_empty + kMaxAcc;                             // [2][kMaxRing]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_all + 2 * kMaxRing);
+    uint64_t* staged_all = res_full_all + 2 * kMaxRing;                       // [2][kMaxRing]  chunk written by the 128 epilogue threads
+    uint64_t* free_all = staged_all + 2 * kMaxRing;                            // [2][kMaxRing]  staging buffer may be overwritten
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(free_all + 2 * kMaxRing);
     float* sbias = reinterpret_cast<float*>(smem + kSmemBias);
     uint8_t* ring_all = smem + kSmemRing;
-    uint8_t* tiles = ring_all + p.epi_groups * p.nb * kChunkBytes;
+    const int a_slot_bytes = p.a_slab ? kSlabBytes : p.a_cover * kABytes;
+    const int b_slot_bytes = p.b_cover * kBBytes;
+    uint8_t* a_ring = ring_all + p.epi_groups * p.nb * kChunkBytes;
+    uint8_t* b_ring = a_ring + p.a_stages * a_slot_bytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = (CTA2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;   // CTA2: tiles of 256 rows
-    const int k_iters = (p.num_taps / p.tps) * p.k_chunks;   // operand stages per tile
-    const int stage_bytes = p.tps * (kABytes + kBBytes);
+    const int row_groups = p.num_taps / p.gt;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -359,9 +463,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (p.res != nullptr) tma_prefetch_desc(&tmap_res);
         if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
         if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
-        for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CTA2 ? 8 : 4); }
-        for (int s = 0; s < 2 * kMaxRing; ++s) mbar_init(&res_full_all[s], 1);
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (CTA2 ? 8 : 4) * ((BN >= 64 && p.epi_groups == 2 && p.epi_split != 0) ? 2 : 1)); }
+        for (int s = 0; s < 2 * kMaxRing; ++s) { mbar_init(&res_full_all[s], 1); mbar_init(&staged_all[s], kEpiThreads); mbar_init(&free_all[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -376,75 +481,94 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     // Everything above touched no memory written by the previous layer; from here on we do.
+    // (Resident weights could be fetched before the wait; they are a few KB per CTA and overlap the first A loads anyway.)
     pdl_launch_dependents();
     pdl_wait();
 
+    // Three single-thread roles feed the tensor pipe: the A producer (warp 0), the B producer (warp 10) and the MMA issuer
+    // (warp 1).  Measured on B200 (tools/tma_bench.cu): one thread sustains one TMA instruction per ~170-250 cycles whatever
+    // the box size, independent threads scale linearly up to ~72 B/clk/SM with every SM loading - so A and B are issued by
+    // different warps, and every loop below keeps running counters instead of divisions.
+    const int taps_per_tile = p.num_taps * p.k_chunks;
+    const bool bres = p.b_resident != 0;
+
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== A producer =====================
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
+            int as_ = 0; uint32_t aph = 0;
+            const bool bo = p.epi_groups == 2;
+            const uint32_t tx = (CTA2 ? 2u : 1u) * (uint32_t)a_slot_bytes;   // CTA2: the leader's arrival expects the bytes of BOTH CTAs
+            const bool arrives = !CTA2 || cta_rank == 0;
+            const int a_loads = p.a_slab ? 1 : p.a_cover;
+            long long dbg_wait = 0;
             for (int tile = cta_first; tile < num_tiles; tile += cta_step) {
                 const int m0 = (tile / p.num_n_tiles) * (CTA2 ? 2 * kBlockM : kBlockM) + (int)cta_rank * kBlockM;
-                const int n0 = (tile % p.num_n_tiles) * BN + (CTA2 ? (int)cta_rank * (BN / 2) : 0);
-                for (int tap = 0; tap < p.num_taps; tap += p.tps) {
+                for (int tap0 = 0; tap0 < p.num_taps; tap0 += p.gt) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1, p.epi_groups == 2);
-                        uint8_t* sa = tiles + stage * stage_bytes;
-                        uint8_t* sb = sa + p.tps * kABytes;
-                        if constexpr (CTA2) {
-                            // one arrival (the leader's) per phase; it expects the bytes of BOTH CTAs, whose loads all signal the leader's barrier
-                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
-                            for (int t = 0; t < p.tps; ++t) {
-                                tma_load_2d_pair(sa + t * kABytes, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, m0 + p.tap_off[tap + t]);
-                                tma_load_2d_pair(sb + t * kBBytes, &tmap_b, &full_bar[stage], ((tap + t) * p.k_chunks + kc) * BK, n0);
+                        for (int t = 0; t < p.gt; t += p.a_cover) {
+                            const long long c0 = p.dbg ? clock64() : 0;
+                            mbar_wait(&a_empty[as_], aph ^ 1, bo);
+                            if (p.dbg) dbg_wait += clock64() - c0;
+                            uint8_t* sa = a_ring + as_ * a_slot_bytes;
+                            if (arrives) mbar_expect_tx(&a_full[as_], tx);
+                            for (int j = 0; j < a_loads; ++j) {
+                                if constexpr (CTA2) tma_load_2d_pair(sa + j * kABytes, &tmap_a, &a_full[as_], p.a_choff + kc * BK, m0 + p.tap_off[tap0 + t + j]);
+                                else tma_load_2d(sa + j * kABytes, &tmap_a, &a_full[as_], p.a_choff + kc * BK, m0 + p.tap_off[tap0 + t + j]);
                             }
-                        } else {
-                            mbar_expect_tx(&full_bar[stage], stage_bytes);
-                            for (int t = 0; t < p.tps; ++t) {
-                                tma_load_2d(sa + t * kABytes, &tmap_a, &full_bar[stage], p.a_choff + kc * BK, m0 + p.tap_off[tap + t]);
-                                tma_load_2d(sb + t * kBBytes, &tmap_b, &full_bar[stage], ((tap + t) * p.k_chunks + kc) * BK, n0);
-                            }
+                            if (++as_ == p.a_stages) { as_ = 0; aph ^= 1; }
                         }
-                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
+            if (p.dbg) p.dbg[blockIdx.x * 16 + 4] = (unsigned long long)dbg_wait;
+        }
+    } else if (warp == kBProducerWarp) {
+        // ===================== B producer (resident weights: the CTA's first tile only) =====================
+        if (elect_one()) {
+            int bs = 0; uint32_t bph = 0;
+            const bool bo = p.epi_groups == 2;
+            const uint32_t tx = (CTA2 ? 2u : 1u) * (uint32_t)b_slot_bytes;
+            const bool arrives = !CTA2 || cta_rank == 0;
+            long long dbg_wait = 0;
+            for (int tile = cta_first; tile < num_tiles; tile += cta_step) {
+                const int n0 = (tile % p.num_n_tiles) * BN + (CTA2 ? (int)cta_rank * (BN / 2) : 0);
+                for (int tap0 = 0; tap0 < p.num_taps; tap0 += p.gt) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        for (int t = 0; t < p.gt; t += p.b_cover) {
+                            const long long c0 = p.dbg ? clock64() : 0;
+                            if (!bres) mbar_wait(&b_empty[bs], bph ^ 1, bo);
+                            if (p.dbg) dbg_wait += clock64() - c0;
+                            uint8_t* sb = b_ring + bs * b_slot_bytes;
+                            if (arrives) mbar_expect_tx(&b_full[bs], tx);
+                            for (int j = 0; j < p.b_cover; ++j) {
+                                if constexpr (CTA2) tma_load_2d_pair(sb + j * kBBytes, &tmap_b, &b_full[bs], ((tap0 + t + j) * p.k_chunks + kc) * BK, n0);
+                                else tma_load_2d(sb + j * kBBytes, &tmap_b, &b_full[bs], ((tap0 + t + j) * p.k_chunks + kc) * BK, n0);
+                            }
+                            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                }
+                if (bres) break;
+            }
+            if (p.dbg) p.dbg[blockIdx.x * 16 + 5] = (unsigned long long)dbg_wait;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (CTA2: the leader CTA issues for the pair) =====================
         if ((!CTA2 || cta_rank == 0) && elect_one()) {
-            int stage = 0; uint32_t phase = 0;
-            uint32_t it_tile = 0;                                   // tiles issued by this CTA
-            for (int tile = cta_first; tile < num_tiles; tile += cta_step, ++it_tile) {
-                const int as = it_tile % kAcc;
-                mbar_wait(&tmem_empty[as], ((it_tile / kAcc) & 1) ^ 1, p.epi_groups == 2);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int it = 0; it < k_iters; ++it) {
-                    mbar_wait(&full_bar[stage], phase, p.epi_groups == 2);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
-                    const uint32_t sb = sa + p.tps * kABytes;
-                    for (int t = 0; t < p.tps; ++t) {
-                        const uint64_t da = make_smem_desc<BK>(sa + t * kABytes);
-                        const uint64_t db = make_smem_desc<BK>(sb + t * kBBytes);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                            if constexpr (CTA2) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | t | k) != 0);
-                            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (it | t | k) != 0);
-                        }
-                    }
-                    if constexpr (CTA2) {
-                        umma_commit_pair(&empty_bar[stage]);                      // frees the slot in both CTAs
-                        if (it == k_iters - 1) umma_commit_pair(&tmem_full[as]);  // both CTAs' epilogues may drain their half
-                    } else {
-                        umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
-                        if (it == k_iters - 1) umma_commit(&tmem_full[as]);   // accumulator complete
-                    }
-                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
-                }
-            }
+            MmaCtx c;
+            c.a_full = a_full; c.a_empty = a_empty; c.b_full = b_full; c.b_empty = b_empty; c.tmem_full = tmem_full; c.tmem_empty = tmem_empty;
+            c.desc_hi = make_smem_desc<BK>(0);
+            c.a_ring16 = (smem_u32(a_ring) & 0x3FFFF) >> 4; c.b_ring16 = (smem_u32(b_ring) & 0x3FFFF) >> 4;
+            c.a_slot16 = (uint32_t)a_slot_bytes >> 4; c.b_slot16 = (uint32_t)b_slot_bytes >> 4;
+            // slab: tap t is the slab read from t rows further (address-based swizzle, see slab_rows)
+            c.a_tap16 = (uint32_t)(p.a_slab ? kRowBytes : kABytes) >> 4; c.b_tap16 = (uint32_t)kBBytes >> 4;
+            c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.bres = bres; c.bo = p.epi_groups == 2;
+            c.tmem_base = tmem_base; c.units = taps_per_tile / p.gt;
+            c.first = cta_first; c.step = cta_step; c.num_tiles = num_tiles; c.dbg = p.dbg ? p.dbg + blockIdx.x * 16 : nullptr;
+            if (p.gt == 1) mma_issue<BN, BK, CTA2, 1, 1, 1>(c);
+            else if (p.a_cover == 1) mma_issue<BN, BK, CTA2, 3, 1, 1>(c);
+            else if (p.b_cover == 1) mma_issue<BN, BK, CTA2, 3, 3, 1>(c);
+            else mma_issue<BN, BK, CTA2, 3, 3, 3>(c);
         }
     } else if (warp < 2 + 4 * p.epi_groups) {
         // ===================== epilogue: group g = warps 2+4g .. 5+4g (128 threads) =====================
@@ -453,40 +577,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;               // row of the tile handled by this thread (TMEM lane)
         const int et = (threadIdx.x - 64) & (kEpiThreads - 1);   // 0..127 within the group
-        const bool issuer = et == 0;
         const bool has_res = p.res != nullptr;
-        const bool any_tma = p.out[0].tma || p.out[1].tma;
-        const int nb = p.nb, lead = p.lead;
+        const bool any_direct = (p.out[0].kind != OUT_NONE && p.out[0].kind != OUT_HEAD_F32 && !p.out[0].tma) ||
+                                (p.out[1].kind != OUT_NONE && p.out[1].kind != OUT_HEAD_F32 && !p.out[1].tma);
+        const int nb = p.nb;
         const uint32_t swz = (uint32_t)((r >> 1) & 3);          // 64-byte swizzle: 16-byte slot j of row r lives at slot j ^ swz
         uint8_t* ring = ring_all + g * nb * kChunkBytes;
         uint64_t* res_full = res_full_all + g * kMaxRing;
+        uint64_t* staged = staged_all + g * kMaxRing;
+        uint64_t* buf_free = free_all + g * kMaxRing;
         int* myrow_base = reinterpret_cast<int*>(smem + kSmemRowIdx) + g * 4 * kBlockM;
         const int bar_id = 1 + g;
-        const int tile_step = cta_step * ng;
-        const int tile_first = cta_first + g * cta_step;
+        // Two groups: tiles with >= 2 chunks are split by COLUMNS (group g drains chunks g, g+2, ...: half the drain latency per
+        // tile, which is what stays exposed at the end of a layer); single-chunk tiles (BN = 32) alternate between the groups.
+        const bool split = kChunks >= 2 && ng == 2 && p.epi_split != 0;
+        const int tile_step = split ? cta_step : cta_step * ng;
+        const int tile_first = split ? cta_first : cta_first + g * cta_step;
+        const int c_first = split ? g : 0, c_step = split ? 2 : 1;
         constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
         const int m_rank_off = (int)cta_rank * kBlockM;
 
-        // residual prefetch cursor (issuer only): runs `lead` chunks ahead of this group's consumption
-        int pf_tile = tile_first, pf_chunk = 0;
-        uint32_t pf_count = 0;
-        auto prefetch_res = [&]() {
-            if (pf_tile >= num_tiles) return;
-            const int buf = pf_count % nb;
-            mbar_expect_tx(&res_full[buf], kChunkBytes);
-            tma_load_2d(ring + buf * kChunkBytes, &tmap_res, &res_full[buf],
-                        p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kTileM + m_rank_off);
-            ++pf_count;
-            if (++pf_chunk == kChunks) { pf_chunk = 0; pf_tile += tile_step; }
-        };
-        if (has_res && issuer)
-            for (int i = 0; i < lead; ++i) prefetch_res();
-
         uint32_t cg = 0;                           // chunks consumed so far by this group
-        uint32_t it_tile = g;                      // index of the tile in this CTA's sequence (selects the accumulator stage)
-        for (int tile = tile_first; tile < num_tiles; tile += tile_step, it_tile += ng) {
+        int buf = 0; uint32_t buf_ph = 0;          // staging buffer of the current chunk and the phase of its barriers
+        const bool dbg_on = p.dbg != nullptr && et == 0 && g == 0;
+        long long dbg_e_tmem = 0, dbg_e_res = 0, dbg_e_bar = 0, dbg_e_tma = 0, dbg_e_ld = 0, dbg_e_body = 0; const long long dbg_e0 = dbg_on ? clock64() : 0;
+        uint32_t it_tile = split ? 0 : g;          // index of the tile in this CTA's sequence (selects the accumulator stage)
+        uint32_t my_tiles = 0;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, it_tile += (split ? 1 : ng), ++my_tiles) {
             const int as = it_tile % kAcc;
-            int* myrow = myrow_base + ((it_tile / ng) & 1) * 2 * kBlockM;   // double-buffered: a fast thread may be one tile ahead
+            int* myrow = myrow_base + (my_tiles & 1) * 2 * kBlockM;   // double-buffered: a fast thread may be one tile ahead
             const int m0 = (tile / p.num_n_tiles) * kTileM + m_rank_off;
             const int m = m0 + r;
             const int n0 = (tile % p.num_n_tiles) * BN;
@@ -517,18 +636,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 myrow[o * kBlockM + r] = ridx;
             }
-            mbar_wait(&tmem_full[as], (it_tile / kAcc) & 1);
+            { const long long c0 = dbg_on ? clock64() : 0;
+              mbar_wait(&tmem_full[as], (it_tile / kAcc) & 1);
+              if (dbg_on) dbg_e_tmem += clock64() - c0; }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c, ++cg) {
+            for (int c = c_first; c < kChunks; c += c_step, ++cg) {
                 const int c0 = c * 32;
-                const int buf = cg % nb;
                 uint8_t* sbuf = ring + buf * kChunkBytes;
                 uint4* myslot = reinterpret_cast<uint4*>(sbuf + r * 64);
                 uint32_t acc[32];
+                const long long tl0 = dbg_on ? clock64() : 0;
                 tmem_ld_32x32(taddr + c0, acc);
                 tmem_ld_wait();
+                if (dbg_on) dbg_e_ld += clock64() - tl0;
                 float v[32];
                 {
                     const float4* b4 = reinterpret_cast<const float4*>(sbias + n0 + c0);
@@ -545,8 +667,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
                 }
+                {   // the staging buffer is ours once the residual chunk has landed in it / once its previous contents have left
+                    const long long tq0 = dbg_on ? clock64() : 0;
+                    if (has_res) mbar_wait(&res_full[buf], buf_ph);
+                    else mbar_wait(&buf_free[buf], buf_ph ^ 1);
+                    if (dbg_on) dbg_e_res += clock64() - tq0;
+                }
                 if (has_res) {
-                    mbar_wait(&res_full[buf], (cg / nb) & 1);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 t = myslot[j ^ swz];
@@ -581,13 +708,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
                     myslot[j ^ swz] = pk;
                 }
-                if (any_tma || has_res) fence_proxy_async();   // generic-proxy smem writes -> visible to TMA
-                named_bar_sync(bar_id, kEpiThreads);
-                if (issuer) {
-                    if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + c0, m0);
-                    if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + c0, m0);
-                    if (any_tma) { bulk_commit(); bulk_wait_read(nb - lead); }   // the buffer of chunk cg + lead - nb has been read
-                    if (has_res) prefetch_res();                                 // ... so the residual of chunk cg + lead may land in it
+                if (dbg_on) dbg_e_body += clock64() - tl0;
+                if (any_direct) {   // the direct forms read rows staged by other threads
+                    const long long tq0 = dbg_on ? clock64() : 0;
+                    named_bar_sync(bar_id, kEpiThreads);
+                    if (dbg_on) dbg_e_bar += clock64() - tq0;
                 }
                 // remaining output forms: 4 threads per 64-byte row, 32 rows per pass
 #pragma unroll
@@ -612,6 +737,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         }
                     }
                 }
+                // hand the staged chunk to the store warp (generic-proxy writes -> visible to the async proxy first)
+                fence_proxy_async();
+                mbar_arrive(&staged[buf]);
+                if (++buf == nb) { buf = 0; buf_ph ^= 1; }
             }
             // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above): hand it back
             tc_fence_before();
@@ -621,7 +750,71 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 else mbar_arrive(&tmem_empty[as]);
             }
         }
-        if (issuer && any_tma) bulk_wait_all();             // smem must outlive the last TMA store
+        if (dbg_on) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16 + 8;
+            d[0] = (unsigned long long)(clock64() - dbg_e0); d[1] = (unsigned long long)dbg_e_tmem; d[2] = (unsigned long long)dbg_e_res;
+            d[3] = (unsigned long long)dbg_e_bar; d[4] = (unsigned long long)dbg_e_tma; d[5] = cg; d[6] = (unsigned long long)dbg_e_ld; d[7] = (unsigned long long)dbg_e_body;
+        }
+    } else if (warp >= kStoreWarp0 && warp < kStoreWarp0 + p.epi_groups) {
+        // ===================== store warp of epilogue group g: every TMA instruction of the epilogue =====================
+        // A TMA instruction costs its issuing thread ~200 cycles; here they overlap the 128 math threads instead of stalling
+        // them.  Per staged chunk: TMA store(s) of the chunk, then - once the PREVIOUS chunk's store has read its buffer -
+        // that buffer is refilled with the residual of the chunk that will use it next (nb chunks later) or marked free.
+        if (elect_one()) {
+            const int g = warp - kStoreWarp0;
+            const int ng = p.epi_groups, nb = p.nb;
+            const bool has_res = p.res != nullptr;
+            const bool any_tma = p.out[0].tma || p.out[1].tma;
+            uint8_t* ring = ring_all + g * nb * kChunkBytes;
+            uint64_t* res_full = res_full_all + g * kMaxRing;
+            uint64_t* staged = staged_all + g * kMaxRing;
+            uint64_t* buf_free = free_all + g * kMaxRing;
+            const bool split = kChunks >= 2 && ng == 2 && p.epi_split != 0;
+            const int tile_step = split ? cta_step : cta_step * ng;
+            const int tile_first = split ? cta_first : cta_first + g * cta_step;
+            const int c_first = split ? g : 0, c_step = split ? 2 : 1;
+            constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
+            const int m_rank_off = (int)cta_rank * kBlockM;
+            // residual prefetch cursor: walks this group's chunks in order, one staging buffer after the other
+            int pf_tile = tile_first, pf_chunk = c_first, pf_buf = 0;
+            auto prefetch_res = [&]() {
+                if (pf_tile < num_tiles) {
+                    mbar_expect_tx(&res_full[pf_buf], kChunkBytes);
+                    tma_load_2d(ring + pf_buf * kChunkBytes, &tmap_res, &res_full[pf_buf],
+                                p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kTileM + m_rank_off);
+                    if ((pf_chunk += c_step) >= kChunks) { pf_chunk = c_first; pf_tile += tile_step; }
+                }
+                if (++pf_buf == nb) pf_buf = 0;
+            };
+            if (has_res)
+                for (int i = 0; i < nb; ++i) prefetch_res();      // every buffer starts free
+            int buf = 0, prev = -1; uint32_t sph = 0;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int m0 = (tile / p.num_n_tiles) * kTileM + m_rank_off;
+                const int n0 = (tile % p.num_n_tiles) * BN;
+#pragma unroll 1
+                for (int c = c_first; c < kChunks; c += c_step) {
+                    mbar_wait(&staged[buf], sph);
+                    if (any_tma) {
+                        const uint8_t* sbuf = ring + buf * kChunkBytes;
+                        if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + c * 32, m0);
+                        if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + c * 32, m0);
+                        bulk_commit();
+                    }
+                    if (prev >= 0) {
+                        if (any_tma) bulk_wait_read(1);             // the previous chunk's store has read its buffer
+                        if (has_res) prefetch_res(); else mbar_arrive(&buf_free[prev]);
+                    }
+                    prev = buf;
+                    if (++buf == nb) { buf = 0; sph ^= 1; }
+                }
+            }
+            if (prev >= 0) {
+                if (any_tma) bulk_wait_read(0);
+                if (has_res) prefetch_res(); else mbar_arrive(&buf_free[prev]);
+            }
+            if (any_tma) bulk_wait_all();                           // shared memory must outlive the last TMA store
+        }
     }
 
     tc_fence_before();

@@ -250,7 +250,8 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
 struct Layer {
     ConvSpec s;
     int Hin, Win, Hout, Wout;
-    int BN, BK, stages, num_n_tiles, cout_pad, cin_pad, taps, occ;
+    int BN, BK, stages, b_stages = 0, b_resident = 0, num_n_tiles, cout_pad, cin_pad, taps, occ;
+    bool deep_k = false;
     bool cta2 = false;            // CTA pair (cta_group::2): 256-row tiles, each CTA stages half of the B tile
     size_t smem_bytes;
     __nv_bfloat16* w = nullptr;   // [cout_pad][taps * cin_pad]
@@ -345,7 +346,7 @@ static int launch_conv_t(fvy_handle* h, Layer& L, int grid) {
         ++na;
     }
     cfg.attrs = at; cfg.numAttrs = na;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.tmap_a, L.tmap_b, L.tmap_res, L.tmap_out[0], L.tmap_out[1], L.p, L.stages));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.tmap_a, L.tmap_b, L.tmap_res, L.tmap_out[0], L.tmap_out[1], L.p));
     ++h->launches;
     return FVY_OK;
 }
@@ -377,13 +378,13 @@ static int query_occ_t(size_t smem, int* occ) {
     } while (0)
 
 static int launch_conv(fvy_handle* h, Layer& L, int grid) {
-    if (L.cta2) return launch_conv_t<256, 64, true>(h, L, grid);
+    if (L.cta2) return L.BN == 256 ? launch_conv_t<256, 64, true>(h, L, grid) : launch_conv_t<128, 64, true>(h, L, grid);
 #define CALL(bn, bk, c2) launch_conv_t<bn, bk, c2>(h, L, grid)
     FVY_DISPATCH(L.BN, L.BK, CALL);
 #undef CALL
 }
 static int query_occ(int BN, int BK, bool cta2, size_t smem, int* occ) {
-    if (cta2) return query_occ_t<256, 64, true>(smem, occ);
+    if (cta2) return BN == 256 ? query_occ_t<256, 64, true>(smem, occ) : query_occ_t<128, 64, true>(smem, occ);
 #define CALL(bn, bk, c2) query_occ_t<bn, bk, c2>(smem, occ)
     FVY_DISPATCH(BN, BK, CALL);
 #undef CALL
@@ -446,8 +447,8 @@ static int build_plan(fvy_handle* h) {
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     const int bn_cap = c.tile_n_max > 0 ? c.tile_n_max : env_int("FVY_BN", 256);
     const int bn_res_cap = std::min(bn_cap, env_int("FVY_BN_RES", 256));
-    const int nb_res = env_int("FVY_NB_RES", 6), lead_res = env_int("FVY_LEAD", 4), nb_plain = env_int("FVY_NB", 3);
-    const int stages_cap = env_int("FVY_STAGES", kMaxStages);
+    const int nb_res = env_int("FVY_NB_RES", 4), nb_plain = env_int("FVY_NB", 3);
+    const int stages_cap = env_int("FVY_STAGES", kMaxA);
     const int groups_kn = env_int("FVY_GROUPS_KN", 150);   // (K iterations x 32-column chunks) at or below which a layer gets two epilogue groups
     h->use_pdl = env_int("FVY_PDL", 1) != 0;
     size_t stream_off = 0;
@@ -472,21 +473,55 @@ static int build_plan(fvy_handle* h) {
         for (int bn : {256, 128, 64, 32})
             if (bn <= cap_n && L.cout_pad % bn == 0) { L.BN = bn; break; }
         L.num_n_tiles = L.cout_pad / L.BN;
-        int tps = (L.taps == 9 && L.cin_pad == L.BK && env_int("FVY_TPS", 3) == 3) ? 3 : 1;   // one filter row per stage when Cin fits one K chunk
-        if (tps == 3 && (size_t)3 * 3 * (kBlockM + L.BN) * L.BK * 2 > 150 * 1024) tps = 1;              // needs >= 3 such stages next to the epilogue rings
-        L.cta2 = !stem && L.BN == 256 && L.BK == 64 && env_int("FVY_CTA2", 1) != 0;
-        const size_t stage_bytes = (size_t)tps * (kBlockM + (L.cta2 ? L.BN / 2 : L.BN)) * L.BK * 2;
+        const int gt = L.taps == 9 ? 3 : 1;                       // column taps per filter row
+        // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of the B tile): every 256-wide layer, and the
+        // 128-wide 3x3 layers whose whole weight tile then fits in shared memory (conv_5/7/10)
+        L.cta2 = !stem && L.BK == 64 && env_int("FVY_CTA2", 1) != 0 &&
+                 (L.BN == 256 || (L.BN == 128 && L.taps == 9 && L.num_n_tiles == 1 && env_int("FVY_CTA2_128", 1) != 0));
+        // stride-1 3x3: the three column taps of a filter row read one A slab at row shifts 0, 1, 2
+        const bool slab = L.taps == 9 && s.stride == 1 && env_int("FVY_SLAB", 1) != 0;
+        const int srows = L.BK == 64 ? slab_rows<64>() : slab_rows<32>();
+        const size_t a_tile = (size_t)kBlockM * L.BK * 2, b_tile = (size_t)(L.cta2 ? L.BN / 2 : L.BN) * L.BK * 2;
+        const int a_cover = slab ? gt : (L.BK == 32 ? gt : 1);
+        const size_t a_slot = slab ? (size_t)srows * L.BK * 2 : a_cover * a_tile;
+        int b_cover = (gt * b_tile <= 16384 && a_cover == gt) ? gt : 1;     // b_cover divides a_cover (the A slot rides on a B slot's barrier)
         // Layers with a short K loop are epilogue-bound: two epilogue groups alternate tiles.  Deep-K layers keep one
         // group so that the shared memory goes to the operand pipeline instead of a second staging ring.
-        const int k_iters = (L.taps / tps) * (L.cin_pad / L.BK);
-        const int groups = env_int("FVY_GROUPS", 0) > 0 ? env_int("FVY_GROUPS", 0) : (k_iters * (L.BN / 32) <= groups_kn ? 2 : 1);
-        int nb = has_res ? nb_res : nb_plain, lead = has_res ? lead_res : 2;
-        if (groups == 2 && has_res) { nb = std::min(nb, 4); lead = nb - 1; }
-        nb = std::max(3, std::min(nb, kMaxRing)); lead = std::max(2, std::min(lead, nb - 1));
+        const int k_chunks = L.cin_pad / L.BK;
+        const int k_iters = (L.taps / (k_chunks == 1 ? gt : 1)) * k_chunks;
+        const int groups = env_int("FVY_GROUPS", 0) > 0 ? env_int("FVY_GROUPS", 0) : 2;
+        L.deep_k = k_iters * (L.BN / 32) > groups_kn;        // MMA-bound tiles: the epilogue has slack, its latency is what shows
+        int nb = has_res ? nb_res : nb_plain, lead = 0;
+        nb = std::max(2, std::min(nb, kMaxRing));
         const size_t fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;
         const size_t budget = 232448 - fixed;
-        L.stages = (int)std::min<size_t>(std::min(kMaxStages, stages_cap), std::max<size_t>(2, budget / stage_bytes));
-        L.smem_bytes = fixed + (size_t)L.stages * stage_bytes;
+        // Resident weights: with a single N tile per CTA the whole [BN, K] weight tile is loaded once and every later
+        // tile of the persistent CTA only streams A (half the operand bytes of a 1x1 layer, a quarter of a slab 3x3 layer).
+        const size_t b_total = (size_t)L.taps * k_chunks * b_tile;
+        int a_stages = 0, b_stages = 0, b_res = 0;
+        if (L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot <= budget) {
+            if (L.taps * k_chunks / b_cover > kMaxB && a_cover == gt) b_cover = gt;
+            if (L.taps * k_chunks / b_cover <= kMaxB) {
+                b_res = 1;
+                b_stages = L.taps * k_chunks / b_cover;
+                a_stages = (int)std::min<size_t>(std::min(kMaxA, stages_cap), (budget - b_total) / a_slot);
+            }
+        }
+        if (!b_res) {
+            // streaming: maximise the taps in flight of the scarcer operand, then the bytes in flight
+            const size_t b_slot = b_cover * b_tile;
+            long best = -1;
+            for (int a = 2; a <= std::min(kMaxA, stages_cap); ++a)
+                for (int b = 2; b <= std::min(kMaxB, stages_cap * gt); ++b) {
+                    const size_t bytes = a * a_slot + b * b_slot;
+                    if (bytes > budget) break;
+                    const long score = (long)std::min(a * a_cover, b * b_cover) * 1000000 + (long)(bytes >> 10);
+                    if (score > best) { best = score; a_stages = a; b_stages = b; }
+                }
+            if (best < 0) return fail(FVY_E_INVALID, "conv_%d: no operand pipeline fits in shared memory", s.idx);
+        }
+        L.stages = a_stages; L.b_stages = b_stages; L.b_resident = b_res;
+        L.smem_bytes = fixed + (size_t)a_stages * a_slot + (size_t)b_stages * b_cover * b_tile;
         if (L.smem_bytes > 232448) return fail(FVY_E_INVALID, "conv_%d: shared memory plan %zu exceeds 227 KB", s.idx, L.smem_bytes);
         if (int e = query_occ(L.BN, L.BK, L.cta2, L.smem_bytes, &L.occ)) return e;
         L.occ = 1;   // 320 threads x ~140 registers: one CTA per SM; latency is hidden inside the CTA (stages, two epilogue groups)
@@ -504,7 +539,9 @@ static int build_plan(fvy_handle* h) {
         p.leaky = s.leaky ? 1 : 0;
         p.bias = L.bias;
         p.num_n_tiles = L.num_n_tiles;
-        p.nb = nb; p.lead = lead; p.epi_groups = groups; p.tps = tps;
+        p.nb = nb; p.lead = lead; p.epi_groups = groups;
+        p.gt = gt; p.a_slab = slab ? 1 : 0; p.a_cover = a_cover; p.a_stages = a_stages;
+        p.b_cover = b_cover; p.b_stages = b_stages; p.b_resident = b_res;
         const void* a_base = nullptr;
         uint64_t a_rows = 0, a_pitch = 0;
         if (stem) {
@@ -535,7 +572,7 @@ static int build_plan(fvy_handle* h) {
         p.magic_plane = ~0ull / (unsigned long long)p.dom_plane + 1ull;
         p.magic_w = ~0ull / (unsigned long long)p.dom_w + 1ull;
         if ((long long)nmax * p.dom_plane >= (1ll << 31)) return fail(FVY_E_INVALID, "conv_%d: %d x %d rows overflow int32", s.idx, nmax, p.dom_plane);
-        if (int e = make_tmap_2d(&L.tmap_a, a_base, a_pitch, a_rows, a_pitch, L.BK, kBlockM)) return e;
+        if (int e = make_tmap_2d(&L.tmap_a, a_base, a_pitch, a_rows, a_pitch, L.BK, slab ? srows : kBlockM)) return e;
         L.tmap_res = L.tmap_a; L.tmap_out[0] = L.tmap_a; L.tmap_out[1] = L.tmap_a;   // placeholders for unused maps
         // rows of the compute domain coincide with rows of a padded (H, W) buffer only for stride-1 convs on a padded input
         const bool coincident = !stem && s.stride == 1;
@@ -681,6 +718,13 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             grid = std::min(2 * tiles, h->num_sms & ~1);
         } else {
             grid = std::min(L.p.num_m_tiles * L.p.num_n_tiles, h->num_sms * L.occ);
+        }
+        {   // column-split epilogue (both groups drain every tile): when the tile's K loop hides the drain anyway, or when a CTA
+            // only gets a few tiles and the drain of the last one is what the layer waits for
+            const int tiles = L.cta2 ? ((L.p.num_m_tiles + 1) / 2) * L.p.num_n_tiles : L.p.num_m_tiles * L.p.num_n_tiles;
+            const int ctas = L.cta2 ? grid / 2 : grid;
+            static const int split_env = [] { const char* v = getenv("FVY_SPLIT"); return v && *v ? atoi(v) : -1; }();
+            L.p.epi_split = split_env >= 0 ? split_env : ((L.BN >= 128 && (L.deep_k || tiles <= 3 * ctas)) ? 1 : 0);
         }
         if (int e = launch_conv(h, L, grid)) return e;
     }
@@ -1136,7 +1180,8 @@ int fvy_layer_info(const fvy_handle* h, int layer, int* info) {
     const Layer& L = h->layers[layer];
     const int m_total = h->cfg.max_batch * L.p.dom_plane;
     const int tiles = ((m_total + kBlockM - 1) / kBlockM) * L.num_n_tiles;
-    const int v[12] = {L.s.idx, L.s.cin, L.s.cout, L.s.k, L.s.stride, L.Hout, L.Wout, L.BN, L.BK, L.stages,
+    const int v[12] = {L.s.idx, L.s.cin, L.s.cout, L.s.k, L.s.stride, L.Hout, L.Wout, L.BN, L.BK,
+                       L.stages + 100 * L.b_stages + 10000 * L.b_resident + 100000 * (L.cta2 ? 1 : 0) + 1000000 * L.p.a_slab,
                        std::min(tiles, h->num_sms * L.occ), tiles};
     memcpy(info, v, sizeof(v));
     return FVY_OK;
@@ -1194,6 +1239,39 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
     if (layer < 0 || layer >= (int)h->layers.size() || batch < 1 || batch > h->cfg.max_batch || iters < 1) return fail(FVY_E_INVALID, "bad layer/batch/iters");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (int e = run_layers(h, batch, layer, layer + 1)) return e;
+    if (getenv("FVY_DBG") && !(h->layers[layer].s.src == -1 && h->fused_stem)) {
+        // cycle counters of the two single-thread roles, averaged over CTAs (profiling aid)
+        Layer& L = h->layers[layer];
+        unsigned long long* d = nullptr;
+        const int n = h->num_sms * 16;
+        CUDA_TRY(cudaMalloc(&d, n * 8));
+        CUDA_TRY(cudaMemsetAsync(d, 0, n * 8, h->stream));
+        L.p.dbg = d;
+        int e = run_layers(h, batch, layer, layer + 1);
+        L.p.dbg = nullptr;
+        std::vector<unsigned long long> v(n);
+        cudaMemcpyAsync(v.data(), d, n * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(d);
+        if (e) return e;
+        double s[16] = {0}; int cnt = 0, ecnt = 0;
+        for (int c = 0; c < h->num_sms; ++c)
+            if (v[c * 16] || v[c * 16 + 4] || v[c * 16 + 8]) {
+                for (int k = 0; k < 16; ++k) s[k] += (double)v[c * 16 + k];
+                if (v[c * 16]) ++cnt;
+                if (v[c * 16 + 8]) ++ecnt;
+            }
+        if (ecnt)
+            fprintf(stderr, "fvy dbg conv_%d epilogue group 0: total %.0f clk  chunks %.0f  => %.0f clk/chunk: wait_tmem_full %.0f  wait_res %.0f  "
+                            "named_barrier %.0f  issuer(store+wait_read+prefetch) %.0f  tmem_ld %.0f  body(ld..fence, incl. wait_res) %.0f\n",
+                    L.s.idx, s[8] / ecnt, s[13] / ecnt, s[8] / std::max(1.0, s[13]), s[9] / std::max(1.0, s[13]), s[10] / std::max(1.0, s[13]),
+                    s[11] / std::max(1.0, s[13]), s[12] / std::max(1.0, s[13]), s[14] / std::max(1.0, s[13]), s[15] / std::max(1.0, s[13]));
+        if (cnt)
+            fprintf(stderr, "fvy dbg conv_%d: issuing CTAs %d  total %.0f clk  wait_full %.0f  wait_tmem_empty %.0f  taps %.0f  => %.0f clk/tap "
+                            "(%.0f outside waits); producers wait_empty A %.0f B %.0f\n",
+                    L.s.idx, cnt, s[0] / cnt, s[1] / cnt, s[2] / cnt, s[3] / cnt, s[0] / std::max(1.0, s[3]),
+                    (s[0] - s[1] - s[2]) / std::max(1.0, s[3]), s[4] / cnt, s[5] / cnt);
+    }
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     for (int it = 0; it < iters; ++it)
         if (int e = run_layers(h, batch, layer, layer + 1)) return e;

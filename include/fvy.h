@@ -146,7 +146,8 @@ int fvy_detect(fvy_handle* h, const void* images, int dtype, int batch, const fv
 
 /* Introspection for tests / bench: */
 int fvy_num_layers(const fvy_handle* h);
-/* info[0..11] = idx, cin, cout, k, stride, H_out, W_out, tile_n, tile_k, stages, grid, num_tiles */
+/* info[0..11] = idx, cin, cout, k, stride, H_out, W_out, tile_n, tile_k, stages, grid, num_tiles;
+ * stages = A slots + 100 * B slots + 10000 * weights resident + 100000 * CTA pair + 1000000 * A slab */
 int fvy_layer_info(const fvy_handle* h, int layer, int* info12);
 /* Copies layer `layer`'s stored output for `batch` images into dst as dense NHWC float32 (debug / layer-wise parity). */
 int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host);

@@ -22,6 +22,11 @@ from face_vijnana_yolov3_b200.engine import Engine, post_params   # noqa: E402
 from oracle import darknet_ref as D, postproc as P   # noqa: E402
 
 
+def fmt_stages(v):
+    a, b, res, pair, slab = v % 100, v // 100 % 100, v // 10000 % 10, v // 100000 % 10, v // 1000000
+    return f"A{a}/B{b}{'R' if res else ''}{'P' if pair else ''}{'S' if slab else ''}"
+
+
 def rel_l2(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
@@ -50,7 +55,7 @@ def check_forward(size, batch, init, head, tile_n_max, out):
         bad += r >= 3e-2
         rows.append((info["idx"], r))
         print(f"  layer {li:2d} conv_{info['idx']:<4d} {info['cin']:4d}->{info['cout']:4d} k{info['k']} s{info['stride']} "
-              f"{info['H']:3d}x{info['W']:<3d} tileN={info['tile_n']:3d} tileK={info['tile_k']} st={info['stages']} grid={info['grid']:4d} "
+              f"{info['H']:3d}x{info['W']:<3d} tileN={info['tile_n']:3d} tileK={info['tile_k']} st={fmt_stages(info['stages'])} grid={info['grid']:4d} "
               f"tiles={info['tiles']:6d} relL2(vs bf16 emu)={r:.3e}{flag}", flush=True)
     if head == L.HEAD_FD6:
         outs_l, emu_l, ref_l = [outs[0]], [emu], [ref]
