@@ -272,6 +272,27 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// Explicit shared-space accesses: the epilogue's pointers are carved out of an aligned uintptr_t, which makes the compiler fall
+// back to generic LD/ST (+ two R2UR per access for the memory descriptor); these keep them LDS / STS.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
@@ -466,7 +487,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (CTA2 ? 8 : 4) * ((BN >= 64 && p.epi_groups == 2 && p.epi_split != 0) ? 2 : 1)); }
-        for (int s = 0; s < 2 * kMaxRing; ++s) { mbar_init(&res_full_all[s], 1); mbar_init(&staged_all[s], kEpiThreads); mbar_init(&free_all[s], 1); }
+        for (int s = 0; s < 2 * kMaxRing; ++s) { mbar_init(&res_full_all[s], 1); mbar_init(&staged_all[s], kEpiThreads / 32); mbar_init(&free_all[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -578,15 +599,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int r = q * 32 + lane;               // row of the tile handled by this thread (TMEM lane)
         const int et = (threadIdx.x - 64) & (kEpiThreads - 1);   // 0..127 within the group
         const bool has_res = p.res != nullptr;
-        const bool any_direct = (p.out[0].kind != OUT_NONE && p.out[0].kind != OUT_HEAD_F32 && !p.out[0].tma) ||
-                                (p.out[1].kind != OUT_NONE && p.out[1].kind != OUT_HEAD_F32 && !p.out[1].tma);
+        // output forms, hoisted out of the tile / chunk loops (uniform per launch)
+        const int kind0 = p.out[0].kind, kind1 = p.out[1].kind;
+        const bool direct0 = kind0 != OUT_NONE && kind0 != OUT_HEAD_F32 && !p.out[0].tma;
+        const bool direct1 = kind1 != OUT_NONE && kind1 != OUT_HEAD_F32 && !p.out[1].tma;
+        const bool any_direct = direct0 || direct1;
+        const bool head0 = kind0 == OUT_HEAD_F32, head1 = kind1 == OUT_HEAD_F32;
+        const int nnt = p.num_n_tiles;
         const int nb = p.nb;
         const uint32_t swz = (uint32_t)((r >> 1) & 3);          // 64-byte swizzle: 16-byte slot j of row r lives at slot j ^ swz
         uint8_t* ring = ring_all + g * nb * kChunkBytes;
         uint64_t* res_full = res_full_all + g * kMaxRing;
         uint64_t* staged = staged_all + g * kMaxRing;
         uint64_t* buf_free = free_all + g * kMaxRing;
-        int* myrow_base = reinterpret_cast<int*>(smem + kSmemRowIdx) + g * 4 * kBlockM;
+        const uint32_t myrow_base = smem_u32(smem + kSmemRowIdx) + (uint32_t)g * 4u * kBlockM * 4u;
+        const uint32_t ring_u32 = smem_u32(ring), sbias_u32 = smem_u32(sbias);
         const int bar_id = 1 + g;
         // Two groups: tiles with >= 2 chunks are split by COLUMNS (group g drains chunks g, g+2, ...: half the drain latency per
         // tile, which is what stays exposed at the end of a layer); single-chunk tiles (BN = 32) alternate between the groups.
@@ -604,11 +631,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t it_tile = split ? 0 : g;          // index of the tile in this CTA's sequence (selects the accumulator stage)
         uint32_t my_tiles = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step, it_tile += (split ? 1 : ng), ++my_tiles) {
+            const long long tt0 = dbg_on ? clock64() : 0;
             const int as = it_tile % kAcc;
-            int* myrow = myrow_base + (my_tiles & 1) * 2 * kBlockM;   // double-buffered: a fast thread may be one tile ahead
-            const int m0 = (tile / p.num_n_tiles) * kTileM + m_rank_off;
+            const uint32_t myrow = myrow_base + (my_tiles & 1) * 2 * kBlockM * 4u;   // double-buffered: a fast thread may be one tile ahead
+            const int mt = nnt == 1 ? tile : tile / nnt;
+            const int m0 = mt * kTileM + m_rank_off;
             const int m = m0 + r;
-            const int n0 = (tile % p.num_n_tiles) * BN;
+            const int n0 = (tile - mt * nnt) * BN;
             // decode the pixel and decide whether the row is a real output (exact division by multiply-high)
             bool valid = m < p.m_total;
             int img = 0, h = 0, w = 0;
@@ -623,8 +652,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // destination row of this pixel for the outputs that are not stored by TMA
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
+                if (!(o == 0 ? direct0 : direct1)) continue;
                 const OutDesc& od = p.out[o];
-                if (od.kind == OUT_NONE || od.kind == OUT_HEAD_F32 || od.tma) continue;
                 int ridx = -1;
                 if (valid) {
                     if (od.kind == OUT_PADDED) ridx = (img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
@@ -634,9 +663,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         ridx = ((((hp & 1) << 1) | (wp & 1)) * od.nmax + img) * plane + (hp >> 1) * pw + (wp >> 1);
                     } else ridx = (img * (2 * p.H + 2) + (2 * h + 1)) * (2 * p.W + 2) + (2 * w + 1);   // OUT_UP2_PADDED
                 }
-                myrow[o * kBlockM + r] = ridx;
+                sts32(myrow + (uint32_t)(o * kBlockM + r) * 4u, ridx);
             }
             { const long long c0 = dbg_on ? clock64() : 0;
+              if (dbg_on) dbg_e_ld += c0 - tt0;        // per-tile set-up (row decode, destination rows)
               mbar_wait(&tmem_full[as], (it_tile / kAcc) & 1);
               if (dbg_on) dbg_e_tmem += clock64() - c0; }
             tc_fence_after();
@@ -644,19 +674,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
             for (int c = c_first; c < kChunks; c += c_step, ++cg) {
                 const int c0 = c * 32;
-                uint8_t* sbuf = ring + buf * kChunkBytes;
-                uint4* myslot = reinterpret_cast<uint4*>(sbuf + r * 64);
+                const uint32_t sbuf = ring_u32 + (uint32_t)buf * kChunkBytes;
+                const uint32_t myslot = sbuf + (uint32_t)r * 64u;
                 uint32_t acc[32];
                 const long long tl0 = dbg_on ? clock64() : 0;
                 tmem_ld_32x32(taddr + c0, acc);
                 tmem_ld_wait();
-                if (dbg_on) dbg_e_ld += clock64() - tl0;
                 float v[32];
                 {
-                    const float4* b4 = reinterpret_cast<const float4*>(sbias + n0 + c0);
+                    const uint32_t b4 = sbias_u32 + (uint32_t)(n0 + c0) * 4u;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 b = b4[j];
+                        const float4 b = lds128f(b4 + 16u * j);
                         v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
                         v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
                         v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
@@ -676,7 +705,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 if (has_res) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 t = myslot[j ^ swz];
+                        const uint4 t = lds128(myslot + ((j ^ swz) << 4));
                         v[8 * j + 0] += __uint_as_float(t.x << 16); v[8 * j + 1] += __uint_as_float(t.x & 0xFFFF0000u);
                         v[8 * j + 2] += __uint_as_float(t.y << 16); v[8 * j + 3] += __uint_as_float(t.y & 0xFFFF0000u);
                         v[8 * j + 4] += __uint_as_float(t.z << 16); v[8 * j + 5] += __uint_as_float(t.z & 0xFFFF0000u);
@@ -687,7 +716,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
                     const OutDesc& od = p.out[o];
-                    if (od.kind == OUT_HEAD_F32 && valid) {
+                    if ((o == 0 ? head0 : head1) && valid) {
                         float* dst = reinterpret_cast<float*>(od.ptr) + (((long long)img * p.H + h) * p.W + w) * od.c_real;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -706,8 +735,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
                     pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
                     pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                    myslot[j ^ swz] = pk;
+                    sts128(myslot + ((j ^ swz) << 4), pk);
                 }
+                fence_proxy_async();          // generic-proxy writes of the staged chunk -> visible to the async proxy (TMA store)
                 if (dbg_on) dbg_e_body += clock64() - tl0;
                 if (any_direct) {   // the direct forms read rows staged by other threads
                     const long long tq0 = dbg_on ? clock64() : 0;
@@ -715,17 +745,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if (dbg_on) dbg_e_bar += clock64() - tq0;
                 }
                 // remaining output forms: 4 threads per 64-byte row, 32 rows per pass
+                const long long td0 = dbg_on ? clock64() : 0;
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
+                    if (!(o == 0 ? direct0 : direct1)) continue;
                     const OutDesc& od = p.out[o];
-                    if (od.kind == OUT_NONE || od.kind == OUT_HEAD_F32 || od.tma) continue;
                     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(od.ptr) + od.choff + n0 + c0 + (et & 3) * 8;
 #pragma unroll
                     for (int pass = 0; pass < 4; ++pass) {
                         const int row = pass * 32 + (et >> 2);
-                        const int ridx = myrow[o * kBlockM + row];
+                        const int ridx = lds32(myrow + (uint32_t)(o * kBlockM + row) * 4u);
                         if (ridx < 0) continue;
-                        const uint4 t = *reinterpret_cast<const uint4*>(sbuf + row * 64 + (((et & 3) ^ ((row >> 1) & 3)) << 4));
+                        const uint4 t = lds128(sbuf + (uint32_t)row * 64u + (uint32_t)(((et & 3) ^ ((row >> 1) & 3)) << 4));
                         if (od.kind == OUT_UP2_PADDED) {
                             const int W2 = 2 * p.W + 2;
                             *reinterpret_cast<uint4*>(base + (long long)ridx * od.pitch) = t;
@@ -737,9 +768,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         }
                     }
                 }
-                // hand the staged chunk to the store warp (generic-proxy writes -> visible to the async proxy first)
-                fence_proxy_async();
-                mbar_arrive(&staged[buf]);
+                if (dbg_on) dbg_e_tma += clock64() - td0;
+                // hand the staged chunk to the store warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&staged[buf]);      // one arrival per warp
                 if (++buf == nb) { buf = 0; buf_ph ^= 1; }
             }
             // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above): hand it back

@@ -252,6 +252,7 @@ struct Layer {
     int Hin, Win, Hout, Wout;
     int BN, BK, stages, b_stages = 0, b_resident = 0, num_n_tiles, cout_pad, cin_pad, taps, occ;
     bool deep_k = false;
+    int head_slot = -1;           // index of the logit tensor a head layer writes
     bool cta2 = false;            // CTA pair (cta_group::2): 256-row tiles, each CTA stages half of the B tile
     size_t smem_bytes;
     __nv_bfloat16* w = nullptr;   // [cout_pad][taps * cin_pad]
@@ -292,6 +293,12 @@ struct fvy_handle {
     unsigned stage_slot = 0; int last_slot = -1;
     __nv_bfloat16* d_stem = nullptr;                        // im2col operand
     float* d_logits[3] = {nullptr, nullptr, nullptr};
+    // Asynchronous detect calls post-process on their own (low-priority) stream: decode / NMS of call i fill the gaps that the
+    // persistent conv kernels of call i+1 leave at layer boundaries.  Head logits alternate between two sets for that.
+    float* d_logits_alt[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t post_stream = nullptr, ps = nullptr;       // ps: the stream post-processing is enqueued on for the current call
+    cudaEvent_t ev_fwd_done[2] = {nullptr, nullptr}, ev_post_done[2] = {nullptr, nullptr};
+    int logit_set = 0; bool overlap_post = true;
     int gh[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, head_c = 0;
     // post
     int cap = 0, capP = 0, words = 0, np2max = 0, smem_keys = 0;
@@ -442,6 +449,7 @@ static int build_plan(fvy_handle* h) {
             if (nh >= 3) return fail(FVY_E_INVALID, "more than 3 heads");
             h->gh[nh] = H; h->gw[nh] = W; h->head_c = s.cout;
             if (int e = dev_alloc(h, (void**)&h->d_logits[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
+            if (int e = dev_alloc(h, (void**)&h->d_logits_alt[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
             ++nh;
         }
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
@@ -595,6 +603,7 @@ static int build_plan(fvy_handle* h) {
             ++no;
         };
         if (!s.bn) {
+            L.head_slot = head_i;
             add_out(h->d_logits[head_i++], OUT_HEAD_F32, s.cout, 0, s.cout);
         } else {
             if (bufs[s.idx].padded) add_out(bufs[s.idx].padded, OUT_PADDED, s.cout, 0, s.cout);
@@ -710,14 +719,20 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
             continue;
         }
+        if (!L.s.bn && L.head_slot >= 0)     // head logits of this call's set
+            L.p.out[0].ptr = h->logit_set ? h->d_logits_alt[L.head_slot] : h->d_logits[L.head_slot];
         L.p.m_total = batch * L.p.dom_plane;
         L.p.num_m_tiles = (L.p.m_total + kBlockM - 1) / kBlockM;
+        static const int nowork = [] { const char* v = getenv("FVY_NOWORK"); return v && *v ? atoi(v) : 0; }();   // profiling aid: launch cost only
+        // SMs the persistent conv grids may occupy; the rest is left to the overlapped post-processing of the previous call
+        static const int conv_sms_env = [] { const char* v = getenv("FVY_CONV_SMS"); return v && *v ? atoi(v) : 0; }();
+        const int conv_sms = conv_sms_env > 0 ? std::min(conv_sms_env, h->num_sms) : h->num_sms;
         int grid;
         if (L.cta2) {
             const int tiles = ((L.p.num_m_tiles + 1) / 2) * L.p.num_n_tiles;
-            grid = std::min(2 * tiles, h->num_sms & ~1);
+            grid = std::min(2 * tiles, conv_sms & ~1);
         } else {
-            grid = std::min(L.p.num_m_tiles * L.p.num_n_tiles, h->num_sms * L.occ);
+            grid = std::min(L.p.num_m_tiles * L.p.num_n_tiles, conv_sms * L.occ);
         }
         {   // column-split epilogue (both groups drain every tile): when the tile's K loop hides the drain anyway, or when a CTA
             // only gets a few tiles and the drain of the last one is what the layer waits for
@@ -726,6 +741,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             static const int split_env = [] { const char* v = getenv("FVY_SPLIT"); return v && *v ? atoi(v) : -1; }();
             L.p.epi_split = split_env >= 0 ? split_env : ((L.BN >= 128 && (L.deep_k || tiles <= 3 * ctas)) ? 1 : 0);
         }
+        if (nowork) L.p.num_m_tiles = 0;
         if (int e = launch_conv(h, L, grid)) return e;
     }
     return FVY_OK;
@@ -771,7 +787,7 @@ static int resolve_logits(fvy_handle* h, const float* o0, const float* o1, const
     const float* in[3] = {o0, o1, o2};
     const int nheads = h->cfg.head == FVY_HEAD_FD6 ? 1 : 3;
     for (int i = 0; i < nheads; ++i) {
-        if (in[i] == nullptr) { dev[i] = h->d_logits[i]; continue; }
+        if (in[i] == nullptr) { dev[i] = h->logit_set ? h->d_logits_alt[i] : h->d_logits[i]; continue; }
         if (is_device_ptr(in[i])) { dev[i] = in[i]; continue; }
         const size_t bytes = (size_t)batch * h->gh[i] * h->gw[i] * h->head_c * 4;
         CUDA_TRY(cudaMemcpyAsync(h->d_logits[i], in[i], bytes, cudaMemcpyHostToDevice, h->stream));
@@ -783,19 +799,19 @@ static int resolve_logits(fvy_handle* h, const float* o0, const float* o1, const
 static int upload_image_hw(fvy_handle* h, const int* image_hw, int batch, const int** dev) {
     if (!image_hw) { *dev = nullptr; return FVY_OK; }
     if (is_device_ptr(image_hw)) { *dev = image_hw; return FVY_OK; }
-    CUDA_TRY(cudaMemcpyAsync(h->d_image_hw, image_hw, (size_t)batch * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_image_hw, image_hw, (size_t)batch * 8, cudaMemcpyHostToDevice, h->ps));
     *dev = h->d_image_hw;
     return FVY_OK;
 }
 
 static int decode_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy_post_params* pp, const int* d_hw, bool want_nbox) {
-    CUDA_TRY(cudaMemsetAsync(h->d_status, 0, 4, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_status, 0, 4, h->ps));
     if (h->cfg.head == FVY_HEAD_FD6) {
         DecodeFd6Args a;
         a.cands = dev[0]; a.grid = h->gh[0]; a.image_size = h->cfg.net_h; a.cell_px = h->cfg.net_h / 13;
         a.face_conf_th = pp->obj_thresh; a.arith = pp->arith; a.cap = h->cap;
         a.ibox = h->d_ibox; a.objness = h->d_obj; a.score = h->d_cls; a.cand = h->d_cand; a.counts = h->d_counts;
-        decode_fd6_kernel<<<batch, 512, 0, h->stream>>>(a);
+        decode_fd6_kernel<<<batch, 512, 0, h->ps>>>(a);
     } else {
         DecodeArgs a;
         for (int i = 0; i < 3; ++i) { a.out[i] = dev[i]; a.gh[i] = h->gh[i]; a.gw[i] = h->gw[i]; }
@@ -806,7 +822,7 @@ static int decode_enqueue(fvy_handle* h, const float* dev[3], int batch, const f
         a.image_hw = d_hw; a.cap = h->cap;
         a.nbox = want_nbox ? h->d_nbox : nullptr; a.ibox = h->d_ibox; a.objness = h->d_obj; a.classes = h->d_cls;
         a.cand = h->d_cand; a.counts = h->d_counts; a.status = h->d_status;
-        decode_yolo_kernel<<<batch, 1024, 0, h->stream>>>(a);
+        decode_yolo_kernel<<<batch, 1024, 0, h->ps>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
@@ -821,17 +837,17 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
         s.ibox = d_ibox; s.classes = d_cls; s.counts = d_counts; s.seg_stride = seg_stride; s.nb_class = nb_class; s.cls = c;
         s.capP = h->capP; s.descending = 1; s.order = h->d_order; s.sbox = h->d_sbox; s.gkeys = h->d_gkeys;
         s.smem_keys = h->smem_keys; s.np2max = h->np2max;
-        sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->stream>>>(s);
+        sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->ps>>>(s);
         CUDA_TRY(cudaGetLastError());
         MaskArgs m;
         m.sbox = h->d_sbox; m.counts = d_counts; m.seg_stride = seg_stride; m.batch = batch; m.capP = h->capP; m.words = h->words;
         m.th = th; m.mask = h->d_mask;
-        nms_mask_kernel<<<h->num_sms * 16, 64, 0, h->stream>>>(m);
+        nms_mask_kernel<<<h->num_sms * 16, 64, 0, h->ps>>>(m);
         CUDA_TRY(cudaGetLastError());
         SweepArgs w;
         w.mask = h->d_mask; w.order = h->d_order; w.counts = d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
         w.nb_class = nb_class; w.cls = c; w.classes = d_cls;
-        nms_sweep_kernel<<<batch, 1024, (size_t)h->words * 8, h->stream>>>(w);
+        nms_sweep_kernel<<<batch, 1024, (size_t)h->words * 8, h->ps>>>(w);
         CUDA_TRY(cudaGetLastError());
         h->launches += 3;
     }
@@ -852,12 +868,12 @@ static int post_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy
         s.ibox = h->d_ibox; s.classes = h->d_cls; s.counts = h->d_counts; s.seg_stride = h->cap; s.nb_class = 1; s.cls = 0;
         s.capP = h->capP; s.descending = 0; s.order = h->d_order; s.sbox = nullptr; s.gkeys = h->d_gkeys;
         s.smem_keys = h->smem_keys; s.np2max = h->np2max;
-        sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->stream>>>(s);
+        sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->ps>>>(s);
         CUDA_TRY(cudaGetLastError());
-        assemble_fd6_kernel<<<batch, 512, 0, h->stream>>>(a, h->d_order, h->capP);
+        assemble_fd6_kernel<<<batch, 512, 0, h->ps>>>(a, h->d_order, h->capP);
         h->launches += 2;
     } else {
-        assemble_yolo_kernel<<<batch, 1024, 0, h->stream>>>(a);
+        assemble_yolo_kernel<<<batch, 1024, 0, h->ps>>>(a);
         ++h->launches;
     }
     CUDA_TRY(cudaGetLastError());
@@ -886,6 +902,7 @@ void fvy_destroy(fvy_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->post_stream) cudaStreamSynchronize(h->post_stream);
     if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -895,6 +912,8 @@ void fvy_destroy(fvy_handle* h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->post_stream) cudaStreamDestroy(h->post_stream);
+    for (cudaEvent_t e : {h->ev_fwd_done[0], h->ev_fwd_done[1], h->ev_post_done[0], h->ev_post_done[1]}) if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -923,6 +942,16 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { e = fail(FVY_E_CUDA, "cudaStreamCreate failed"); break; }
         bool ok = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+        {   // post-processing stream at the LOWEST priority: it only takes what the conv kernels leave
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            ok = ok && cudaStreamCreateWithPriority(&h->post_stream, cudaStreamNonBlocking, lo) == cudaSuccess;
+            h->ps = h->stream;
+            const char* v = getenv("FVY_OVERLAP_POST");
+            h->overlap_post = !(v && *v && atoi(v) == 0);
+        }
+        for (cudaEvent_t* ev : {&h->ev_fwd_done[0], &h->ev_fwd_done[1], &h->ev_post_done[0], &h->ev_post_done[1]})
+            ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
         for (auto& ev : h->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
         for (cudaEvent_t* ev : {&h->ev_ready[0], &h->ev_ready[1], &h->ev_consumed[0], &h->ev_consumed[1], &h->ev_post, &h->ev_d2h})
             ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
@@ -1116,11 +1145,11 @@ static int postprocess_common(fvy_handle* h, const float* out0, const float* out
     if (int e = resolve_logits(h, out0, out1, out2, batch, dev)) return e;
     const int* d_hw = nullptr;
     if (int e = upload_image_hw(h, image_hw, batch, &d_hw)) return e;
-    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h, 0));      // the previous call's detections have left the device buffers
-    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->ps, h->ev_d2h, 0));          // the previous call's detections have left the device buffers
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->ps));
     if (int e = post_enqueue(h, dev, batch, pp, d_hw, max_out)) return e;
-    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-    CUDA_TRY(cudaEventRecord(h->ev_post, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->ps));
+    CUDA_TRY(cudaEventRecord(h->ev_post, h->ps));
     CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_post, 0));
     CUDA_TRY(cudaMemcpyAsync(dets, h->d_dets, (size_t)batch * max_out * sizeof(FvyDet), cudaMemcpyDefault, h->d2h_stream));
     CUDA_TRY(cudaMemcpyAsync(det_counts, h->d_det_counts, (size_t)batch * 4, cudaMemcpyDefault, h->d2h_stream));
@@ -1146,10 +1175,30 @@ static int detect_common(fvy_handle* h, const void* images, int dtype, int batch
     if (!h || !images) return fail(FVY_E_INVALID, "NULL argument");
     if (h->cfg.head == FVY_HEAD_NONE) return fail(FVY_E_STATE, "handle has no network");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const bool overlap = !sync && h->overlap_post;
+    if (overlap) {
+        h->logit_set ^= 1;
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_post_done[h->logit_set], 0));   // the post-processing that read this set (two calls ago) is done
+    } else {
+        h->logit_set = 0;
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_post_done[0], 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_post_done[1], 0));              // nothing of an earlier asynchronous call is still in flight
+    }
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     if (int e = forward_enqueue(h, images, dtype, batch)) return e;
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
-    if (int e = postprocess_common(h, nullptr, nullptr, nullptr, batch, pp, image_hw, max_out, dets, det_counts, sync)) return e;
+    int e = FVY_OK;
+    if (overlap) {
+        CUDA_TRY(cudaEventRecord(h->ev_fwd_done[h->logit_set], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->post_stream, h->ev_fwd_done[h->logit_set], 0));
+        h->ps = h->post_stream;
+        e = postprocess_common(h, nullptr, nullptr, nullptr, batch, pp, image_hw, max_out, dets, det_counts, false);
+        h->ps = h->stream;
+        if (e == FVY_OK) CUDA_TRY(cudaEventRecord(h->ev_post_done[h->logit_set], h->post_stream));
+    } else {
+        e = postprocess_common(h, nullptr, nullptr, nullptr, batch, pp, image_hw, max_out, dets, det_counts, sync);
+    }
+    if (e) return e;
     if (sync) CUDA_TRY(cudaEventElapsedTime(&h->last_fwd_ms, h->ev[0], h->ev[1]));
     return FVY_OK;
 }
@@ -1169,6 +1218,7 @@ int fvy_sync(fvy_handle* h) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->h2d_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->post_stream));
     CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     return FVY_OK;
 }
@@ -1263,7 +1313,7 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
             }
         if (ecnt)
             fprintf(stderr, "fvy dbg conv_%d epilogue group 0: total %.0f clk  chunks %.0f  => %.0f clk/chunk: wait_tmem_full %.0f  wait_res %.0f  "
-                            "named_barrier %.0f  issuer(store+wait_read+prefetch) %.0f  tmem_ld %.0f  body(ld..fence, incl. wait_res) %.0f\n",
+                            "named_barrier %.0f  direct_stores %.0f  tile_setup(per chunk) %.0f  body(ld..fence, incl. wait_res) %.0f\n",
                     L.s.idx, s[8] / ecnt, s[13] / ecnt, s[8] / std::max(1.0, s[13]), s[9] / std::max(1.0, s[13]), s[10] / std::max(1.0, s[13]),
                     s[11] / std::max(1.0, s[13]), s[12] / std::max(1.0, s[13]), s[14] / std::max(1.0, s[13]), s[15] / std::max(1.0, s[13]));
         if (cnt)
