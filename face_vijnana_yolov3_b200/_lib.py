@@ -41,7 +41,7 @@ class FvyPostParams(C.Structure):
 SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_load_weights", "fvy_weight_count", "fvy_forward",
            "fvy_decode", "fvy_correct_boxes", "fvy_nms", "fvy_bbox_iou", "fvy_postprocess", "fvy_detect", "fvy_num_layers",
            "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
-           "fvy_detect_async", "fvy_host_alloc", "fvy_host_free"]
+           "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step"]
 
 _lib = None
 
@@ -89,6 +89,8 @@ def load():
     L.fvy_sync.restype = C.c_int; L.fvy_sync.argtypes = [H]
     L.fvy_host_alloc.restype = C.c_void_p; L.fvy_host_alloc.argtypes = [C.c_size_t]
     L.fvy_host_free.restype = None; L.fvy_host_free.argtypes = [C.c_void_p]
+    L.fvy_adam_step.restype = C.c_int
+    L.fvy_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     _lib = L
     return L
 

@@ -1350,6 +1350,53 @@ int fvy_timer_stop(fvy_handle* h, float* ms) {
     return FVY_OK;
 }
 
+// Keras Adam over a flat bucket: 16 bytes of each of p, g, m, v per thread and iteration (HBM-bound: 28 B per parameter).
+// Separately rounded operations (the library is built with -fmad=false) so that the update equals the torch-op restatement.
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+                                                        float gs) {
+    const long long n4 = n >> 2;
+    const float c1 = 1.0f - b1, c2 = 1.0f - b2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = ga[k] * gs;
+            ma[k] = ma[k] * b1 + c1 * gk;
+            va[k] = va[k] * b2 + c2 * (gk * gk);
+            pa[k] = pa[k] - (lr_t * ma[k]) / (sqrtf(va[k]) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {          // tail
+        const long long i = (n4 << 2) + threadIdx.x;
+        const float gk = g[i] * gs;
+        m[i] = m[i] * b1 + c1 * gk;
+        v[i] = v[i] * b2 + c2 * (gk * gk);
+        p[i] = p[i] - (lr_t * m[i]) / (sqrtf(v[i]) + eps);
+    }
+}
+
+int fvy_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta_1, float beta_2,
+                  float epsilon, float grad_scale, void* cuda_stream) {
+    if (!param || !grad || !m || !v || n < 0) return fail(FVY_E_INVALID, "fvy_adam_step: bad argument");
+    if (n == 0) return FVY_OK;
+    if (!is_device_ptr(param) || !is_device_ptr(grad) || !is_device_ptr(m) || !is_device_ptr(v))
+        return fail(FVY_E_INVALID, "fvy_adam_step takes device pointers (there is no CPU path)");
+    if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15)
+        return fail(FVY_E_INVALID, "fvy_adam_step: buffers must be 16-byte aligned");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long want = ((n >> 2) + 255) / 256;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
+    adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(param, grad, m, v, n, lr_t, beta_1, beta_2, epsilon, grad_scale);
+    CUDA_TRY(cudaGetLastError());
+    return FVY_OK;
+}
+
 void* fvy_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -4,7 +4,7 @@
       .detect(image) -> [BoundBox]          reference :885-949   (predict + decode + do_nms_v2 + select, one GPU call)
       .detect_batch(images) -> [[BoundBox]] additive: the same per image, batched
       .evaluate() / .test()                 reference :632-781 / :783-883  (host image loop kept; per-image detect on the GPU)
-      .train()                              reference :602-630   (SURVEY 8 f-1 "next": not built this round)
+      .train()                              reference :602-630   (data-parallel step of train.py: NCCL gradient all-reduce)
     main()                                  reference :951-985
 
 The model is the reference's: Darknet-53 base conv_0..conv_73 (:384-600) + Conv2D(6, 3x3, same, linear)
@@ -199,9 +199,36 @@ class FaceDetector(object):
         """Detect on every ``test_path/*.jpg`` and write the ``file,x,y,w,h,score`` CSV (<= 60 rows per file)."""
         self._run_files(draw_dir=None)
 
-    def train(self):
-        raise NotImplementedError("FaceDetector.train (fit_generator + multi_gpu_model, face_detection.py:602-630) is the "
-                                  "'next' row f-1 of SURVEY section 8 and is not part of this build round")
+    def train(self, device=None, on_step=None):
+        """Train on ``raw_data_path/training.csv`` (reference :602-630): MSE against the 13x13x6 ground truth, Keras Adam,
+        ``hps['epochs']`` x ``hps['step']`` steps.  Under ``torchrun`` (one process per GPU, ``conf['multi_gpu']``) every
+        rank takes its contiguous slice of each batch and gradients are all-reduced over NCCL - the replacement of
+        ``multi_gpu_model`` (:330, :369).  Weights are saved to ``WEIGHTS_PATH`` and loaded into the inference engine."""
+        import torch
+        import torch.distributed as dist
+        from .. import train as T
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        if device is None:
+            device = f"cuda:{self.device}" if torch.cuda.is_available() else "cpu"
+        seq = T.TrainingSequence(self.raw_data_path, self.hps, self.nn_arch, self.CELL_SIZE)
+        trainer = T.DataParallelTrainer(self.hps, device=device, bb_info_c_size=self.nn_arch['bb_info_c_size'], stream=self._stream)
+        for epoch in range(self.hps['epochs']):
+            for i in range(len(seq)):
+                images, gts = seq[i]
+                xs, ts = T.slice_for_rank(images, gts, rank, world)
+                if len(xs) == 0:       # a short last batch may leave a rank without images: it still joins the all-reduce
+                    xs, ts = images[:1], gts[:1]
+                loss = trainer.step(torch.from_numpy(np.ascontiguousarray(xs)), torch.from_numpy(np.ascontiguousarray(ts)))
+                if on_step is not None:
+                    on_step(epoch, i, loss)
+                elif DEBUG and rank == 0:
+                    print(f"epoch {epoch + 1}/{self.hps['epochs']} step {i + 1}/{len(seq)} loss {loss:.6f}")
+        stream = trainer.weight_stream()
+        if rank == 0:
+            print('Save the model.')
+            np.asarray(stream, '<f4').tofile(self.WEIGHTS_PATH)
+        self.set_weight_stream(stream)
 
 
 def main():

@@ -168,6 +168,13 @@ int fvy_sync(fvy_handle* h);
 /* Async variants for pipelined serving: enqueue only; results valid after fvy_sync. Host buffers must be pinned. */
 int fvy_detect_async(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp,
                      const int* image_hw, int max_out, fvy_det* dets, int32_t* det_counts);
+/* Keras-2.2.4 Adam update over one flat fp32 bucket, all pointers DEVICE memory, enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = default stream):  g' = g * grad_scale;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr_t m / (sqrt(v) + eps).
+ * lr_t carries Keras' decay and bias correction (lr / (1 + decay it) * sqrt(1 - b2^t) / (1 - b1^t)).  Replaces the optimizer the
+ * reference compiles in src/space/face_detection.py:361-364; grad_scale = 1 / world_size turns the all-reduced SUM of the
+ * per-GPU gradients into multi_gpu_model's whole-batch mean (face_detection.py:369). */
+int fvy_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta_1, float beta_2,
+                  float epsilon, float grad_scale, void* cuda_stream);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void* fvy_host_alloc(size_t bytes);
 void fvy_host_free(void* p);

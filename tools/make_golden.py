@@ -11,6 +11,8 @@ as small fixtures (this script is their provenance):
   post_fd6.npz            reference FaceDetector.detect (src/space/face_detection.py:885-949) on seeded
                           (1,13,13,6) maps through a fake model.predict.
   iou_cases.json          bbox_iou / _interval_overlap known answers computed by the reference code.
+  gt_tensor.npz           reference TrainingSequence.__getitem__ ground-truth tensors (src/space/face_detection.py:98-310)
+                          for synthetic images / training.csv rows (letterbox geometry + cell assignment).
 
 usage: python tools/make_golden.py
 """
@@ -117,6 +119,42 @@ def iou_cases():
     print("iou cases", len(out))
 
 
+def gt_tensor_cases():
+    """Reference TrainingSequence.__getitem__ (src/space/face_detection.py:98-310) on synthetic images + training.csv."""
+    import tempfile
+    import cv2 as cv
+    import pandas as pd
+    fdm = R.load_face_detection()
+    fdm.imread = lambda path: cv.imread(path, cv.IMREAD_COLOR)[:, :, ::-1]
+    sizes = {"a_wide.jpg": (640, 480), "b_tall.jpg": (375, 500), "c_square.jpg": (512, 512), "d_wide2.jpg": (1024, 300), "e_tall2.jpg": (200, 711)}
+    rng = np.random.default_rng(5)
+    rows = []
+    fid = 0
+    for name, (w, h) in sizes.items():
+        for k in range(6):
+            fw, fh = int(rng.integers(8, max(9, w // 3))), int(rng.integers(8, max(9, h // 3)))
+            fx, fy = int(rng.integers(1, w - fw)), int(rng.integers(1, h - fh))
+            if k == 4:
+                fw = 0                                      # invalid row: skipped by the reference (:147-149)
+            rows.append([fid, name, 1000 + fid, fx, fy, fw, fh]); fid += 1
+    with tempfile.TemporaryDirectory() as d:
+        for name, (w, h) in sizes.items():
+            cv.imwrite(os.path.join(d, name), np.zeros((h, w, 3), np.uint8))
+        pd.DataFrame(rows, columns=["FACE_ID", "FILE", "SUBJECT_ID", "FACE_X", "FACE_Y", "FACE_WIDTH", "FACE_HEIGHT"]).to_csv(
+            os.path.join(d, "training.csv"), index=False)
+        seq = fdm.FaceDetector.TrainingSequence(d, {"batch_size": 2}, {"image_size": 416, "bb_info_c_size": 6}, 13, 32)
+        names, targets, shapes = list(seq.file_names), [], []
+        for i in range(len(seq)):
+            x, y = seq[i]
+            targets += list(y["output"]); shapes += [im.shape for im in x["input1"]]
+    assert len(targets) == len(names) and all(s == (416, 416, 3) for s in shapes)
+    faces = np.array([[r[3], r[4], r[5], r[6]] for r in rows], np.int64)
+    owner = np.array([names.index(r[1]) for r in rows], np.int64)
+    wh = np.array([sizes[n] for n in names], np.int64)
+    np.savez_compressed(os.path.join(OUT, "gt_tensor.npz"), faces=faces, owner=owner, wh=wh, targets=np.asarray(targets, np.float64))
+    print("gt tensors", len(targets), "positive cells", int(sum((t[..., 0] > 0).sum() for t in targets)))
+
+
 if __name__ == "__main__":
     if not R.available():
         raise SystemExit("/root/reference is not available: golden fixtures can only be generated in the build container")
@@ -127,3 +165,4 @@ if __name__ == "__main__":
     post_yolo3("c", seed=23, image_hw=(500, 375), obj_thresh=0.5, nms_thresh=0.3)
     post_fd6()
     iou_cases()
+    gt_tensor_cases()
