@@ -478,16 +478,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int num_tiles = (CTA2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;   // CTA2: tiles of 256 rows
     const int row_groups = p.num_taps / p.gt;
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
-        if (p.res != nullptr) tma_prefetch_desc(&tmap_res);
-        if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
-        if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
-        for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (CTA2 ? 8 : 4) * ((BN >= 64 && p.epi_groups == 2 && p.epi_split != 0) ? 2 : 1)); }
-        for (int s = 0; s < 2 * kMaxRing; ++s) { mbar_init(&res_full_all[s], 1); mbar_init(&staged_all[s], kEpiThreads / 32); mbar_init(&free_all[s], 1); }
+    if (p.m_total < 0) return;    // profiling aid (FVY_NOWORK=2): cost of the bare launch
+    pdl_launch_dependents();      // the next layer's CTAs may be scheduled as soon as SMs free up (they wait for our completion below)
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_a);
+            tma_prefetch_desc(&tmap_b);
+            if (p.res != nullptr) tma_prefetch_desc(&tmap_res);
+            if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
+            if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
+        }
+        // all 152 barriers, 5 per lane (arrival counts: 1, except the accumulator-free and chunk-staged barriers)
+        constexpr int kBars = 2 * kMaxA + 2 * kMaxB + 2 * kMaxAcc + 6 * kMaxRing;
+        const uint32_t empty_count = (CTA2 ? 8 : 4) * ((BN >= 64 && p.epi_groups == 2 && p.epi_split != 0) ? 2 : 1);
+        for (int i = lane; i < kBars; i += 32) {
+            uint64_t* bar = a_full + i;
+            uint32_t count = 1;
+            if (bar >= tmem_empty && bar < tmem_empty + kMaxAcc) count = empty_count;           // every epilogue warp that drains the stage
+            else if (bar >= staged_all && bar < staged_all + 2 * kMaxRing) count = kEpiThreads / 32;
+            mbar_init(bar, count);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -501,10 +511,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if constexpr (CTA2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // Everything above touched no memory written by the previous layer; from here on we do.
-    // (Resident weights could be fetched before the wait; they are a few KB per CTA and overlap the first A loads anyway.)
-    pdl_launch_dependents();
-    pdl_wait();
+    // Everything above touched no memory written by the previous layer; from here on we do - except the B producer, which only
+    // reads weights: it starts streaming (or loads the resident weight tile) while the previous layer is still finishing.
+    if (warp != kBProducerWarp) pdl_wait();
 
     // Three single-thread roles feed the tensor pipe: the A producer (warp 0), the B producer (warp 10) and the MMA issuer
     // (warp 1).  Measured on B200 (tools/tma_bench.cu): one thread sustains one TMA instruction per ~170-250 cycles whatever

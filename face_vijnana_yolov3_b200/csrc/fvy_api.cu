@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/fvy.h"
@@ -299,6 +300,14 @@ struct fvy_handle {
     cudaStream_t post_stream = nullptr, ps = nullptr;       // ps: the stream post-processing is enqueued on for the current call
     cudaEvent_t ev_fwd_done[2] = {nullptr, nullptr}, ev_post_done[2] = {nullptr, nullptr};
     int logit_set = 0; bool overlap_post = true;
+    // The conv stack of one forward is captured once per (batch, dtype, input pointer, logit set) into a CUDA graph (the PDL
+    // edges between the layers are kept) and replayed: one graph launch instead of 75 kernel launches.
+    struct GraphKey {
+        int batch, dtype, set; const void* img;
+        bool operator<(const GraphKey& o) const { return std::tie(batch, dtype, set, img) < std::tie(o.batch, o.dtype, o.set, o.img); }
+    };
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    bool use_graph = true, capturing = false;
     int gh[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, head_c = 0;
     // post
     int cap = 0, capP = 0, words = 0, np2max = 0, smem_keys = 0;
@@ -306,6 +315,7 @@ struct fvy_handle {
     int* d_ibox = nullptr; float* d_obj = nullptr; float* d_cls = nullptr; int* d_cand = nullptr; int* d_counts = nullptr;
     int* d_status = nullptr; int* d_image_hw = nullptr;
     int* d_order = nullptr; int4* d_sbox = nullptr; unsigned long long* d_mask = nullptr; unsigned long long* d_gkeys = nullptr;
+    unsigned long long* d_rowflag = nullptr;
     int* d_kept = nullptr; int* d_kept_counts = nullptr;
     FvyDet* d_dets = nullptr; int* d_det_counts = nullptr; int dets_cap = 0;
     float last_fwd_ms = 0.f, last_post_ms = 0.f;
@@ -663,6 +673,7 @@ static int build_post(fvy_handle* h) {
     if (int e = dev_alloc(h, (void**)&h->d_order, (size_t)B * h->capP * 4, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_sbox, (size_t)B * h->capP * 16, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_mask, (size_t)B * h->capP * h->words * 8, false)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_rowflag, (size_t)B * h->words * 8, true)) return e;
     if (h->np2max > h->smem_keys)
         if (int e = dev_alloc(h, (void**)&h->d_gkeys, (size_t)B * h->np2max * 8, false)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_kept, n * 4, true)) return e;
@@ -716,7 +727,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
                                                                         L.w, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
             CUDA_TRY(cudaGetLastError());
             ++h->launches;
-            if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
+            if (h->last_slot >= 0 && !h->capturing) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
             continue;
         }
         if (!L.s.bn && L.head_slot >= 0)     // head logits of this call's set
@@ -742,6 +753,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             L.p.epi_split = split_env >= 0 ? split_env : ((L.BN >= 128 && (L.deep_k || tiles <= 3 * ctas)) ? 1 : 0);
         }
         if (nowork) L.p.num_m_tiles = 0;
+        if (nowork == 2) L.p.m_total = -1;
         if (int e = launch_conv(h, L, grid)) return e;
     }
     return FVY_OK;
@@ -765,7 +777,35 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
         ++h->launches;
         if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
     }
-    return run_layers(h, batch, 0, (int)h->layers.size());
+    const int nl = (int)h->layers.size();
+    if (!h->use_graph || !h->fused_stem) return run_layers(h, batch, 0, nl);
+    const fvy_handle::GraphKey key{batch, dtype, h->logit_set, dimg};
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        if (h->graphs.size() >= 16) {          // callers that keep changing device pointers: do not hoard graphs
+            for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+            h->graphs.clear();
+        }
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        const long long launches0 = h->launches;
+        CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capturing = true;
+        const int e = run_layers(h, batch, 0, nl);
+        h->capturing = false;
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+        if (e) { if (g) cudaGraphDestroy(g); return e; }
+        if (ce != cudaSuccess) return fail(FVY_E_CUDA, "graph capture of the conv stack failed: %s", cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) return fail(FVY_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        h->launches = launches0;
+        it = h->graphs.emplace(key, ge).first;
+    }
+    CUDA_TRY(cudaGraphLaunch(it->second, h->stream));
+    h->launches += nl;
+    if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
+    return FVY_OK;
 }
 
 static int copy_out(fvy_handle* h, const void* dev, void* dst, size_t bytes) {
@@ -841,12 +881,13 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
         CUDA_TRY(cudaGetLastError());
         MaskArgs m;
         m.sbox = h->d_sbox; m.counts = d_counts; m.seg_stride = seg_stride; m.batch = batch; m.capP = h->capP; m.words = h->words;
-        m.th = th; m.mask = h->d_mask;
+        m.th = th; m.mask = h->d_mask; m.rowflag = h->d_rowflag;
+        CUDA_TRY(cudaMemsetAsync(h->d_rowflag, 0, (size_t)batch * h->words * 8, h->ps));
         nms_mask_kernel<<<h->num_sms * 16, 64, 0, h->ps>>>(m);
         CUDA_TRY(cudaGetLastError());
         SweepArgs w;
         w.mask = h->d_mask; w.order = h->d_order; w.counts = d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
-        w.nb_class = nb_class; w.cls = c; w.classes = d_cls;
+        w.nb_class = nb_class; w.cls = c; w.classes = d_cls; w.rowflag = h->d_rowflag;
         nms_sweep_kernel<<<batch, 1024, (size_t)h->words * 8, h->ps>>>(w);
         CUDA_TRY(cudaGetLastError());
         h->launches += 3;
@@ -913,6 +954,7 @@ void fvy_destroy(fvy_handle* h) {
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->post_stream) cudaStreamDestroy(h->post_stream);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
     for (cudaEvent_t e : {h->ev_fwd_done[0], h->ev_fwd_done[1], h->ev_post_done[0], h->ev_post_done[1]}) if (e) cudaEventDestroy(e);
     delete h;
 }
@@ -949,6 +991,8 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
             h->ps = h->stream;
             const char* v = getenv("FVY_OVERLAP_POST");
             h->overlap_post = !(v && *v && atoi(v) == 0);
+            const char* g = getenv("FVY_GRAPH");
+            h->use_graph = !(g && *g && atoi(g) == 0);
         }
         for (cudaEvent_t* ev : {&h->ev_fwd_done[0], &h->ev_fwd_done[1], &h->ev_post_done[0], &h->ev_post_done[1]})
             ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;

@@ -385,6 +385,7 @@ struct MaskArgs {
     int batch, capP, words; // words = capP / 64
     double th;
     unsigned long long* mask;   // [B][capP][words]; only words >= row/64 are written
+    unsigned long long* rowflag; // [B][words], zeroed by the caller; see SweepArgs
 };
 
 // Persistent blocks of 64 threads; one 64x64 tile per iteration: thread t owns sorted row r*64+t and
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
                     if (iou_ge(me, cbox[j], a.th, zero_ge)) word |= 1ull << j;
             }
             a.mask[((size_t)img * a.capP + row) * a.words + c] = word;
+            if (c > r && word) atomicOr(&a.rowflag[(size_t)img * a.words + r], 1ull << threadIdx.x);
         }
     }
 }
@@ -451,17 +453,22 @@ struct SweepArgs {
     int seg_stride, capP, words;
     int nb_class, cls;
     float* classes;         // in/out
+    const unsigned long long* rowflag;   // [B][words]: bit i of word i/64 set <=> sorted row i suppresses something in a later block
 };
 
-// One block per image.  Walks the sorted list in blocks of 64.  Per block: (1) the 64 diagonal words and the
-// "score != 0" bits are fetched in parallel, (2) warp 0 resolves the in-block dependencies with the words held in
-// registers (shuffle broadcast, no memory in the dependent chain), (3) every (kept row, later word) pair is fetched
-// by its own thread and OR-ed into the removed mask with a shared-memory atomic, so a block step costs one memory
-// latency instead of one per kept row.  Boxes whose score is already 0 never suppress (yolov3_detect.py:438).
+// One block per image.  Walks the sorted list in blocks of 64.  Per block step:
+//   (1) the 64 diagonal words and the "score != 0" bits of the NEXT block are prefetched by warps 2-3 while
+//   (2) warp 0 resolves the current block with the words held in registers: only rows that are still candidates AND whose
+//       diagonal word hits another candidate can change anything, so the dependent chain visits those rows alone (none at
+//       all in the common case of a block without mutual overlaps) instead of all 64;
+//   (3) kept rows that suppress something in a LATER block (row flags set by nms_mask_kernel) have their later words
+//       OR-ed into the removed mask; rows without such a word cost no memory access.
+// Boxes whose score is already 0 never suppress (yolov3_detect.py:438).  Same result as the literal sweep (:440-444).
 __global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
     extern __shared__ unsigned long long removed[];    // [words]
-    __shared__ unsigned long long diag[64];
-    __shared__ unsigned long long alive_w, keep_w;
+    __shared__ unsigned long long diag[2][64];
+    __shared__ unsigned alive32[2][2];
+    __shared__ unsigned long long keep_w, flagged_w;
     const int img = blockIdx.x;
     const int n = min(a.counts[img], a.seg_stride);
     if (n <= 0) return;
@@ -469,46 +476,60 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
     const size_t seg = (size_t)img * a.seg_stride;
     const int* ord = a.order + (size_t)img * a.capP;
     const unsigned long long* mk = a.mask + (size_t)img * a.capP * a.words;
+    const unsigned long long* rf = a.rowflag + (size_t)img * a.words;
     for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
-    if (threadIdx.x == 0) alive_w = 0;
-    __syncthreads();
+    auto fetch_block = [&](int blk, int buf, int t /* 0..63 */) {
+        const int i = blk * 64 + t;
+        unsigned long long d = 0;
+        bool alive = false;
+        if (i < n) {
+            d = mk[(size_t)i * a.words + blk];
+            alive = a.classes[(seg + ord[i]) * a.nb_class + a.cls] != 0.f;
+        }
+        diag[buf][t] = d;
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if ((t & 31) == 0) alive32[buf][t >> 5] = bal;
+    };
+    if (threadIdx.x < 64) fetch_block(0, 0, threadIdx.x);
     for (int blk = 0; blk < nb; ++blk) {
-        if (threadIdx.x < 64) {
-            const int i = blk * 64 + threadIdx.x;
-            unsigned long long d = 0;
-            bool alive = false;
-            if (i < n) {
-                d = mk[(size_t)i * a.words + blk];
-                alive = a.classes[(seg + ord[i]) * a.nb_class + a.cls] != 0.f;
-            }
-            diag[threadIdx.x] = d;
-            const unsigned bal = __ballot_sync(0xffffffffu, alive);
-            if ((threadIdx.x & 31) == 0) atomicOr(&alive_w, (unsigned long long)bal << (threadIdx.x & 32));
-        }
-        __syncthreads();
+        const int cur = blk & 1;
+        __syncthreads();        // diag[cur] / alive32[cur] are in place; every OR into removed[blk] has been made
+        if (threadIdx.x >= 64 && threadIdx.x < 128 && blk + 1 < nb) fetch_block(blk + 1, cur ^ 1, threadIdx.x - 64);
         if (threadIdx.x < 32) {
-            const unsigned long long d_lo = diag[threadIdx.x], d_hi = diag[threadIdx.x + 32];
-            unsigned long long cur = removed[blk], keep = 0;
-            const unsigned long long alive = alive_w;
-#pragma unroll 1
-            for (int b = 0; b < 64; ++b) {
+            const int lane = threadIdx.x;
+            const unsigned long long d_lo = diag[cur][lane], d_hi = diag[cur][lane + 32];
+            const unsigned long long alive = (unsigned long long)alive32[cur][0] | ((unsigned long long)alive32[cur][1] << 32);
+            unsigned long long cr = removed[blk];
+            const unsigned long long cand = alive & ~cr;
+            const bool lo_act = ((cand >> lane) & 1ull) && (d_lo & cand) != 0ull;
+            const bool hi_act = ((cand >> (lane + 32)) & 1ull) && (d_hi & cand) != 0ull;
+            unsigned long long act = (unsigned long long)__ballot_sync(0xffffffffu, lo_act) |
+                                     ((unsigned long long)__ballot_sync(0xffffffffu, hi_act) << 32);
+            while (act) {                                   // ascending row order = the reference's score order inside the block
+                const int b = __ffsll((long long)act) - 1;
+                act &= act - 1;
                 const unsigned long long db = __shfl_sync(0xffffffffu, b < 32 ? d_lo : d_hi, b & 31);
-                if (((alive >> b) & 1ull) && !((cur >> b) & 1ull)) { keep |= 1ull << b; cur |= db; }
+                if (!((cr >> b) & 1ull)) cr |= db;
             }
-            if (threadIdx.x == 0) { removed[blk] = cur; keep_w = keep; alive_w = 0; }
+            if (lane == 0) {
+                const unsigned long long keep = alive & ~cr;
+                removed[blk] = cr; keep_w = keep; flagged_w = keep & rf[blk];
+            }
         }
         __syncthreads();
-        const unsigned long long keep = keep_w;
+        const unsigned long long fl = flagged_w;
         const int later = nb - (blk + 1);
-        for (int idx = threadIdx.x; idx < 64 * later; idx += blockDim.x) {
-            const int b = idx / later, w = blk + 1 + (idx - b * later);
-            if ((keep >> b) & 1ull) {
-                const unsigned long long m = mk[(size_t)(blk * 64 + b) * a.words + w];
-                if (m) atomicOr(&removed[w], m);
+        if (fl) {                                           // block-uniform; one pass, every (flagged row, later word) pair in parallel
+            for (int idx = threadIdx.x; idx < 64 * later; idx += blockDim.x) {
+                const int b = idx / later, w = blk + 1 + (idx - b * later);
+                if ((fl >> b) & 1ull) {
+                    const unsigned long long m = mk[(size_t)(blk * 64 + b) * a.words + w];
+                    if (m) atomicOr(&removed[w], m);
+                }
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         if ((removed[i >> 6] >> (i & 63)) & 1ull) a.classes[(seg + ord[i]) * a.nb_class + a.cls] = 0.f;   // :444
 }
