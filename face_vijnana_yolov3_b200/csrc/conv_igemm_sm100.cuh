@@ -101,6 +101,11 @@ struct ConvParams {
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
@@ -153,6 +158,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 
@@ -229,6 +242,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(map_to_cta(smem_u32(bar), 0)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(map_to_cta(smem_u32(bar), 0)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
@@ -354,6 +374,16 @@ struct SmemLayout {
 };
 __host__ __device__ constexpr int acc_stages(int bn) { return bn <= 64 ? 4 : 2; }
 
+// Packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogue is instruction-issue bound, these halve its add / multiply count.
+// Each half is an ordinary IEEE round-to-nearest operation - same result as the scalar form.
+__device__ __forceinline__ void add2(float& x0, float& x1, float y0, float y1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "+f"(x0), "+f"(x1) : "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void mul2(float& r0, float& r1, float x0, float x1, float c) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmul.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(x0), "f"(x1), "f"(c));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -401,7 +431,7 @@ __device__ __forceinline__ void mma_issue(const MmaCtx& c) {
                     if (first || !c.bres) mbar_wait(&c.b_full[bs], bph, c.bo);
                     db0 = c.desc_hi | (uint64_t)(c.b_ring16 + (uint32_t)bs * c.b_slot16);
                 }
-                if (c.dbg) dbg_full += clock64() - c0;
+                if (c.dbg) { dbg_full += clock64() - c0; if (first && u == 0 && t == 0) c.dbg[19] = globaltimer_ns(); }
                 tc_fence_after();
                 const uint64_t da = da0 + (uint32_t)(t % ACOV) * c.a_tap16, db = db0 + (uint32_t)(t % BCOV) * c.b_tap16;
 #pragma unroll
@@ -432,6 +462,7 @@ __device__ __forceinline__ void mma_issue(const MmaCtx& c) {
     if (c.dbg) {
         c.dbg[0] = (unsigned long long)(clock64() - dbg_t0); c.dbg[1] = (unsigned long long)dbg_full; c.dbg[2] = (unsigned long long)dbg_tmem;
         c.dbg[3] = (unsigned long long)dbg_taps;
+        c.dbg[20] = globaltimer_ns();
     }
 }
 
@@ -479,6 +510,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int row_groups = p.num_taps / p.gt;
 
     if (p.m_total < 0) return;    // profiling aid (FVY_NOWORK=2): cost of the bare launch
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 16] = globaltimer_ns();
     pdl_launch_dependents();      // the next layer's CTAs may be scheduled as soon as SMs free up (they wait for our completion below)
     if (warp == 0) {
         if (lane == 0) {
@@ -513,7 +545,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
     // Everything above touched no memory written by the previous layer; from here on we do - except the B producer, which only
     // reads weights: it starts streaming (or loads the resident weight tile) while the previous layer is still finishing.
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = globaltimer_ns();
     if (warp != kBProducerWarp) pdl_wait();
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 18] = globaltimer_ns();
 
     // Three single-thread roles feed the tensor pipe: the A producer (warp 0), the B producer (warp 10) and the MMA issuer
     // (warp 1).  Measured on B200 (tools/tma_bench.cu): one thread sustains one TMA instruction per ~170-250 cycles whatever
@@ -550,7 +584,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                 }
             }
-            if (p.dbg) p.dbg[blockIdx.x * 16 + 4] = (unsigned long long)dbg_wait;
+            if (p.dbg) p.dbg[blockIdx.x * 32 + 4] = (unsigned long long)dbg_wait;
         }
     } else if (warp == kBProducerWarp) {
         // ===================== B producer (resident weights: the CTA's first tile only) =====================
@@ -570,9 +604,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             if (p.dbg) dbg_wait += clock64() - c0;
                             uint8_t* sb = b_ring + bs * b_slot_bytes;
                             if (arrives) mbar_expect_tx(&b_full[bs], tx);
-                            for (int j = 0; j < p.b_cover; ++j) {
-                                if constexpr (CTA2) tma_load_2d_pair(sb + j * kBBytes, &tmap_b, &b_full[bs], ((tap0 + t + j) * p.k_chunks + kc) * BK, n0);
-                                else tma_load_2d(sb + j * kBBytes, &tmap_b, &b_full[bs], ((tap0 + t + j) * p.k_chunks + kc) * BK, n0);
+                            if (p.b_cover == 3) {      // the B tiles of a whole filter row: one 3-D box (Cin chunk, rows, 3 taps)
+                                if constexpr (CTA2) tma_load_3d_pair(sb, &tmap_b, &b_full[bs], kc * BK, n0, tap0);
+                                else tma_load_3d(sb, &tmap_b, &b_full[bs], kc * BK, n0, tap0);
+                            } else {
+                                if constexpr (CTA2) tma_load_2d_pair(sb, &tmap_b, &b_full[bs], ((tap0 + t) * p.k_chunks + kc) * BK, n0);
+                                else tma_load_2d(sb, &tmap_b, &b_full[bs], ((tap0 + t) * p.k_chunks + kc) * BK, n0);
                             }
                             if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
                         }
@@ -580,7 +617,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 if (bres) break;
             }
-            if (p.dbg) p.dbg[blockIdx.x * 16 + 5] = (unsigned long long)dbg_wait;
+            if (p.dbg) p.dbg[blockIdx.x * 32 + 5] = (unsigned long long)dbg_wait;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (CTA2: the leader CTA issues for the pair) =====================
@@ -594,7 +631,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             c.a_tap16 = (uint32_t)(p.a_slab ? kRowBytes : kABytes) >> 4; c.b_tap16 = (uint32_t)kBBytes >> 4;
             c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.bres = bres; c.bo = p.epi_groups == 2;
             c.tmem_base = tmem_base; c.units = taps_per_tile / p.gt;
-            c.first = cta_first; c.step = cta_step; c.num_tiles = num_tiles; c.dbg = p.dbg ? p.dbg + blockIdx.x * 16 : nullptr;
+            c.first = cta_first; c.step = cta_step; c.num_tiles = num_tiles; c.dbg = p.dbg ? p.dbg + blockIdx.x * 32 : nullptr;
             if (p.gt == 1) mma_issue<BN, BK, CTA2, 1, 1, 1>(c);
             else if (p.a_cover == 1) mma_issue<BN, BK, CTA2, 3, 1, 1>(c);
             else if (p.b_cover == 1) mma_issue<BN, BK, CTA2, 3, 3, 1>(c);
@@ -695,15 +732,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 b = lds128f(b4 + 16u * j);
-                        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
-                        v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
-                        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
-                        v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+                        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]); v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]);
+                        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]); v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]);
+                        add2(v[4 * j + 0], v[4 * j + 1], b.x, b.y);
+                        add2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
                     }
                 }
                 if (p.leaky) {   // LeakyReLU(0.1) == max(v, 0.1 v)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                    for (int j = 0; j < 32; j += 2) {
+                        float m0, m1;
+                        mul2(m0, m1, v[j], v[j + 1], 0.1f);
+                        v[j] = fmaxf(v[j], m0); v[j + 1] = fmaxf(v[j + 1], m1);
+                    }
                 }
                 {   // the staging buffer is ours once the residual chunk has landed in it / once its previous contents have left
                     const long long tq0 = dbg_on ? clock64() : 0;
@@ -715,10 +756,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 t = lds128(myslot + ((j ^ swz) << 4));
-                        v[8 * j + 0] += __uint_as_float(t.x << 16); v[8 * j + 1] += __uint_as_float(t.x & 0xFFFF0000u);
-                        v[8 * j + 2] += __uint_as_float(t.y << 16); v[8 * j + 3] += __uint_as_float(t.y & 0xFFFF0000u);
-                        v[8 * j + 4] += __uint_as_float(t.z << 16); v[8 * j + 5] += __uint_as_float(t.z & 0xFFFF0000u);
-                        v[8 * j + 6] += __uint_as_float(t.w << 16); v[8 * j + 7] += __uint_as_float(t.w & 0xFFFF0000u);
+                        add2(v[8 * j + 0], v[8 * j + 1], __uint_as_float(t.x << 16), __uint_as_float(t.x & 0xFFFF0000u));
+                        add2(v[8 * j + 2], v[8 * j + 3], __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xFFFF0000u));
+                        add2(v[8 * j + 4], v[8 * j + 5], __uint_as_float(t.z << 16), __uint_as_float(t.z & 0xFFFF0000u));
+                        add2(v[8 * j + 6], v[8 * j + 7], __uint_as_float(t.w << 16), __uint_as_float(t.w & 0xFFFF0000u));
                     }
                 }
                 // fp32 head logits go straight from registers (18 / 255 / 6 valid channels)
@@ -792,9 +833,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
         if (dbg_on) {
-            unsigned long long* d = p.dbg + blockIdx.x * 16 + 8;
+            unsigned long long* d = p.dbg + blockIdx.x * 32 + 8;
             d[0] = (unsigned long long)(clock64() - dbg_e0); d[1] = (unsigned long long)dbg_e_tmem; d[2] = (unsigned long long)dbg_e_res;
             d[3] = (unsigned long long)dbg_e_bar; d[4] = (unsigned long long)dbg_e_tma; d[5] = cg; d[6] = (unsigned long long)dbg_e_ld; d[7] = (unsigned long long)dbg_e_body;
+            p.dbg[blockIdx.x * 32 + 21] = globaltimer_ns();
         }
     } else if (warp >= kStoreWarp0 && warp < kStoreWarp0 + p.epi_groups) {
         // ===================== store warp of epilogue group g: every TMA instruction of the epilogue =====================
@@ -866,6 +908,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if constexpr (CTA2) tmem_dealloc_pair(tmem_base, kTmemCols);
         else tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 22] = globaltimer_ns();
 }
 
 }  // namespace fvy

@@ -70,6 +70,25 @@ static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_
     return FVY_OK;
 }
 
+// Weights [Cout][taps][Cin] bf16 seen as a 3-D tensor (Cin, Cout, tap): one box = the [box_rows, box_cols] tiles of `box_taps`
+// consecutive taps, laid out in shared memory tap after tap - i.e. the B tiles of a whole filter row with ONE TMA instruction
+// (a thread issues a TMA instruction every ~200 cycles whatever its size, tools/tma_bench.cu).
+static int make_tmap_b3(CUtensorMap* m, const void* base, uint64_t cin, uint64_t cout, uint64_t taps, uint32_t box_cols, uint32_t box_rows,
+                        uint32_t box_taps) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {cin, cout, taps};
+    cuuint64_t strides[2] = {taps * cin * 2, cin * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, box_taps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled (3-D weights) failed with CUresult %d (cin=%llu cout=%llu taps=%llu box=%ux%ux%u)",
+                                       (int)r, (unsigned long long)cin, (unsigned long long)cout, (unsigned long long)taps, box_cols, box_rows, box_taps);
+    return FVY_OK;
+}
+
 // ------------------------------------------------------------------------------------------ small kernels
 // Stem operand: im2col of the 3x3 / pad 1 / stride 1 window of the RGB input, K index = (r*3+s)*3 + c,
 // padded 27 -> 32 (one 64-byte swizzle row per pixel).  yolov3_detect.py:221 (conv_0), :205 (ZeroPadding2D(1)).
@@ -486,7 +505,8 @@ static int build_plan(fvy_handle* h) {
         L.cout_pad = (s.cout + 31) / 32 * 32;
         if (L.cout_pad > kMaxCout) return fail(FVY_E_INVALID, "conv_%d: Cout %d exceeds %d", s.idx, s.cout, kMaxCout);
         const bool has_res = s.res >= 0;
-        const int cap_n = has_res ? bn_res_cap : bn_cap;
+        int cap_n = has_res ? bn_res_cap : bn_cap;
+        if (!stem && s.k == 3 && s.stride == 1 && s.cin >= 128) cap_n = std::min(cap_n, env_int("FVY_BN3", 256));   // deep 3x3 layers: narrower tiles = finer waves
         L.BN = 32;
         for (int bn : {256, 128, 64, 32})
             if (bn <= cap_n && L.cout_pad % bn == 0) { L.BN = bn; break; }
@@ -495,14 +515,14 @@ static int build_plan(fvy_handle* h) {
         // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of the B tile): every 256-wide layer, and the
         // 128-wide 3x3 layers whose whole weight tile then fits in shared memory (conv_5/7/10)
         L.cta2 = !stem && L.BK == 64 && env_int("FVY_CTA2", 1) != 0 &&
-                 (L.BN == 256 || (L.BN == 128 && L.taps == 9 && L.num_n_tiles == 1 && env_int("FVY_CTA2_128", 1) != 0));
+                 (L.BN == 256 || (L.BN == 128 && L.taps == 9 && (L.num_n_tiles == 1 ? env_int("FVY_CTA2_128", 1) != 0 : env_int("FVY_CTA2_128", 1) >= 2)));
         // stride-1 3x3: the three column taps of a filter row read one A slab at row shifts 0, 1, 2
         const bool slab = L.taps == 9 && s.stride == 1 && env_int("FVY_SLAB", 1) != 0;
         const int srows = L.BK == 64 ? slab_rows<64>() : slab_rows<32>();
         const size_t a_tile = (size_t)kBlockM * L.BK * 2, b_tile = (size_t)(L.cta2 ? L.BN / 2 : L.BN) * L.BK * 2;
         const int a_cover = slab ? gt : (L.BK == 32 ? gt : 1);
         const size_t a_slot = slab ? (size_t)srows * L.BK * 2 : a_cover * a_tile;
-        int b_cover = (gt * b_tile <= 16384 && a_cover == gt) ? gt : 1;     // b_cover divides a_cover (the A slot rides on a B slot's barrier)
+        int b_cover = (gt == 3 && a_cover == gt && gt * b_tile <= (size_t)env_int("FVY_B3_MAX", 24576)) ? gt : 1;   // a filter row of B tiles per slot (one 3-D TMA box)
         // Layers with a short K loop are epilogue-bound: two epilogue groups alternate tiles.  Deep-K layers keep one
         // group so that the shared memory goes to the operand pipeline instead of a second staging ring.
         const int k_chunks = L.cin_pad / L.BK;
@@ -547,7 +567,8 @@ static int build_plan(fvy_handle* h) {
         const size_t kdim = (size_t)L.taps * L.cin_pad;
         if (int e = dev_alloc(h, (void**)&L.w, (size_t)L.cout_pad * kdim * 2, true)) return e;
         if (int e = dev_alloc(h, (void**)&L.bias, (size_t)L.cout_pad * 4, true)) return e;
-        if (int e = make_tmap_2d(&L.tmap_b, L.w, kdim, L.cout_pad, kdim, L.BK, L.cta2 ? L.BN / 2 : L.BN)) return e;
+        if (b_cover == 3) { if (int e = make_tmap_b3(&L.tmap_b, L.w, L.cin_pad, L.cout_pad, L.taps, L.BK, L.cta2 ? L.BN / 2 : L.BN, 3)) return e; }
+        else if (int e = make_tmap_2d(&L.tmap_b, L.w, kdim, L.cout_pad, kdim, L.BK, L.cta2 ? L.BN / 2 : L.BN)) return e;
         ConvParams& p = L.p;
         memset(&p, 0, sizeof(p));
         p.num_taps = L.taps;
@@ -1334,26 +1355,29 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (int e = run_layers(h, batch, layer, layer + 1)) return e;
     if (getenv("FVY_DBG") && !(h->layers[layer].s.src == -1 && h->fused_stem)) {
-        // cycle counters of the two single-thread roles, averaged over CTAs (profiling aid)
+        // cycle counters of the single-thread roles and wall-clock (globaltimer) milestones, from two back-to-back launches
         Layer& L = h->layers[layer];
         unsigned long long* d = nullptr;
-        const int n = h->num_sms * 16;
-        CUDA_TRY(cudaMalloc(&d, n * 8));
-        CUDA_TRY(cudaMemsetAsync(d, 0, n * 8, h->stream));
+        const int n = h->num_sms * 32;
+        CUDA_TRY(cudaMalloc(&d, 2 * n * 8));
+        CUDA_TRY(cudaMemsetAsync(d, 0, 2 * n * 8, h->stream));
         L.p.dbg = d;
         int e = run_layers(h, batch, layer, layer + 1);
+        L.p.dbg = d + n;
+        if (!e) e = run_layers(h, batch, layer, layer + 1);
         L.p.dbg = nullptr;
-        std::vector<unsigned long long> v(n);
-        cudaMemcpyAsync(v.data(), d, n * 8, cudaMemcpyDeviceToHost, h->stream);
+        std::vector<unsigned long long> v2(2 * n);
+        cudaMemcpyAsync(v2.data(), d, 2 * n * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaStreamSynchronize(h->stream);
         cudaFree(d);
         if (e) return e;
+        const unsigned long long* v = v2.data() + n;           // second launch
         double s[16] = {0}; int cnt = 0, ecnt = 0;
         for (int c = 0; c < h->num_sms; ++c)
-            if (v[c * 16] || v[c * 16 + 4] || v[c * 16 + 8]) {
-                for (int k = 0; k < 16; ++k) s[k] += (double)v[c * 16 + k];
-                if (v[c * 16]) ++cnt;
-                if (v[c * 16 + 8]) ++ecnt;
+            if (v[c * 32] || v[c * 32 + 4] || v[c * 32 + 8]) {
+                for (int k = 0; k < 16; ++k) s[k] += (double)v[c * 32 + k];
+                if (v[c * 32]) ++cnt;
+                if (v[c * 32 + 8]) ++ecnt;
             }
         if (ecnt)
             fprintf(stderr, "fvy dbg conv_%d epilogue group 0: total %.0f clk  chunks %.0f  => %.0f clk/chunk: wait_tmem_full %.0f  wait_res %.0f  "
@@ -1365,6 +1389,21 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
                             "(%.0f outside waits); producers wait_empty A %.0f B %.0f\n",
                     L.s.idx, cnt, s[0] / cnt, s[1] / cnt, s[2] / cnt, s[3] / cnt, s[0] / std::max(1.0, s[3]),
                     (s[0] - s[1] - s[2]) / std::max(1.0, s[3]), s[4] / cnt, s[5] / cnt);
+        // timeline in microseconds relative to the first CTA start of the second launch: [min / max over CTAs]
+        auto mm = [&](const unsigned long long* base, int slot, unsigned long long* lo, unsigned long long* hi) {
+            *lo = ~0ull; *hi = 0;
+            for (int c = 0; c < h->num_sms; ++c) { const unsigned long long t = base[c * 32 + slot]; if (t) { *lo = std::min(*lo, t); *hi = std::max(*hi, t); } }
+        };
+        unsigned long long lo[7], hi[7], plo, phi;
+        for (int k = 0; k < 7; ++k) mm(v, 16 + k, &lo[k], &hi[k]);
+        mm(v2.data(), 22, &plo, &phi);
+        const double t0 = (double)lo[0];
+        auto us = [&](unsigned long long t) { return t == ~0ull || t == 0 ? -1.0 : ((double)t - t0) / 1e3; };
+        fprintf(stderr, "fvy dbg conv_%d timeline [us, min..max over CTAs; 0 = first CTA start]: previous launch's last CTA end %.2f | start %.2f..%.2f | "
+                        "prologue done %.2f..%.2f | after griddepcontrol.wait %.2f..%.2f | first operands landed %.2f..%.2f | MMA loop done %.2f..%.2f | "
+                        "epilogue done %.2f..%.2f | CTA end %.2f..%.2f\n",
+                L.s.idx, ((double)phi - t0) / 1e3, us(lo[0]), us(hi[0]), us(lo[1]), us(hi[1]), us(lo[2]), us(hi[2]), us(lo[3]), us(hi[3]),
+                us(lo[4]), us(hi[4]), us(lo[5]), us(hi[5]), us(lo[6]), us(hi[6]));
     }
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     for (int it = 0; it < iters; ++it)

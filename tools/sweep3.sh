@@ -1,5 +1,3 @@
-L=${LAYERS:-1,2,3,6,10,11,27,28,45,58}
-run() { echo "== $*"; env "$@" python tools/run_layer.py --layers $L --iters 5 2>&1 | grep -v "^$" | sed -E "s/\{.*'stages': ([0-9]+).*\}/st=\1/"; }
+L=${LAYERS:-28,27,10,3,1,6}
+run() { echo "== $*"; env "$@" python tools/run_layer.py --layers $L --iters 10 2>&1 | grep -v "^$" | sed -E "s/\{.*'tile_n': ([0-9]+).*'stages': ([0-9]+).*\}/bn=\1 st=\2/" | grep -v "timeline\|dbg conv_[0-9]*:"; }
 run FVY_DBG=1
-run FVY_NB=4 FVY_NB_RES=6
-run FVY_NB=2 FVY_NB_RES=3
