@@ -222,7 +222,7 @@ def main():
     flops_step = 2.0 * eng.macs_per_image() * B                      # algorithmic, un-padded
     peaks = _peaks()
     achieved = flops_step / (fwd_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (75 launches/step + stem im2col)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": f"conv_igemm_kernel ({n_conv - 1} launches/step) + stem_conv_kernel (1 launch)", "achieved": achieved,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "frac_of_burst_peak": achieved / peaks["tf_burst"], "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_step": flops_step, "avg_launch_ms": fwd_ms / (n_conv + 1), "forward_ms": fwd_ms,
@@ -230,7 +230,12 @@ def main():
     prof = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_step")
+            tr = json.load(open(prof))
+            # dram__bytes_read.sum + dram__bytes_write.sum of the conv launches (ncu, profiles/conv_traffic.json), per launch like `achieved`
+            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+            roofline["traffic_unit"] = "bytes per launch (DRAM read + write, ncu; average over the conv launches of one step)"
+            roofline["traffic_per_step"] = tr.get("dram_bytes_per_step")
+            roofline["algorithmic_bytes_per_step_unfused"] = tr.get("algorithmic_bytes_per_step_unfused")
         except Exception:
             pass
 
