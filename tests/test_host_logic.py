@@ -99,5 +99,5 @@ def test_reference_config_schema_loads():
     fd = FaceDetector(json.loads(json.dumps(conf))["fd_conf"])   # unknown keys ignored; no GPU touched until detect()
     assert fd.cell_image_size == 32 and FaceDetector.CELL_SIZE == 13 and FaceDetector.MODEL_PATH == "face_detector.h5"
     assert fd._stream.size == 40675942
-    with pytest.raises(NotImplementedError):
-        fd.train()
+    with pytest.raises(FileNotFoundError):           # train() reads raw_data_path/training.csv like the reference (:82)
+        fd.train(device="cpu")
