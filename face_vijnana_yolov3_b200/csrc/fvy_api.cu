@@ -135,8 +135,11 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], const uint32_t 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+#ifndef STEM_MIN_BLOCKS
+#define STEM_MIN_BLOCKS 4
+#endif
 template <typename T>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax,
+__global__ void __launch_bounds__(256, STEM_MIN_BLOCKS) stem_conv_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax,
                                                         const __nv_bfloat16* __restrict__ wgt /*[32][32] k-major*/,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*4-phase*/) {
     __shared__ __align__(16) uint32_t stile[8][16][20];     // per warp: 16 pixels x 32 bf16 (16 words) + 4 words of padding
@@ -739,7 +742,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
         Layer& L = h->layers[i];
         if (L.s.src == -1 && h->fused_stem) {
             if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
-            const int blocks = h->num_sms * 8;
+            const int blocks = h->num_sms * 8;   // persistent warps, 2 waves of 4 resident blocks per SM
             if (h->cur_dtype == FVY_F32)
                 stem_conv_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
                                                                        L.w, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
