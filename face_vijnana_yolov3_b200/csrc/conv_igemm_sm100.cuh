@@ -92,6 +92,8 @@ struct ConvParams {
     int b_cover;         // taps per B slot (1 or gt)
     int b_stages;
     int b_resident;      // 1: the B ring holds the whole [BN, K] weight tile of this CTA; loaded once, never released
+    int split_from;      // CTA pairs: work items >= split_from are HALF tiles (N/2 columns) of tile split_from + (item - split_from)/2:
+                         // the last, partial wave of tiles is spread over twice as many pairs (num_tiles if no split)
     unsigned long long* dbg;   // profiling aid (FVY_DBG): per CTA 8 cycle counters, or nullptr
     OutDesc out[2];
 };
@@ -389,13 +391,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Work items of the persistent loop: full tiles, then (tail split) the two column halves of each remaining tile.
+__device__ __forceinline__ void decode_item(int item, int split_from, int& tile, int& half) {
+    if (item < split_from) { tile = item; half = -1; }
+    else { const int k = item - split_from; tile = split_from + (k >> 1); half = k & 1; }
+}
+// First global column (relative to the tile's n0) of 32-column chunk c of a half tile: the pair MMA with N/2 columns takes
+// BN/4 weight rows from EACH CTA's B tile, so accumulator columns [0, BN/4) are CTA 0's rows and [BN/4, BN/2) CTA 1's.
+template <int BN>
+__device__ __forceinline__ int half_chunk_col(int c, int half) {
+    constexpr int kQ = BN / 128;                  // chunks per CTA quarter
+    return c < kQ ? half * (BN / 4) + c * 32 : BN / 2 + half * (BN / 4) + (c - kQ) * 32;
+}
+
 // State handed to the MMA issue loop (one thread per CTA / CTA pair).
 struct MmaCtx {
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *tmem_full, *tmem_empty;
     uint64_t desc_hi;
     uint32_t a_ring16, b_ring16, a_slot16, b_slot16, a_tap16, b_tap16;   // shared-memory addresses / strides in 16-byte units
     uint32_t tmem_base;
-    int a_stages, b_stages, units, first, step, num_tiles;
+    int a_stages, b_stages, units, first, step, num_tiles, split_from;
     bool bres, bo;
     unsigned long long* dbg;
 };
@@ -405,13 +420,18 @@ struct MmaCtx {
 template <int BN, int BK, bool CTA2, int GT, int ACOV, int BCOV>
 __device__ __forceinline__ void mma_issue(const MmaCtx& c) {
     constexpr int kAcc = acc_stages(BN);
-    constexpr uint32_t kIdesc = make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, BN);
+    constexpr uint32_t kIdescFull = make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, BN);
+    constexpr uint32_t kIdescHalf = make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, BN / 2);
+    constexpr uint32_t kHalfRows16 = (uint32_t)(BN / 4) * (BK * 2) >> 4;     // BN/4 weight rows of this CTA's B tile, in 16-byte units
     int as_ = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_ph = 0;
     bool first = true;
     long long dbg_full = 0, dbg_tmem = 0, dbg_taps = 0;
     const long long dbg_t0 = c.dbg ? clock64() : 0;
-    for (int tile = c.first; tile < c.num_tiles; tile += c.step) {
+    for (int item = c.first; item < c.num_tiles; item += c.step) {
+        const int half = item < c.split_from ? -1 : ((item - c.split_from) & 1);
+        const uint32_t kIdesc = half < 0 ? kIdescFull : kIdescHalf;
+        const uint32_t b_half16 = half > 0 ? kHalfRows16 : 0u;
         long long c0 = c.dbg ? clock64() : 0;
         mbar_wait(&c.tmem_empty[acc], acc_ph ^ 1, c.bo);
         if (c.dbg) dbg_tmem += clock64() - c0;
@@ -429,7 +449,7 @@ __device__ __forceinline__ void mma_issue(const MmaCtx& c) {
                 }
                 if (t % BCOV == 0) {
                     if (first || !c.bres) mbar_wait(&c.b_full[bs], bph, c.bo);
-                    db0 = c.desc_hi | (uint64_t)(c.b_ring16 + (uint32_t)bs * c.b_slot16);
+                    db0 = c.desc_hi | (uint64_t)(c.b_ring16 + (uint32_t)bs * c.b_slot16 + b_half16);
                 }
                 if (c.dbg) { dbg_full += clock64() - c0; if (first && u == 0 && t == 0) c.dbg[19] = globaltimer_ns(); }
                 tc_fence_after();
@@ -507,6 +527,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = (CTA2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;   // CTA2: tiles of 256 rows
+    const int split_from = CTA2 ? min(p.split_from, num_tiles) : num_tiles;
+    const int num_items = num_tiles + (num_tiles - split_from);                                // tail tiles count twice (two halves)
     const int row_groups = p.num_taps / p.gt;
 
     if (p.m_total < 0) return;    // profiling aid (FVY_NOWORK=2): cost of the bare launch
@@ -565,7 +587,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const bool arrives = !CTA2 || cta_rank == 0;
             const int a_loads = p.a_slab ? 1 : p.a_cover;
             long long dbg_wait = 0;
-            for (int tile = cta_first; tile < num_tiles; tile += cta_step) {
+            for (int item = cta_first; item < num_items; item += cta_step) {
+                int tile, half;
+                decode_item(item, split_from, tile, half);
                 const int m0 = (tile / p.num_n_tiles) * (CTA2 ? 2 * kBlockM : kBlockM) + (int)cta_rank * kBlockM;
                 for (int tap0 = 0; tap0 < p.num_taps; tap0 += p.gt) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -594,7 +618,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t tx = (CTA2 ? 2u : 1u) * (uint32_t)b_slot_bytes;
             const bool arrives = !CTA2 || cta_rank == 0;
             long long dbg_wait = 0;
-            for (int tile = cta_first; tile < num_tiles; tile += cta_step) {
+            for (int item = cta_first; item < num_items; item += cta_step) {
+                int tile, half;
+                decode_item(item, split_from, tile, half);      // a half tile loads the whole B tile; the MMA reads its quarter of the rows
                 const int n0 = (tile % p.num_n_tiles) * BN + (CTA2 ? (int)cta_rank * (BN / 2) : 0);
                 for (int tap0 = 0; tap0 < p.num_taps; tap0 += p.gt) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -631,7 +657,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             c.a_tap16 = (uint32_t)(p.a_slab ? kRowBytes : kABytes) >> 4; c.b_tap16 = (uint32_t)kBBytes >> 4;
             c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.bres = bres; c.bo = p.epi_groups == 2;
             c.tmem_base = tmem_base; c.units = taps_per_tile / p.gt;
-            c.first = cta_first; c.step = cta_step; c.num_tiles = num_tiles; c.dbg = p.dbg ? p.dbg + blockIdx.x * 32 : nullptr;
+            c.first = cta_first; c.step = cta_step; c.num_tiles = num_items; c.split_from = split_from; c.dbg = p.dbg ? p.dbg + blockIdx.x * 32 : nullptr;
             if (p.gt == 1) mma_issue<BN, BK, CTA2, 1, 1, 1>(c);
             else if (p.a_cover == 1) mma_issue<BN, BK, CTA2, 3, 1, 1>(c);
             else if (p.b_cover == 1) mma_issue<BN, BK, CTA2, 3, 3, 1>(c);
@@ -676,8 +702,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         long long dbg_e_tmem = 0, dbg_e_res = 0, dbg_e_bar = 0, dbg_e_tma = 0, dbg_e_ld = 0, dbg_e_body = 0; const long long dbg_e0 = dbg_on ? clock64() : 0;
         uint32_t it_tile = split ? 0 : g;          // index of the tile in this CTA's sequence (selects the accumulator stage)
         uint32_t my_tiles = 0;
-        for (int tile = tile_first; tile < num_tiles; tile += tile_step, it_tile += (split ? 1 : ng), ++my_tiles) {
+        for (int item = tile_first; item < num_items; item += tile_step, it_tile += (split ? 1 : ng), ++my_tiles) {
             const long long tt0 = dbg_on ? clock64() : 0;
+            int tile, half;
+            decode_item(item, split_from, tile, half);
+            const int n_chunks = half < 0 ? kChunks : kChunks / 2;
             const int as = it_tile % kAcc;
             const uint32_t myrow = myrow_base + (my_tiles & 1) * 2 * kBlockM * 4u;   // double-buffered: a fast thread may be one tile ahead
             const int mt = nnt == 1 ? tile : tile / nnt;
@@ -718,13 +747,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = c_first; c < kChunks; c += c_step, ++cg) {
-                const int c0 = c * 32;
+            for (int c = c_first; c < n_chunks; c += c_step, ++cg) {
+                const int tc = c * 32;                                            // accumulator column of the chunk
+                const int c0 = half < 0 ? tc : half_chunk_col<BN>(c, half);       // its first channel inside the N tile
                 const uint32_t sbuf = ring_u32 + (uint32_t)buf * kChunkBytes;
                 const uint32_t myslot = sbuf + (uint32_t)r * 64u;
                 uint32_t acc[32];
                 const long long tl0 = dbg_on ? clock64() : 0;
-                tmem_ld_32x32(taddr + c0, acc);
+                tmem_ld_32x32(taddr + tc, acc);
                 tmem_ld_wait();
                 float v[32];
                 {
@@ -859,29 +889,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
             const int m_rank_off = (int)cta_rank * kBlockM;
             // residual prefetch cursor: walks this group's chunks in order, one staging buffer after the other
-            int pf_tile = tile_first, pf_chunk = c_first, pf_buf = 0;
+            int pf_item = tile_first, pf_chunk = c_first, pf_buf = 0;
             auto prefetch_res = [&]() {
-                if (pf_tile < num_tiles) {
+                if (pf_item < num_items) {
+                    int tile, half;
+                    decode_item(pf_item, split_from, tile, half);
+                    const int col = half < 0 ? pf_chunk * 32 : half_chunk_col<BN>(pf_chunk, half);
                     mbar_expect_tx(&res_full[pf_buf], kChunkBytes);
                     tma_load_2d(ring + pf_buf * kChunkBytes, &tmap_res, &res_full[pf_buf],
-                                p.res_choff + (pf_tile % p.num_n_tiles) * BN + pf_chunk * 32, (pf_tile / p.num_n_tiles) * kTileM + m_rank_off);
-                    if ((pf_chunk += c_step) >= kChunks) { pf_chunk = c_first; pf_tile += tile_step; }
+                                p.res_choff + (tile % p.num_n_tiles) * BN + col, (tile / p.num_n_tiles) * kTileM + m_rank_off);
+                    if ((pf_chunk += c_step) >= (half < 0 ? kChunks : kChunks / 2)) { pf_chunk = c_first; pf_item += tile_step; }
                 }
                 if (++pf_buf == nb) pf_buf = 0;
             };
             if (has_res)
                 for (int i = 0; i < nb; ++i) prefetch_res();      // every buffer starts free
             int buf = 0, prev = -1; uint32_t sph = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            for (int item = tile_first; item < num_items; item += tile_step) {
+                int tile, half;
+                decode_item(item, split_from, tile, half);
+                const int n_chunks = half < 0 ? kChunks : kChunks / 2;
                 const int m0 = (tile / p.num_n_tiles) * kTileM + m_rank_off;
                 const int n0 = (tile % p.num_n_tiles) * BN;
 #pragma unroll 1
-                for (int c = c_first; c < kChunks; c += c_step) {
+                for (int c = c_first; c < n_chunks; c += c_step) {
+                    const int col = half < 0 ? c * 32 : half_chunk_col<BN>(c, half);
                     mbar_wait(&staged[buf], sph);
                     if (any_tma) {
                         const uint8_t* sbuf = ring + buf * kChunkBytes;
-                        if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + c * 32, m0);
-                        if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + c * 32, m0);
+                        if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + col, m0);
+                        if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + col, m0);
                         bulk_commit();
                     }
                     if (prev >= 0) {

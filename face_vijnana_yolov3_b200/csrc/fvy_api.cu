@@ -775,6 +775,16 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             const int ctas = L.cta2 ? grid / 2 : grid;
             static const int split_env = [] { const char* v = getenv("FVY_SPLIT"); return v && *v ? atoi(v) : -1; }();
             L.p.epi_split = split_env >= 0 ? split_env : ((L.BN >= 128 && (L.deep_k || tiles <= 3 * ctas)) ? 1 : 0);
+            // Tail split (CTA pairs, FVY_TAIL_SPLIT=1): when the last wave of tiles would occupy at most half of the pairs, each
+            // of its tiles is processed as two column halves by two pairs.  Measured: a half tile is latency-bound on the
+            // operand ring (6 taps in flight at 256 clk per tap) and takes 0.96 of a full tile's time - 2.5 us off a 26^2
+            // layer in isolation, nothing in the chained forward - so it is OFF by default.
+            static const int tail_env = [] { const char* v = getenv("FVY_TAIL_SPLIT"); return v && *v ? atoi(v) : 0; }();
+            L.p.split_from = tiles;
+            if (L.cta2 && tail_env && L.p.epi_split && tiles > ctas) {
+                const int full = (tiles / ctas) * ctas, t = tiles - full;
+                if (t > 0 && 2 * t <= ctas) L.p.split_from = full;
+            }
         }
         if (nowork) L.p.num_m_tiles = 0;
         if (nowork == 2) L.p.m_total = -1;
