@@ -94,6 +94,14 @@ struct ConvParams {
     int b_resident;      // 1: the B ring holds the whole [BN, K] weight tile of this CTA; loaded once, never released
     int split_from;      // CTA pairs: work items >= split_from are HALF tiles (N/2 columns) of tile split_from + (item - split_from)/2:
                          // the last, partial wave of tiles is spread over twice as many pairs (num_tiles if no split)
+    // Cross-layer tile dependencies (instead of the kernel boundary): a layer whose outputs all leave by TMA counts, per
+    // 128-row block of its output, the (N tile, epilogue group) pairs whose stores have completed; a consumer of the same
+    // geometry starts a tile as soon as the blocks its A rows (and residual rows) come from are complete.
+    int* sig_flags;            // this layer's completion counters [ceil(rows / 128)], or nullptr
+    const int* wait_flags;     // the producer's counters, or nullptr (then griddepcontrol.wait orders the layers)
+    int wait_expected;         // value of a complete counter
+    int wait_margin;           // rows before / after the tile that its taps reach (W + 3 for 3x3, 0 for 1x1)
+    int wait_blocks;           // number of counters of the producer
     unsigned long long* dbg;   // profiling aid (FVY_DBG): per CTA 8 cycle counters, or nullptr
     OutDesc out[2];
 };
@@ -391,6 +399,46 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- cross-layer tile dependencies ------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Blocks until the producer's 128-row blocks [lo, hi] are complete; `ready` caches the highest block known complete
+// (tiles are visited in increasing row order).  The loads that follow are TMA (async proxy): fence after the acquire.
+__device__ __forceinline__ void wait_blocks_ready(const int* flags, int expected, int lo, int hi, int& ready) {
+    if (hi <= ready) return;
+    for (int b = max(lo, ready + 1); b <= hi; ++b) {
+        for (uint32_t spin = 0; ld_acquire_gpu(flags + b) < expected; ++spin) {
+            __nanosleep(spin < 16 ? 40 : 200);
+            if (spin > (1u << 22)) {
+                printf("fvy: tile dependency wait timed out (block %d, counter %d of %d)\n", blockIdx.x, b, expected);
+                __trap();
+            }
+        }
+    }
+    ready = hi;
+    fence_proxy_async_all();
+}
+__device__ __forceinline__ void bulk_wait_complete(int n) {   // at most n of this thread's bulk groups still pending (writes performed)
+    switch (n) {
+        case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.bulk.wait_group 6;" ::: "memory"); break;
+        case 7: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group 8;" ::: "memory"); break;
+    }
+}
+
 // Work items of the persistent loop: full tiles, then (tail split) the two column halves of each remaining tile.
 __device__ __forceinline__ void decode_item(int item, int split_from, int& tile, int& half) {
     if (item < split_from) { tile = item; half = -1; }
@@ -568,7 +616,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // Everything above touched no memory written by the previous layer; from here on we do - except the B producer, which only
     // reads weights: it starts streaming (or loads the resident weight tile) while the previous layer is still finishing.
     if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = globaltimer_ns();
-    if (warp != kBProducerWarp) pdl_wait();
+    if (warp != kBProducerWarp && p.wait_flags == nullptr) pdl_wait();
     if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 18] = globaltimer_ns();
 
     // Three single-thread roles feed the tensor pipe: the A producer (warp 0), the B producer (warp 10) and the MMA issuer
@@ -586,11 +634,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t tx = (CTA2 ? 2u : 1u) * (uint32_t)a_slot_bytes;   // CTA2: the leader's arrival expects the bytes of BOTH CTAs
             const bool arrives = !CTA2 || cta_rank == 0;
             const int a_loads = p.a_slab ? 1 : p.a_cover;
+            int dep_ready = -1;
             long long dbg_wait = 0;
             for (int item = cta_first; item < num_items; item += cta_step) {
                 int tile, half;
                 decode_item(item, split_from, tile, half);
                 const int m0 = (tile / p.num_n_tiles) * (CTA2 ? 2 * kBlockM : kBlockM) + (int)cta_rank * kBlockM;
+                if (p.wait_flags != nullptr)      // the producer's row blocks this tile's taps reach
+                    wait_blocks_ready(p.wait_flags, p.wait_expected, max(0, (m0 - p.wait_margin) >> 7),
+                                      min(p.wait_blocks - 1, (m0 + kBlockM - 1 + p.wait_margin) >> 7), dep_ready);
                 for (int tap0 = 0; tap0 < p.num_taps; tap0 += p.gt) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         for (int t = 0; t < p.gt; t += p.a_cover) {
@@ -890,10 +942,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int m_rank_off = (int)cta_rank * kBlockM;
             // residual prefetch cursor: walks this group's chunks in order, one staging buffer after the other
             int pf_item = tile_first, pf_chunk = c_first, pf_buf = 0;
+            int dep_ready = -1;
             auto prefetch_res = [&]() {
                 if (pf_item < num_items) {
                     int tile, half;
                     decode_item(pf_item, split_from, tile, half);
+                    if (p.wait_flags != nullptr) {     // the residual rows were written by an earlier layer of the same chain
+                        const int rm0 = (tile / p.num_n_tiles) * kTileM + m_rank_off;
+                        wait_blocks_ready(p.wait_flags, p.wait_expected, max(0, (rm0 - p.wait_margin) >> 7),
+                                          min(p.wait_blocks - 1, (rm0 + kBlockM - 1 + p.wait_margin) >> 7), dep_ready);
+                    }
                     const int col = half < 0 ? pf_chunk * 32 : half_chunk_col<BN>(pf_chunk, half);
                     mbar_expect_tx(&res_full[pf_buf], kChunkBytes);
                     tma_load_2d(ring + pf_buf * kChunkBytes, &tmap_res, &res_full[pf_buf],
@@ -927,6 +985,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     prev = buf;
                     if (++buf == nb) { buf = 0; sph ^= 1; }
+                }
+                if (p.sig_flags != nullptr) {
+                    // this tile's stores have been performed: publish its row block (async-proxy writes -> generic release).
+                    // The store warp has slack in the layers that signal (few, long tiles per CTA).
+                    bulk_wait_complete(0);
+                    fence_proxy_async_all();
+                    red_release_gpu_add(p.sig_flags + (m0 >> 7), 1);
                 }
             }
             if (prev >= 0) {

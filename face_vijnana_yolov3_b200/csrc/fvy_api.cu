@@ -276,6 +276,11 @@ struct Layer {
     int BN, BK, stages, b_stages = 0, b_resident = 0, num_n_tiles, cout_pad, cin_pad, taps, occ;
     bool deep_k = false;
     int head_slot = -1;           // index of the logit tensor a head layer writes
+    // cross-layer tile dependencies (see ConvParams::sig_flags)
+    bool signals = false;         // every stored form leaves by TMA and a consumer waits on the counters
+    int wait_on = -1;             // index (in h->layers) of the producer whose counters gate this layer's tiles, or -1
+    int* flags = nullptr;         // this layer's counters
+    int flag_blocks = 0;
     bool cta2 = false;            // CTA pair (cta_group::2): 256-row tiles, each CTA stages half of the B tile
     size_t smem_bytes;
     __nv_bfloat16* w = nullptr;   // [cout_pad][taps * cin_pad]
@@ -330,6 +335,7 @@ struct fvy_handle {
     };
     std::map<GraphKey, cudaGraphExec_t> graphs;
     bool use_graph = true, capturing = false;
+    int* d_flags = nullptr; size_t flags_bytes = 0; bool use_flags = true, flags_live = false;
     int gh[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, head_c = 0;
     // post
     int cap = 0, capP = 0, words = 0, np2max = 0, smem_keys = 0;
@@ -656,6 +662,35 @@ static int build_plan(fvy_handle* h) {
         h->layers.push_back(L);
     }
     h->weight_count = (long long)stream_off;
+    // ---- cross-layer tile dependencies: consumer = stride-1 conv reading the plain padded output of a producer whose stored
+    // forms all leave by TMA (same geometry: the consumer's compute-domain rows ARE the producer's output rows)
+    {
+        h->use_flags = env_int("FVY_FLAGS", 1) != 0;
+        std::map<int, int> layer_of;
+        for (size_t i = 0; i < h->layers.size(); ++i) layer_of[h->layers[i].s.idx] = (int)i;
+        size_t total = 0;
+        for (size_t i = 0; i < h->layers.size() && h->use_flags; ++i) {
+            Layer& C = h->layers[i];
+            if (C.s.src < 0 || C.s.stride != 1 || !layer_of.count(C.s.src)) continue;
+            Layer& P = h->layers[layer_of[C.s.src]];
+            if (P.s.level != C.s.level) continue;
+            bool pure_tma = true;
+            for (int o = 0; o < 2; ++o)
+                if (P.p.out[o].kind != OUT_NONE && !P.p.out[o].tma) pure_tma = false;
+            if (!pure_tma || P.p.out[0].kind != OUT_PADDED) continue;
+            C.wait_on = layer_of[C.s.src];
+            P.signals = true;
+        }
+        for (Layer& L : h->layers)
+            if (L.signals) { L.flag_blocks = (int)(((size_t)nmax * L.p.dom_plane + 127) / 128) + 2; total += (size_t)L.flag_blocks; }
+        if (total) {
+            h->flags_bytes = total * sizeof(int);
+            if (int e = dev_alloc(h, (void**)&h->d_flags, h->flags_bytes, true)) return e;
+            size_t off = 0;
+            for (Layer& L : h->layers)
+                if (L.signals) { L.flags = h->d_flags + off; off += (size_t)L.flag_blocks; }
+        }
+    }
     return FVY_OK;
 }
 
@@ -738,6 +773,19 @@ static int stage_input(fvy_handle* h, const void* images, int dtype, int batch, 
 }
 
 static int run_layers(fvy_handle* h, int batch, int first, int last) {
+    // Tile dependencies pay off where a CTA only gets a few (long) tiles: the per-tile flag check is a global round trip
+    // (~0.5 us) on the A producer, the gain is the overlap of one layer's last wave / drain with the next layer's start.
+    static const int flags_max_tiles = [] { const char* v = getenv("FVY_FLAGS_MAX_TILES"); return v && *v ? atoi(v) : 8; }();
+    std::vector<char> wait_live(h->layers.size(), 0), sig_live(h->layers.size(), 0);
+    if (h->flags_live)
+        for (size_t i = 0; i < h->layers.size(); ++i) {
+            const Layer& C = h->layers[i];
+            if (C.wait_on < 0) continue;
+            const int m_tiles = (batch * C.p.dom_plane + kBlockM - 1) / kBlockM;
+            const int tiles = C.cta2 ? ((m_tiles + 1) / 2) * C.num_n_tiles : m_tiles * C.num_n_tiles;
+            const int ctas = std::max(1, std::min(tiles, C.cta2 ? h->num_sms / 2 : h->num_sms));
+            if ((tiles + ctas - 1) / ctas <= flags_max_tiles) { wait_live[i] = 1; sig_live[C.wait_on] = 1; }
+        }
     for (int i = first; i < last; ++i) {
         Layer& L = h->layers[i];
         if (L.s.src == -1 && h->fused_stem) {
@@ -786,6 +834,19 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
                 if (t > 0 && 2 * t <= ctas) L.p.split_from = full;
             }
         }
+        {   // tile dependencies are live only inside a whole forward (every producer runs in the same pass)
+            L.p.sig_flags = (sig_live[i] && L.signals) ? L.flags : nullptr;
+            L.p.wait_flags = nullptr;
+            if (wait_live[i]) {
+                const Layer& P = h->layers[L.wait_on];
+                const int pgroups = (P.p.epi_groups == 2 && P.BN >= 64 && P.p.epi_split != 0) ? 2 : 1;
+                L.p.wait_flags = P.flags;
+                L.p.wait_expected = P.num_n_tiles * pgroups;
+                L.p.wait_margin = L.s.k == 3 ? L.Win + 3 : 0;
+                L.p.wait_blocks = (batch * P.p.dom_plane + 127) / 128;      // row blocks the producer really writes in this call
+            }
+            if (L.p.sig_flags) L.p.split_from = L.cta2 ? ((L.p.num_m_tiles + 1) / 2) * L.p.num_n_tiles : L.p.num_m_tiles * L.p.num_n_tiles;
+        }
         if (nowork) L.p.num_m_tiles = 0;
         if (nowork == 2) L.p.m_total = -1;
         if (int e = launch_conv(h, L, grid)) return e;
@@ -812,7 +873,49 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
         if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
     }
     const int nl = (int)h->layers.size();
-    if (!h->use_graph || !h->fused_stem) return run_layers(h, batch, 0, nl);
+    auto run_all = [&]() -> int {          // one whole forward: the tile-dependency counters start at zero and are live
+        if (h->use_flags && h->d_flags) {
+            CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, h->flags_bytes, h->stream));
+            h->flags_live = true;
+        }
+        // FVY_TRACE=1 (with FVY_GRAPH=0): %globaltimer milestones of every layer of this forward, printed to stderr
+        static const bool trace = getenv("FVY_TRACE") != nullptr;
+        unsigned long long* d = nullptr;
+        const size_t per = (size_t)h->num_sms * 32;
+        if (trace && !h->capturing) {
+            CUDA_TRY(cudaMalloc(&d, per * nl * 8));
+            CUDA_TRY(cudaMemsetAsync(d, 0, per * nl * 8, h->stream));
+            for (int i = 0; i < nl; ++i) h->layers[i].p.dbg = d + per * i;
+        }
+        const int e = run_layers(h, batch, 0, nl);
+        h->flags_live = false;
+        if (d) {
+            for (int i = 0; i < nl; ++i) h->layers[i].p.dbg = nullptr;
+            std::vector<unsigned long long> v(per * nl);
+            cudaMemcpyAsync(v.data(), d, per * nl * 8, cudaMemcpyDeviceToHost, h->stream);
+            cudaStreamSynchronize(h->stream);
+            cudaFree(d);
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < nl; ++i)
+                for (int c = 0; c < h->num_sms; ++c) { const unsigned long long t = v[per * i + c * 32 + 16]; if (t) t0 = std::min(t0, t); }
+            double prev_end = 0;
+            for (int i = 0; i < nl; ++i) {
+                unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+                const int slot[3] = {16, 19, 22};      // CTA start, first operands landed (leader CTAs), CTA end
+                for (int c = 0; c < h->num_sms; ++c)
+                    for (int k = 0; k < 3; ++k) { const unsigned long long t = v[per * i + c * 32 + slot[k]]; if (t) { lo[k] = std::min(lo[k], t); hi[k] = std::max(hi[k], t); } }
+                if (hi[0] == 0) continue;
+                auto us = [&](unsigned long long t) { return ((double)t - (double)t0) / 1e3; };
+                const Layer& L = h->layers[i];
+                fprintf(stderr, "trace conv_%-4d wait_on=%2d sig=%d | start %8.2f..%8.2f | first operands %8.2f..%8.2f | end %8.2f..%8.2f | since prev end %+7.2f | span %7.2f\n",
+                        L.s.idx, L.p.wait_flags ? L.wait_on : -1, L.p.sig_flags ? 1 : 0, us(lo[0]), us(hi[0]), us(lo[1]), us(hi[1]), us(lo[2]), us(hi[2]),
+                        us(hi[2]) - prev_end, us(hi[2]) - us(lo[0]));
+                prev_end = us(hi[2]);
+            }
+        }
+        return e;
+    };
+    if (!h->use_graph || !h->fused_stem) return run_all();
     const fvy_handle::GraphKey key{batch, dtype, h->logit_set, dimg};
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
@@ -825,7 +928,7 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
         const long long launches0 = h->launches;
         CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->capturing = true;
-        const int e = run_layers(h, batch, 0, nl);
+        const int e = run_all();
         h->capturing = false;
         const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
         if (e) { if (g) cudaGraphDestroy(g); return e; }
