@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfvy.so")
+LIB_PATH = os.environ.get("FVY_LIB_PATH") or os.path.join(_HERE, "libfvy.so")   # FVY_LIB_PATH: A/B runs against another build
 
 FVY_OK = 0
 FVY_E_INVALID, FVY_E_CUDA, FVY_E_STATE, FVY_E_CAPACITY, FVY_E_RANGE = -1, -2, -3, -4, -5

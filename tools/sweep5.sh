@@ -1,4 +1,4 @@
-cat > /tmp/fwdt.py <<PY
+cat > /tmp/fwdt.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
@@ -7,6 +7,13 @@ from face_vijnana_yolov3_b200.engine import Engine
 eng = Engine(416, 416, nb_class=1, max_batch=40)
 eng.load_weights(synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT))
 xd = torch.from_numpy(synth.images(40, 416, 416, 1)).cuda()
-for _ in range(4): eng.forward(xd, want_outputs=False)
+for _ in range(10): eng.forward(xd, want_outputs=False)
+ts = []
+for _ in range(40):
+    eng.forward(xd, want_outputs=False); ts.append(eng.last_timing()[0])
+print("forward ms median %.3f min %.3f" % (float(np.median(ts)), min(ts)))
 PY
-for f in 1 0; do echo "== FVY_FLAGS=$f"; FVY_TRACE=1 FVY_GRAPH=0 FVY_FLAGS=$f python /tmp/fwdt.py 2>&1 | grep "trace" | tail -75 > gpurun_out/trace$f.log; tail -45 gpurun_out/trace$f.log | head -30; done
+for rep in 1 2; do
+for cfg in "FVY_LIB_PATH=$PWD/face_vijnana_yolov3_b200/libfvy_old.so FVY_FLAGS=0" "FVY_LIB_PATH=$PWD/face_vijnana_yolov3_b200/libfvy_old.so FVY_FLAGS=1" "FVY_DYN=0 FVY_FLAGS=0" "FVY_DYN=0 FVY_FLAGS=1" "FVY_DYN=1 FVY_FLAGS=1" "FVY_DYN=1 FVY_FLAGS=1 FVY_DYN_MAX_TILES=4"; do
+  echo "== $cfg" | sed "s#$PWD/face_vijnana_yolov3_b200/##"; env $cfg python /tmp/fwdt.py 2>&1 | tail -1
+done; done
