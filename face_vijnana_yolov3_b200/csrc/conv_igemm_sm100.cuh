@@ -786,7 +786,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if (od.kind == OUT_PADDED) ridx = (img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
                     else if (od.kind == OUT_PHASE) {
                         const int hp = h + 1, wp = w + 1;
-                        const int pw = (p.W >> 1) + 1, plane = ((p.H >> 1) + 1) * pw;
+                        const int pw = (p.W >> 1) + 2, plane = ((p.H >> 1) + 2) * pw;    // planes of the consumer's padded output geometry
                         ridx = ((((hp & 1) << 1) | (wp & 1)) * od.nmax + img) * plane + (hp >> 1) * pw + (wp >> 1);
                     } else ridx = (img * (2 * p.H + 2) + (2 * h + 1)) * (2 * p.W + 2) + (2 * w + 1);   // OUT_UP2_PADDED
                 }

@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(256, STEM_MIN_BLOCKS) stem_conv_kernel(const T
     for (int j = 0; j < 4; ++j) { bia[j][0] = __ldg(bias + j * 8 + quad * 2); bia[j][1] = __ldg(bias + j * 8 + quad * 2 + 1); }
     const int tiles_per_row = W >> 4;
     const int total_tiles = batch * H * tiles_per_row;      // < 2^31 (checked on the host)
-    const int pw = (W >> 1) + 1;
-    const long long plane = (long long)((H >> 1) + 1) * pw;
+    const int pw = (W >> 1) + 2;      // phase planes have the padded geometry of the stride-2 conv's OUTPUT
+    const long long plane = (long long)((H >> 1) + 2) * pw;
     // Per-lane gather table: the 8 K indices this lane feeds (k = ks*16 + half*8 + quad*2 + e) never change, so their
     // element offsets relative to the centre pixel and their edge sensitivities are computed once.
     int koff[8];
@@ -259,8 +259,8 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
             long long row;
             if (od.kind == OUT_PADDED) row = (n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
             else if (od.kind == OUT_PHASE) {
-                const int hp = h + 1, wp = w + 1, ph = ((hp & 1) << 1) | (wp & 1), pw = (W >> 1) + 1;
-                const long long plane = (long long)((H >> 1) + 1) * pw;
+                const int hp = h + 1, wp = w + 1, ph = ((hp & 1) << 1) | (wp & 1), pw = (W >> 1) + 2;
+                const long long plane = (long long)((H >> 1) + 2) * pw;
                 row = ((long long)ph * od.nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
             } else row = (n * (2 * H + 2) + (2 * h + 1)) * (2 * W + 2) + (2 * w + 1);
             v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(od.ptr)[row * od.pitch + od.choff + c]);
@@ -475,7 +475,7 @@ static int build_plan(fvy_handle* h) {
         if (need_padded.count(s.idx))
             if (int e = dev_alloc(h, (void**)&tb.padded, (size_t)nmax * (H + 2) * (W + 2) * s.cout * 2, true)) return e;
         if (need_phase.count(s.idx))
-            if (int e = dev_alloc(h, (void**)&tb.phase, (size_t)4 * nmax * (H / 2 + 1) * (W / 2 + 1) * s.cout * 2, true)) return e;
+            if (int e = dev_alloc(h, (void**)&tb.phase, (size_t)4 * nmax * (H / 2 + 2) * (W / 2 + 2) * s.cout * 2, true)) return e;
         bufs[s.idx] = tb;
     }
     // heads
@@ -598,12 +598,16 @@ static int build_plan(fvy_handle* h) {
             p.dom_plane = L.Hin * L.Win; p.dom_w = L.Win; p.dom_off = 0; p.tap_off[0] = 0;
         } else if (s.stride == 2) {
             const int Ho = L.Hout, Wo = L.Wout;
-            const long long plane = (long long)(Ho + 1) * (Wo + 1);
+            // The compute domain is the padded geometry of the OUTPUT ((Ho+2) x (Wo+2), like a stride-1 layer), and the four
+            // phase planes of the input are stored with that same geometry: output pixel (h, w) = domain row m reads phase
+            // (r&1, s&1) at position (h + (r>>1), w + (s>>1)) = row m + ((r>>1) - 1) * (Wo+2) + ((s>>1) - 1) of that plane:
+            // every tap is a constant row shift AND the rows of the domain are the rows of the padded output (TMA stores).
+            const long long plane = (long long)(Ho + 2) * (Wo + 2);
             a_base = bufs[s.src].phase; a_rows = (uint64_t)(4 * nmax * plane); a_pitch = s.cin;
-            p.dom_plane = (int)plane; p.dom_w = Wo + 1; p.dom_off = 0;
+            p.dom_plane = (int)plane; p.dom_w = Wo + 2; p.dom_off = 1;
             for (int r = 0; r < 3; ++r)
                 for (int q = 0; q < 3; ++q)
-                    p.tap_off[r * 3 + q] = (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + (r >> 1) * (Wo + 1) + (q >> 1));
+                    p.tap_off[r * 3 + q] = (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + ((r >> 1) - 1) * (Wo + 2) + ((q >> 1) - 1));
         } else {
             const int H = L.Hin, W = L.Win;
             if (s.src == -2) { a_base = catA; a_pitch = 768; }
@@ -622,8 +626,9 @@ static int build_plan(fvy_handle* h) {
         if ((long long)nmax * p.dom_plane >= (1ll << 31)) return fail(FVY_E_INVALID, "conv_%d: %d x %d rows overflow int32", s.idx, nmax, p.dom_plane);
         if (int e = make_tmap_2d(&L.tmap_a, a_base, a_pitch, a_rows, a_pitch, L.BK, slab ? srows : kBlockM)) return e;
         L.tmap_res = L.tmap_a; L.tmap_out[0] = L.tmap_a; L.tmap_out[1] = L.tmap_a;   // placeholders for unused maps
-        // rows of the compute domain coincide with rows of a padded (H, W) buffer only for stride-1 convs on a padded input
-        const bool coincident = !stem && s.stride == 1;
+        // rows of the compute domain coincide with rows of the padded (H, W) output buffer (stride-1 convs on a padded input,
+        // stride-2 convs on phase planes of the output's geometry)
+        const bool coincident = !stem;
         const uint64_t out_rows = (uint64_t)nmax * (L.Hout + 2) * (L.Wout + 2);
         if (s.res >= 0) {
             p.res = bufs[s.res].padded; p.res_pitch = by_idx[s.res]->cout; p.res_choff = 0;
