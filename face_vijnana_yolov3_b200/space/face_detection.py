@@ -162,29 +162,38 @@ class FaceDetector(object):
                 box.ymax = np.min([box.ymax * h / S, h])
 
     def _run_files(self, draw_dir=None):
+        """The reference's per-file loop (:645-735, :788-883) with the detector call batched: files are letterboxed on the
+        host exactly as the reference does (cv2 cubic resize + zero border), ``max_batch`` of them go through ONE
+        ``detect_batch`` call, and rows are written in the reference's file order.  ``max_batch = 1`` is the reference."""
         import cv2 as cv
         test_path = self.conf['test_path']
         output_file_path = self.conf['output_file_path']
         file_names = glob.glob(os.path.join(test_path, '*.jpg'))
+        bs = max(1, int(self.max_batch))
         with open(output_file_path, 'w') as f:
-            for count1, file_name in enumerate(file_names, 1):
-                if DEBUG:
-                    print(count1, '/', len(file_names), file_name)
-                image_o = cv.imread(file_name, cv.IMREAD_COLOR)[:, :, ::-1]   # RGB like skimage.io.imread
-                image, geom = self._letterbox(image_o / 255)
-                boxes = self.detect(image)
-                self._unletterbox(boxes, geom)
-                base = file_name.split('\\')[-1] if platform.system() == 'Windows' else file_name.split('/')[-1]
-                for count, box in enumerate(boxes, 1):
-                    if count > 60:                                                # :729, :870
-                        break
-                    f.write(base + ',' + str(box.xmin) + ',' + str(box.ymin) + ',')
-                    f.write(str(box.xmax - box.xmin) + ',' + str(box.ymax - box.ymin) + ',' + str(box.get_score()) + '\n')
-                if draw_dir is not None and len(boxes) > 0:
-                    canvas = np.ascontiguousarray(image_o[:, :, ::-1])
-                    for box in boxes:
-                        cv.rectangle(canvas, (int(box.xmin), int(box.ymin)), (int(box.xmax), int(box.ymax)), (0, 255, 0), 2)
-                    cv.imwrite(os.path.join(draw_dir, base[:-4] + '_detected.jpg'), canvas)
+            for start in range(0, len(file_names), bs):
+                chunk = file_names[start:start + bs]
+                originals, images, geoms = [], [], []
+                for count1, file_name in enumerate(chunk, start + 1):
+                    if DEBUG:
+                        print(count1, '/', len(file_names), file_name)
+                    image_o = cv.imread(file_name, cv.IMREAD_COLOR)[:, :, ::-1]   # RGB like skimage.io.imread
+                    image, geom = self._letterbox(image_o / 255)
+                    originals.append(image_o); images.append(image[0]); geoms.append(geom)
+                all_boxes = self.detect_batch(np.stack(images)) if len(images) > 1 else [self.detect(images[0][np.newaxis])]
+                for file_name, image_o, geom, boxes in zip(chunk, originals, geoms, all_boxes):
+                    self._unletterbox(boxes, geom)
+                    base = file_name.split('\\')[-1] if platform.system() == 'Windows' else file_name.split('/')[-1]
+                    for count, box in enumerate(boxes, 1):
+                        if count > 60:                                                # :729, :870
+                            break
+                        f.write(base + ',' + str(box.xmin) + ',' + str(box.ymin) + ',')
+                        f.write(str(box.xmax - box.xmin) + ',' + str(box.ymax - box.ymin) + ',' + str(box.get_score()) + '\n')
+                    if draw_dir is not None and len(boxes) > 0:
+                        canvas = np.ascontiguousarray(image_o[:, :, ::-1])
+                        for box in boxes:
+                            cv.rectangle(canvas, (int(box.xmin), int(box.ymin)), (int(box.xmax), int(box.ymax)), (0, 255, 0), 2)
+                        cv.imwrite(os.path.join(draw_dir, base[:-4] + '_detected.jpg'), canvas)
 
     def evaluate(self):
         """Detect on every ``test_path/*.jpg``, write ``output_file_path`` CSV and ``results/*_detected.jpg``."""

@@ -316,3 +316,31 @@ def test_capacity_error():
     with pytest.raises(L.FvyError):
         eng.decode(outs, pp=post_params(0.5, 0.45), image_hw=np.array([[416, 416]], np.int32))
     eng.close()
+
+
+def test_facedetector_test_csv_batched_equals_per_image(tmp_path):
+    """FaceDetector.test() (reference :783-883): the batched file loop writes the same CSV as the reference's batch-1 loop."""
+    cv = pytest.importorskip("cv2")
+    from face_vijnana_yolov3_b200.space.face_detection import FaceDetector
+    import face_vijnana_yolov3_b200.space.face_detection as fdm
+    fdm.DEBUG = False
+    rng = np.random.default_rng(4)
+    img_dir = tmp_path / "imgs"
+    img_dir.mkdir()
+    for k, (w, h) in enumerate([(320, 240), (200, 300), (256, 256), (500, 120), (90, 400)]):
+        cv.imwrite(str(img_dir / f"f{k}.jpg"), rng.integers(0, 255, (h, w, 3), dtype=np.uint8))
+    stream = synth.darknet_stream(arch.fd6_table(), 3, synth.INIT_BN_EXERCISING)
+    outs = []
+    for bs in (1, 4):
+        conf = {"mode": "test", "raw_data_path": "", "test_path": str(img_dir), "output_file_path": str(tmp_path / f"out{bs}.csv"),
+                "multi_gpu": False, "num_gpus": 1, "yolov3_base_model_load": False,
+                "hps": {"face_conf_th": 0.2, "nms_iou_th": 0.5, "num_cands": 60}, "nn_arch": {"image_size": 416, "bb_info_c_size": 6},
+                "model_loading": False}
+        fd = FaceDetector(conf, max_batch=bs)
+        fd.set_weight_stream(stream)
+        fd.test()
+        outs.append(open(conf["output_file_path"]).read())
+        fd.engine.close()
+    assert outs[0] == outs[1] and outs[0].count("\n") > 0
+    first = outs[0].splitlines()[0].split(",")
+    assert len(first) == 6 and first[0].endswith(".jpg")

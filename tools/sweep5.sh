@@ -9,11 +9,11 @@ eng.load_weights(synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_D
 xd = torch.from_numpy(synth.images(40, 416, 416, 1)).cuda()
 for _ in range(10): eng.forward(xd, want_outputs=False)
 ts = []
-for _ in range(40):
+for _ in range(60):
     eng.forward(xd, want_outputs=False); ts.append(eng.last_timing()[0])
 print("forward ms median %.3f min %.3f" % (float(np.median(ts)), min(ts)))
 PY
-for rep in 1 2; do
-for cfg in "FVY_LIB_PATH=$PWD/face_vijnana_yolov3_b200/libfvy_old.so FVY_FLAGS=0" "FVY_LIB_PATH=$PWD/face_vijnana_yolov3_b200/libfvy_old.so FVY_FLAGS=1" "FVY_DYN=0 FVY_FLAGS=0" "FVY_DYN=0 FVY_FLAGS=1" "FVY_DYN=1 FVY_FLAGS=1" "FVY_DYN=1 FVY_FLAGS=1 FVY_DYN_MAX_TILES=4"; do
+for rep in 1 2 3; do
+for cfg in "FVY_LIB_PATH=$PWD/face_vijnana_yolov3_b200/libfvy_a.so" "FVY_X=1"; do
   echo "== $cfg" | sed "s#$PWD/face_vijnana_yolov3_b200/##"; env $cfg python /tmp/fwdt.py 2>&1 | tail -1
 done; done
