@@ -344,3 +344,83 @@ def test_facedetector_test_csv_batched_equals_per_image(tmp_path):
     assert outs[0] == outs[1] and outs[0].count("\n") > 0
     first = outs[0].splitlines()[0].split(",")
     assert len(first) == 6 and first[0].endswith(".jpg")
+
+
+def test_full_size_batch_invariance_and_tile_dependency_equivalence():
+    """BASELINE configs[1] size (batch 40 @416).  Size-independent properties of the conv stack: an image's head logits do not
+    depend on the batch it travels in (bit-exact: tiles change, a row's dot products do not), and the cross-layer tile
+    dependencies / CUDA graph (which only engage at this size) change nothing."""
+    import os
+    specs = arch.yolo3_table(1)
+    stream = synth.darknet_stream(specs, 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(40, 416, 416, 5)
+    eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
+    eng.load_weights(stream)
+    full = eng.forward(x)
+    again = eng.forward(x)                      # second call replays the captured graph
+    for a, b in zip(full, again):
+        assert np.array_equal(a, b)
+    eng.close()
+    old = {k: os.environ.get(k) for k in ("FVY_FLAGS", "FVY_GRAPH")}
+    try:
+        os.environ["FVY_FLAGS"] = "0"; os.environ["FVY_GRAPH"] = "0"
+        plain = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
+        plain.load_weights(stream)
+        ref = plain.forward(x)
+        plain.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for a, b in zip(full, ref):
+        assert np.array_equal(a, b)
+    one = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=1)
+    one.load_weights(stream)
+    for i in (0, 17, 39):
+        single = one.forward(x[i:i + 1])
+        for a, b in zip(full, single):
+            assert np.array_equal(a[i], b[0]), f"image {i} differs between batch 40 and batch 1"
+    one.close()
+
+
+def test_full_size_detect_matches_oracle_per_image():
+    """Batch 40 @416 through detect(): every image's kept boxes equal the C oracle run on that image's GPU logits."""
+    specs = arch.yolo3_table(1)
+    stream = synth.darknet_stream(specs, 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(40, 416, 416, 6)
+    eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
+    eng.load_weights(stream)
+    pp = post_params(0.5, 0.45)
+    hw = np.tile(np.array([[416, 416]], np.int32), (40, 1))
+    outs = eng.forward(x)
+    dets, counts = eng.detect(x, pp=pp, image_hw=hw)
+    for b in (0, 13, 39):
+        d = P.decode_image([o[b] for o in outs], obj_thresh=0.5)
+        ib = P.correct_yolo_boxes(d["box"], 416, 416, 416, 416)
+        cls = P.do_nms(ib, d["classes"], 0.45)
+        keep = np.nonzero(cls[:, 0] > 0)[0]
+        n = int(counts[b])
+        assert n == len(keep)
+        got = dets[b, :n]
+        assert np.array_equal(np.stack([got["xmin"], got["ymin"], got["xmax"], got["ymax"]], 1), ib[keep])
+        assert np.array_equal(got["score"], np.minimum(cls[keep, 0], 1.0).astype(np.float32))
+    eng.close()
+
+
+def test_608_batch_invariance():
+    """BASELINE configs[2] geometry (608x608, grids 19/38/76): an image's logits are the same in a batch of 16 and alone."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(16, 608, 608, 9)
+    eng = Engine(608, 608, head=L.HEAD_YOLO3, nb_class=1, max_batch=16)
+    eng.load_weights(stream)
+    full = eng.forward(x)
+    eng.close()
+    one = Engine(608, 608, head=L.HEAD_YOLO3, nb_class=1, max_batch=1)
+    one.load_weights(stream)
+    for i in (0, 15):
+        single = one.forward(x[i:i + 1])
+        for a, b in zip(full, single):
+            assert a.shape[1:] == b.shape[1:] and np.array_equal(a[i], b[0])
+    one.close()
