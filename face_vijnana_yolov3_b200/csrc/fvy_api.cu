@@ -524,7 +524,8 @@ static int build_plan(fvy_handle* h) {
         // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of the B tile): every 256-wide layer, and the
         // 128-wide 3x3 layers whose whole weight tile then fits in shared memory (conv_5/7/10)
         L.cta2 = !stem && L.BK == 64 && env_int("FVY_CTA2", 1) != 0 &&
-                 (L.BN == 256 || (L.BN == 128 && L.taps == 9 && (L.num_n_tiles == 1 ? env_int("FVY_CTA2_128", 1) != 0 : env_int("FVY_CTA2_128", 1) >= 2)));
+                 (L.BN == 256 || (L.BN == 128 && L.taps == 9 && (L.num_n_tiles == 1 ? env_int("FVY_CTA2_128", 1) != 0 : env_int("FVY_CTA2_128", 1) >= 2)) ||
+                  (L.BN == 128 && L.taps == 1 && L.num_n_tiles == 1 && env_int("FVY_CTA2_128_1X1", 0) != 0));
         // stride-1 3x3: the three column taps of a filter row read one A slab at row shifts 0, 1, 2
         const bool slab = L.taps == 9 && s.stride == 1 && env_int("FVY_SLAB", 1) != 0;
         const int srows = L.BK == 64 ? slab_rows<64>() : slab_rows<32>();

@@ -1,5 +1,5 @@
 #!/bin/bash
-# two-ring operand pipeline: parity of every layer + per-layer times
+# Layer-by-layer parity of the conv stack + isolated per-layer times (run under gpurun): gpurun_out/ring1.log
 timeout 900 python tools/gpu_check.py --skip-post --tile-n 256 > gpurun_out/ring1.log 2>&1
 echo "rc=$?"
 grep -c "BAD" gpurun_out/ring1.log
