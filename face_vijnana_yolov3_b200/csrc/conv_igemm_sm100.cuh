@@ -577,7 +577,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int num_tiles = (CTA2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;   // CTA2: tiles of 256 rows
     const int split_from = CTA2 ? min(p.split_from, num_tiles) : num_tiles;
     const int num_items = num_tiles + (num_tiles - split_from);                                // tail tiles count twice (two halves)
-    const int row_groups = p.num_taps / p.gt;
 
     if (p.m_total < 0) return;    // profiling aid (FVY_NOWORK=2): cost of the bare launch
     if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 16] = globaltimer_ns();

@@ -401,8 +401,11 @@ static int query_occ_t(size_t smem, int* occ) {
     auto kern = conv_igemm_kernel<BN, BK, CTA2>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (CTA2) { *occ = 1; return FVY_OK; }
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem));
+    if constexpr (CTA2) {
+        *occ = 1;       // a cluster of two: one CTA per SM by construction
+    } else {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem));
+    }
     return FVY_OK;
 }
 

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
     extern __shared__ unsigned long long removed[];    // [words]
     __shared__ unsigned long long diag[2][64];
     __shared__ unsigned alive32[2][2];
-    __shared__ unsigned long long keep_w, flagged_w;
+    __shared__ unsigned long long flagged_w;
     const int img = blockIdx.x;
     const int n = min(a.counts[img], a.seg_stride);
     if (n <= 0) return;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
             }
             if (lane == 0) {
                 const unsigned long long keep = alive & ~cr;
-                removed[blk] = cr; keep_w = keep; flagged_w = keep & rf[blk];
+                removed[blk] = cr; flagged_w = keep & rf[blk];
             }
         }
         __syncthreads();
