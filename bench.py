@@ -222,7 +222,7 @@ def main():
     flops_step = 2.0 * eng.macs_per_image() * B                      # algorithmic, un-padded
     peaks = _peaks()
     achieved = flops_step / (fwd_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": f"conv_igemm_kernel ({n_conv - 1} launches/step) + stem_conv_kernel (1 launch)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": f"conv_igemm_kernel ({n_conv - 1} launches/step) + stem_rows_kernel (1 launch)", "achieved": achieved,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "frac_of_burst_peak": achieved / peaks["tf_burst"], "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_step": flops_step, "avg_launch_ms": fwd_ms / (n_conv + 1), "forward_ms": fwd_ms,

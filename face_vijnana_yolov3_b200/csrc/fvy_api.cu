@@ -243,6 +243,147 @@ __global__ void __launch_bounds__(256, STEM_MIN_BLOCKS) stem_conv_kernel(const T
     }
 }
 
+// Second form of the fused stem (default): the image rows a strip of outputs needs are staged ONCE in shared memory as bf16
+// (rolling window of three rows: every input element is read from HBM once, coalesced, and converted once instead of nine
+// times), and the MMA fragments are gathered from there with aligned 32-bit loads.  The K order is chosen for that: filter
+// row r occupies k = 10 r .. 10 r + 9 (nine contiguous window elements (dx, c) of the NHWC row + one zero slot), so every
+// fragment register (k, k+1) is two adjacent bf16 of a staged row; a second copy of each row shifted by one element makes
+// the pair 4-byte aligned for odd pixels as well.  Image borders are zeros in the staged rows: no edge tests in the loop.
+constexpr int kStemThreads = 416;      // 13 warps: 26 (416 px) / 38 (608 px) 16-pixel tiles per image row
+template <typename T>
+__global__ void __launch_bounds__(kStemThreads, 2)
+stem_rows_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, const __nv_bfloat16* __restrict__ wgt /*[32][32], k = 10 r + j*/,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*4-phase*/, int rows_per_block, int rowlen) {
+    extern __shared__ __align__(16) uint16_t srows[];        // [8 slots][2 copies][rowlen]
+    __shared__ __align__(16) uint32_t stile[kStemThreads / 32][16][20];
+    const int lane = threadIdx.x & 31, quad = lane & 3, grp = lane >> 2, wib = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const long long total_rows = (long long)batch * H;
+    const long long row0 = (long long)blockIdx.x * rows_per_block;
+    const long long row1 = min(total_rows, row0 + rows_per_block);
+    if (row0 >= row1) return;
+    uint32_t bfrag[4][2][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(wgt + (j * 8 + grp) * 32 + t * 16 + quad * 2);
+            bfrag[j][t][0] = __ldg(wr);
+            bfrag[j][t][1] = __ldg(wr + 4);
+        }
+    float bia[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bia[j][0] = __ldg(bias + j * 8 + quad * 2); bia[j][1] = __ldg(bias + j * 8 + quad * 2 + 1); }
+    // this lane's four (k, k+1) pairs of a pixel: k = ks*16 + half*8 + quad*2 -> filter row r = k / 10, window element j = k % 10
+    int pr[4], pj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (i >> 1) * 16 + (i & 1) * 8 + quad * 2;
+        pr[i] = k < 30 ? k / 10 : 0;             // k = 30, 31: zero weights, any valid address
+        pj[i] = k < 30 ? k % 10 : 0;
+    }
+    const int par = grp & 1;                     // parity of this lane's pixels (w0 and rr*8 are even): which copy gives aligned pairs
+    const int pw = (W >> 1) + 2;
+    const long long plane = (long long)((H >> 1) + 2) * pw;
+    const int tiles_per_row = W >> 4;
+    const int n_elems = (W + 2) * 3 + 2;
+    auto load_row = [&](int slot, long long n, int hh) {
+        uint16_t* E = srows + (size_t)(slot * 2) * rowlen;
+        uint16_t* O = E + rowlen;
+        const bool in = hh >= 0 && hh < H;
+        const T* src = img + ((n * H + (in ? hh : 0)) * W) * 3;
+        for (int e = threadIdx.x; e < n_elems; e += blockDim.x) {
+            float v = 0.f;
+            if (in && e >= 3 && e < (W + 1) * 3) v = (float)__ldg(src + (e - 3));
+            const uint16_t b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            E[e] = b;
+            if (e >= 1) O[e - 1] = b;
+        }
+    };
+    // Two output rows per block-wide barrier; software pipeline: the loads of the next two input rows are in flight while the
+    // current two output rows are computed, and are converted and stored (ring of 8 row slots) after them.
+    constexpr int kFetch = 5;                    // ceil(((608 + 2) * 3 + 2) / 416)
+    float pf[2][kFetch];
+    auto fetch_row = [&](int which, long long n, int hh) {
+        const bool in = hh >= 0 && hh < H;
+        const T* src = img + ((n * H + (in ? hh : 0)) * W) * 3;
+#pragma unroll
+        for (int k = 0; k < kFetch; ++k) {
+            const int e = threadIdx.x + k * kStemThreads;
+            pf[which][k] = (in && e >= 3 && e < (W + 1) * 3) ? (float)__ldg(src + (e - 3)) : 0.f;
+        }
+    };
+    auto store_row = [&](int which, int slot) {
+        uint16_t* E = srows + (size_t)(slot * 2) * rowlen;
+        uint16_t* O = E + rowlen;
+#pragma unroll
+        for (int k = 0; k < kFetch; ++k) {
+            const int e = threadIdx.x + k * kStemThreads;
+            if (e < n_elems) {
+                const uint16_t b = __bfloat16_as_ushort(__float2bfloat16_rn(pf[which][k]));
+                E[e] = b;
+                if (e >= 1) O[e - 1] = b;
+            }
+        }
+    };
+    long long prev_n = -1; int prev_h = -3;
+    for (long long row = row0; row < row1; row += 2) {        // row ranges start on even rows and H is even: (h, h+1) share an image
+        const long long n = row / H;
+        const int h = (int)(row - n * H);
+        if (!(n == prev_n && h == prev_h + 2)) {
+            __syncthreads();                     // a new window: nobody may still be reading the slots
+            for (int d = -1; d <= 2; ++d) load_row((h + d) & 7, n, h + d);
+            __syncthreads();
+        }
+        prev_n = n; prev_h = h;
+        fetch_row(0, n, h + 3);
+        fetch_row(1, n, h + 4);
+        for (int item = wib; item < 2 * tiles_per_row; item += nwarps) {
+            const int second = item >= tiles_per_row ? 1 : 0;
+            const int hh = h + second;
+            const int w0 = (item - second * tiles_per_row) << 4;
+            uint32_t afrag[2][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint16_t* rp = srows + (size_t)((((hh - 1 + pr[i]) & 7) * 2 + par)) * rowlen + pj[i] - par;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                    afrag[i >> 1][(i & 1) * 2 + rr] = *reinterpret_cast<const uint32_t*>(rp + (w0 + grp + rr * 8) * 3);
+            }
+            float acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[j][0] = acc[j][2] = bia[j][0];
+                acc[j][1] = acc[j][3] = bia[j][1];
+                mma_m16n8k16_bf16(acc[j], afrag[0], bfrag[j][0][0], bfrag[j][0][1]);
+                mma_m16n8k16_bf16(acc[j], afrag[1], bfrag[j][1][0], bfrag[j][1][1]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    float a = acc[j][rr * 2 + 0], b = acc[j][rr * 2 + 1];
+                    a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
+                    stile[wib][grp + rr * 8][j * 4 + quad] = *reinterpret_cast<uint32_t*>(&pk);
+                }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint4 o = *reinterpret_cast<const uint4*>(&stile[wib][grp + rr * 8][quad * 4]);
+                const int wpix = w0 + grp + rr * 8;
+                const int hp = hh + 1, wp = wpix + 1;
+                const long long orow = ((long long)((((hp & 1) << 1) | (wp & 1))) * nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
+                *reinterpret_cast<uint4*>(out + orow * 32 + quad * 8) = o;
+            }
+        }
+        store_row(0, (h + 3) & 7);               // slots of rows h-5, h-4: last read two iterations ago
+        store_row(1, (h + 4) & 7);
+        __syncthreads();
+    }
+}
+
 // Debug / parity aid: stored activation -> dense NHWC fp32.
 __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float* __restrict__ dst) {
     const long long total = (long long)batch * H * W * C;
@@ -309,6 +450,8 @@ struct fvy_handle {
     bool weights_loaded = false;
     bool use_pdl = true;
     bool fused_stem = true;              // conv_0 straight from the image (stem_conv_kernel) instead of im2col + GEMM
+    int stem_mode = 2;                   // 2: stem_rows_kernel (staged rows), 1: stem_conv_kernel (register gather)
+    __nv_bfloat16* d_stem_w2 = nullptr;  // conv_0 weights in stem_rows_kernel's K order
     const void* cur_img = nullptr; int cur_dtype = FVY_F32;   // device image of the current forward (layer 0 re-runs)
     long long launches = 0;
     long long weight_count = 0;
@@ -467,6 +610,18 @@ static int build_plan(fvy_handle* h) {
     {
         const char* v = getenv("FVY_FUSED_STEM");
         h->fused_stem = !(v && *v && atoi(v) == 0);
+        const char* m = getenv("FVY_STEM");
+        h->stem_mode = (m && *m) ? atoi(m) : 2;
+        if (c.net_w % 16) h->stem_mode = 1;
+    }
+    if (int e = dev_alloc(h, (void**)&h->d_stem_w2, 32 * 32 * 2, true)) return e;
+    {   // staged rows of stem_rows_kernel: 8 slots x 2 copies x (3 (W + 2) + 2) bf16 - beyond the 48 KB default for wide images
+        const size_t need = (size_t)8 * 2 * ((((c.net_w + 2) * 3 + 2) + 7) & ~7) * 2;
+        if (need > 100 * 1024) h->stem_mode = 1;
+        else {                                   // static (transpose tiles) + dynamic exceed the 48 KB default
+            CUDA_TRY(cudaFuncSetAttribute(stem_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CUDA_TRY(cudaFuncSetAttribute(stem_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        }
     }
     if (!h->fused_stem)
         if (int e = dev_alloc(h, (void**)&h->d_stem, (size_t)nmax * c.net_h * c.net_w * 32 * 2, false)) return e;
@@ -799,6 +954,19 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
         Layer& L = h->layers[i];
         if (L.s.src == -1 && h->fused_stem) {
             if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
+            if (h->stem_mode == 2) {
+                const long long total_rows = (long long)batch * h->cfg.net_h;
+                const int blocks = (int)std::min<long long>(total_rows, (long long)h->num_sms * 2);
+                const int rows_per_block = (int)(((total_rows + blocks - 1) / blocks + 1) & ~1LL);     // even: two rows per iteration
+                const int rowlen = (((h->cfg.net_w + 2) * 3 + 2) + 7) & ~7;
+                const size_t smem = (size_t)8 * 2 * rowlen * 2;
+                if (h->cur_dtype == FVY_F32)
+                    stem_rows_kernel<float><<<blocks, kStemThreads, smem, h->stream>>>((const float*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
+                                                                                      h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr, rows_per_block, rowlen);
+                else
+                    stem_rows_kernel<double><<<blocks, kStemThreads, smem, h->stream>>>((const double*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
+                                                                                       h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr, rows_per_block, rowlen);
+            } else {
             const int blocks = h->num_sms * 8;   // persistent warps, 2 waves of 4 resident blocks per SM
             if (h->cur_dtype == FVY_F32)
                 stem_conv_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
@@ -806,6 +974,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             else
                 stem_conv_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
                                                                         L.w, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
+            }
             CUDA_TRY(cudaGetLastError());
             ++h->launches;
             if (h->last_slot >= 0 && !h->capturing) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
@@ -1188,6 +1357,14 @@ int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats) {
                         const size_t kk = stem ? (size_t)(r * 3 + q) * 3 + ci : (size_t)(r * s.k + q) * L.cin_pad + ci;
                         wbuf[(size_t)o * kdim + kk] = f32_to_bf16_rn(v);
                     }
+        }
+        if (stem) {      // the same folded weights in stem_rows_kernel's K order: k = 10 r + (3 q + ci)
+            std::vector<uint16_t> w2((size_t)32 * 32, 0);
+            for (int o = 0; o < s.cout && o < 32; ++o)
+                for (int r = 0; r < 3; ++r)
+                    for (int j = 0; j < 9; ++j) w2[(size_t)o * 32 + r * 10 + j] = wbuf[(size_t)o * kdim + r * 9 + j];
+            CUDA_TRY(cudaMemcpyAsync(h->d_stem_w2, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
         }
         CUDA_TRY(cudaMemcpyAsync(L.w, wbuf.data(), wbuf.size() * 2, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaMemcpyAsync(L.bias, bbuf.data(), bbuf.size() * 4, cudaMemcpyHostToDevice, h->stream));

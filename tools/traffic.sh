@@ -15,5 +15,5 @@ for _ in range(2):
 PY
 FVY_GRAPH=0 python /tmp/fwd2.py || exit 1
 FVY_GRAPH=0 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k regex:"conv_igemm|stem_conv" -s 75 -c 75 --csv --log-file gpurun_out/traffic.csv python /tmp/fwd2.py > gpurun_out/traffic_ncu.log 2>&1
+    -k regex:"conv_igemm|stem_" -s 75 -c 75 --csv --log-file gpurun_out/traffic.csv python /tmp/fwd2.py > gpurun_out/traffic_ncu.log 2>&1
 tail -3 gpurun_out/traffic.csv
