@@ -87,6 +87,8 @@ struct ConvParams {
     // an A slot serves a_cover consecutive taps, a B slot b_cover.
     int gt;              // taps per filter row: 3 (3x3) or 1 (1x1, stem)
     int a_slab;          // 1: an A slot is ONE box of slab_rows rows; tap t reads it at a row shift of t (stride-1 3x3 convs)
+                         // 2: TWO such boxes (stride-2 3x3 convs, taps ordered s = 0, 2, 1): taps 0 and 1 read the first at row
+                         //    shifts 0 and 1 (same input phase), tap 2 reads the second (the other column phase)
     int a_cover;         // taps served by one A slot (slab: gt; separate tiles: 1 or gt)
     int a_stages;
     int b_cover;         // taps per B slot (1 or gt)
@@ -456,7 +458,8 @@ __device__ __forceinline__ int half_chunk_col(int c, int half) {
 struct MmaCtx {
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *tmem_full, *tmem_empty;
     uint64_t desc_hi;
-    uint32_t a_ring16, b_ring16, a_slot16, b_slot16, a_tap16, b_tap16;   // shared-memory addresses / strides in 16-byte units
+    uint32_t a_ring16, b_ring16, a_slot16, b_slot16, b_tap16;   // shared-memory addresses / strides in 16-byte units
+    uint32_t a_off16[3];                                        // offset of tap t inside its A slot
     uint32_t tmem_base;
     int a_stages, b_stages, units, first, step, num_tiles, split_from;
     bool bres, bo;
@@ -501,7 +504,7 @@ __device__ __forceinline__ void mma_issue(const MmaCtx& c) {
                 }
                 if (c.dbg) { dbg_full += clock64() - c0; if (first && u == 0 && t == 0) c.dbg[19] = globaltimer_ns(); }
                 tc_fence_after();
-                const uint64_t da = da0 + (uint32_t)(t % ACOV) * c.a_tap16, db = db0 + (uint32_t)(t % BCOV) * c.b_tap16;
+                const uint64_t da = da0 + c.a_off16[t % ACOV], db = db0 + (uint32_t)(t % BCOV) * c.b_tap16;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
@@ -567,7 +570,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(free_all + 2 * kMaxRing);
     float* sbias = reinterpret_cast<float*>(smem + kSmemBias);
     uint8_t* ring_all = smem + kSmemRing;
-    const int a_slot_bytes = p.a_slab ? kSlabBytes : p.a_cover * kABytes;
+    const int a_slot_bytes = p.a_slab ? p.a_slab * kSlabBytes : p.a_cover * kABytes;
     const int b_slot_bytes = p.b_cover * kBBytes;
     uint8_t* a_ring = ring_all + p.epi_groups * p.nb * kChunkBytes;
     uint8_t* b_ring = a_ring + p.a_stages * a_slot_bytes;
@@ -632,7 +635,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const bool bo = p.epi_groups == 2;
             const uint32_t tx = (CTA2 ? 2u : 1u) * (uint32_t)a_slot_bytes;   // CTA2: the leader's arrival expects the bytes of BOTH CTAs
             const bool arrives = !CTA2 || cta_rank == 0;
-            const int a_loads = p.a_slab ? 1 : p.a_cover;
+            const int a_loads = p.a_slab ? p.a_slab : p.a_cover;
+            const int a_load_bytes = p.a_slab ? kSlabBytes : kABytes;     // smem distance between the boxes of one slot
+            const int a_load_tap = p.a_slab == 2 ? 2 : 1;                 // tap index distance between them
             int dep_ready = -1;
             long long dbg_wait = 0;
             for (int item = cta_first; item < num_items; item += cta_step) {
@@ -651,8 +656,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             uint8_t* sa = a_ring + as_ * a_slot_bytes;
                             if (arrives) mbar_expect_tx(&a_full[as_], tx);
                             for (int j = 0; j < a_loads; ++j) {
-                                if constexpr (CTA2) tma_load_2d_pair(sa + j * kABytes, &tmap_a, &a_full[as_], p.a_choff + kc * BK, m0 + p.tap_off[tap0 + t + j]);
-                                else tma_load_2d(sa + j * kABytes, &tmap_a, &a_full[as_], p.a_choff + kc * BK, m0 + p.tap_off[tap0 + t + j]);
+                                if constexpr (CTA2) tma_load_2d_pair(sa + j * a_load_bytes, &tmap_a, &a_full[as_], p.a_choff + kc * BK, m0 + p.tap_off[tap0 + t + j * a_load_tap]);
+                                else tma_load_2d(sa + j * a_load_bytes, &tmap_a, &a_full[as_], p.a_choff + kc * BK, m0 + p.tap_off[tap0 + t + j * a_load_tap]);
                             }
                             if (++as_ == p.a_stages) { as_ = 0; aph ^= 1; }
                         }
@@ -705,7 +710,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             c.a_ring16 = (smem_u32(a_ring) & 0x3FFFF) >> 4; c.b_ring16 = (smem_u32(b_ring) & 0x3FFFF) >> 4;
             c.a_slot16 = (uint32_t)a_slot_bytes >> 4; c.b_slot16 = (uint32_t)b_slot_bytes >> 4;
             // slab: tap t is the slab read from t rows further (address-based swizzle, see slab_rows)
-            c.a_tap16 = (uint32_t)(p.a_slab ? kRowBytes : kABytes) >> 4; c.b_tap16 = (uint32_t)kBBytes >> 4;
+            if (p.a_slab == 2) { c.a_off16[0] = 0; c.a_off16[1] = (uint32_t)kRowBytes >> 4; c.a_off16[2] = (uint32_t)kSlabBytes >> 4; }
+            else for (int t = 0; t < 3; ++t) c.a_off16[t] = (uint32_t)t * ((uint32_t)(p.a_slab ? kRowBytes : kABytes) >> 4);
+            c.b_tap16 = (uint32_t)kBBytes >> 4;
             c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.bres = bres; c.bo = p.epi_groups == 2;
             c.tmem_base = tmem_base; c.units = taps_per_tile / p.gt;
             c.first = cta_first; c.step = cta_step; c.num_tiles = num_items; c.split_from = split_from; c.dbg = p.dbg ? p.dbg + blockIdx.x * 32 : nullptr;

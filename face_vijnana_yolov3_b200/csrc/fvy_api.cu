@@ -417,6 +417,7 @@ struct Layer {
     int BN, BK, stages, b_stages = 0, b_resident = 0, num_n_tiles, cout_pad, cin_pad, taps, occ;
     bool deep_k = false;
     int head_slot = -1;           // index of the logit tensor a head layer writes
+    bool tap_perm = false;        // column taps stored in the order s = 0, 2, 1 (stride-2 slab pairs)
     // cross-layer tile dependencies (see ConvParams::sig_flags)
     bool signals = false;         // every stored form leaves by TMA and a consumer waits on the counters
     int wait_on = -1;             // index (in h->layers) of the producer whose counters gate this layer's tiles, or -1
@@ -685,11 +686,16 @@ static int build_plan(fvy_handle* h) {
                  (L.BN == 256 || (L.BN == 128 && L.taps == 9 && (L.num_n_tiles == 1 ? env_int("FVY_CTA2_128", 1) != 0 : env_int("FVY_CTA2_128", 1) >= 2)) ||
                   (L.BN == 128 && L.taps == 1 && L.num_n_tiles == 1 && env_int("FVY_CTA2_128_1X1", 0) != 0));
         // stride-1 3x3: the three column taps of a filter row read one A slab at row shifts 0, 1, 2
-        const bool slab = L.taps == 9 && s.stride == 1 && env_int("FVY_SLAB", 1) != 0;
+        const bool slab1 = L.taps == 9 && s.stride == 1 && env_int("FVY_SLAB", 1) != 0;
+        // stride-2 3x3: column taps 0 and 2 of a filter row are the same input phase one row apart -> one slab for both,
+        // a second box for tap 1 (taps are stored in the order s = 0, 2, 1 for these layers)
+        const bool slab2 = !stem && L.taps == 9 && s.stride == 2 && env_int("FVY_SLAB2", 1) != 0;
+        L.tap_perm = slab2;
+        const bool slab = slab1 || slab2;
         const int srows = L.BK == 64 ? slab_rows<64>() : slab_rows<32>();
         const size_t a_tile = (size_t)kBlockM * L.BK * 2, b_tile = (size_t)(L.cta2 ? L.BN / 2 : L.BN) * L.BK * 2;
         const int a_cover = slab ? gt : (L.BK == 32 ? gt : 1);
-        const size_t a_slot = slab ? (size_t)srows * L.BK * 2 : a_cover * a_tile;
+        const size_t a_slot = slab ? (size_t)(slab2 ? 2 : 1) * srows * L.BK * 2 : a_cover * a_tile;
         int b_cover = (gt == 3 && a_cover == gt && gt * b_tile <= (size_t)env_int("FVY_B3_MAX", 24576)) ? gt : 1;   // a filter row of B tiles per slot (one 3-D TMA box)
         // Layers with a short K loop are epilogue-bound: two epilogue groups alternate tiles.  Deep-K layers keep one
         // group so that the shared memory goes to the operand pipeline instead of a second staging ring.
@@ -747,7 +753,7 @@ static int build_plan(fvy_handle* h) {
         p.bias = L.bias;
         p.num_n_tiles = L.num_n_tiles;
         p.nb = nb; p.lead = lead; p.epi_groups = groups;
-        p.gt = gt; p.a_slab = slab ? 1 : 0; p.a_cover = a_cover; p.a_stages = a_stages;
+        p.gt = gt; p.a_slab = slab2 ? 2 : (slab1 ? 1 : 0); p.a_cover = a_cover; p.a_stages = a_stages;
         p.b_cover = b_cover; p.b_stages = b_stages; p.b_resident = b_res;
         const void* a_base = nullptr;
         uint64_t a_rows = 0, a_pitch = 0;
@@ -766,7 +772,8 @@ static int build_plan(fvy_handle* h) {
             p.dom_plane = (int)plane; p.dom_w = Wo + 2; p.dom_off = 1;
             for (int r = 0; r < 3; ++r)
                 for (int q = 0; q < 3; ++q)
-                    p.tap_off[r * 3 + q] = (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + ((r >> 1) - 1) * (Wo + 2) + ((q >> 1) - 1));
+                    p.tap_off[r * 3 + (L.tap_perm ? (q == 0 ? 0 : (q == 2 ? 1 : 2)) : q)] =
+                        (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + ((r >> 1) - 1) * (Wo + 2) + ((q >> 1) - 1));
         } else {
             const int H = L.Hin, W = L.Win;
             if (s.src == -2) { a_base = catA; a_pitch = 768; }
@@ -1354,7 +1361,8 @@ int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats) {
                 for (int r = 0; r < s.k; ++r)
                     for (int q = 0; q < s.k; ++q) {
                         const float v = kern[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q] * scale;
-                        const size_t kk = stem ? (size_t)(r * 3 + q) * 3 + ci : (size_t)(r * s.k + q) * L.cin_pad + ci;
+                        const int qp = L.tap_perm ? (q == 0 ? 0 : (q == 2 ? 1 : 2)) : q;      // stored position of column tap q
+                        const size_t kk = stem ? (size_t)(r * 3 + q) * 3 + ci : (size_t)(r * s.k + qp) * L.cin_pad + ci;
                         wbuf[(size_t)o * kdim + kk] = f32_to_bf16_rn(v);
                     }
         }
