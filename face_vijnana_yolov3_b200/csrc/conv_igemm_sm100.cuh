@@ -18,23 +18,28 @@
 // up-sampled into a channel slice of a concat buffer (:282-283, :298-299), or dense fp32 head
 // logits (:278, :294, :308).
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..5 = epilogue group 0, warps 6..9 = epilogue group 1
-// (TMEM lane quarter = warp_idx & 3).  With two groups, consecutive tiles of a CTA alternate between
-// them (layers with a short K loop are epilogue-bound); accumulators are 2 (BN >= 128) or 4 (BN <= 64)
-// TMEM stages deep.  Persistent: grid = min(#tiles, #SMs); tiles are strided by gridDim.x.
+// Warp roles (416 threads): warp 0 = A producer, warp 10 = B producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane each), warps 2..5 / 6..9 = epilogue groups 0 / 1 (TMEM lane quarter = warp_idx & 3), warps 11 / 12 = the store warps
+// of the groups (every TMA store and residual prefetch).  Accumulators are 2 (BN >= 128) or 4 (BN <= 64) TMEM stages deep.
+// Persistent: grid = min(#tiles, #SMs); tiles are strided by gridDim.x.  CTA2 = true: two CTAs of a cluster share one
+// 256-row tile (cta_group::2), each staging its own 128 rows of A and half of the B tile.
 //
-// Epilogue data path: the accumulator is drained in chunks of 32 channels.  Each chunk is staged in a
-// ring of 8 KB shared-memory buffers laid out exactly as TMA's 64-byte swizzle expects, so that
-//   * the residual chunk arrives by TMA (prefetched `lead` chunks ahead) into the buffer the output
-//     chunk will be written to (in place: each thread reads and rewrites its own 64-byte row),
-//   * stride-1 layers store the chunk with one TMA store per output (rows of the compute domain ARE
-//     rows of the padded output; halo rows are stored as zeros which keeps the padding invariant),
-//   * the other output forms (4-phase, stride-2 remap, 2x up-sample) are written from the staged chunk
-//     with 4 threads per 64-byte row (8 rows per warp instruction instead of 32 scattered 16-byte pieces).
-// Kernels are chained with programmatic dependent launch: the prologue (barrier init, TMEM alloc,
-// tensor-map prefetch) overlaps the previous layer's tail; griddepcontrol.wait precedes the first
-// dependent global access.
+// Operand pipeline: two independent rings.  The K loop runs over (filter row, K chunk, column tap).  The three column taps
+// of a filter row read ONE A slab (the activation rows are pixels in row-major padded order, so a column shift is a row
+// shift of 1, and tcgen05 shared-memory descriptors swizzle by ADDRESS: any start row inside a TMA-written slab is legal).
+// B slots hold one tap or one filter row (a 3-D TMA box), or - resident weights - the whole [BN, K] tile for the CTA's life.
+//
+// Epilogue data path: the accumulator is drained in chunks of 32 channels.  Each chunk is staged in a ring of 8 KB
+// shared-memory buffers laid out exactly as TMA's 64-byte swizzle expects, so that
+//   * the residual chunk arrives by TMA (prefetched by the store warp) into the buffer the output chunk will be written to
+//     (in place: each thread reads and rewrites its own 64-byte row),
+//   * layers whose compute-domain rows ARE rows of the padded output (every layer but the stem) store the chunk with one
+//     TMA store per output (halo rows are stored as zeros, which keeps the padding invariant),
+//   * the other output forms (4-phase, 2x up-sample) are written from the staged chunk with 4 threads per 64-byte row.
+// Two groups either split every tile by columns (short drain) or alternate tiles (per-tile set-up amortised).
+//
+// Layers are chained with programmatic dependent launch; where producer and consumer share a geometry the kernel boundary
+// is replaced by per-128-row-block completion counters (ConvParams::sig_flags / wait_flags).
 #pragma once
 
 #include <cuda.h>
