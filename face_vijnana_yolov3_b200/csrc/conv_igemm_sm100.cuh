@@ -424,13 +424,35 @@ __device__ __forceinline__ void wait_blocks_ready(const int* flags, int expected
         for (uint32_t spin = 0; ld_acquire_gpu(flags + b) < expected; ++spin) {
             __nanosleep(spin < 16 ? 40 : 200);
             if (spin > (1u << 22)) {
-                printf("fvy: tile dependency wait timed out (block %d, counter %d of %d)\n", blockIdx.x, b, expected);
+                printf("fvy: tile dependency wait timed out (block %d thread %d, counter %d = %d of %d, range %d..%d)\n", blockIdx.x, threadIdx.x, b,
+                       ld_acquire_gpu(flags + b), expected, lo, hi);
                 __trap();
             }
         }
     }
     ready = hi;
     fence_proxy_async_all();
+}
+// Non-blocking form: true once blocks [lo, hi] are complete (one acquire load per block not yet known complete).
+__device__ __forceinline__ bool blocks_ready_now(const int* flags, int expected, int lo, int hi, int& ready) {
+    for (int b = max(lo, ready + 1); b <= hi; ++b) {
+        if (ld_acquire_gpu(flags + b) < expected) return false;
+        ready = b;
+    }
+    fence_proxy_async_all();
+    return true;
+}
+// Non-blocking mbarrier phase test.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void bulk_wait_complete(int n) {   // at most n of this thread's bulk groups still pending (writes performed)
     switch (n) {

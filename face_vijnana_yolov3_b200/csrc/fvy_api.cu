@@ -17,6 +17,7 @@
 
 #include "../../include/fvy.h"
 #include "conv_igemm_sm100.cuh"
+#include "conv_chain_sm100.cuh"
 #include "fvy_plan.h"
 #include "postproc_kernels.cuh"
 
@@ -418,6 +419,7 @@ struct Layer {
     bool deep_k = false;
     int head_slot = -1;           // index of the logit tensor a head layer writes
     bool tap_perm = false;        // column taps stored in the order s = 0, 2, 1 (stride-2 slab pairs)
+    int chain = -1, chain_pos = 0;   // index into fvy_handle::chains and position inside it (conv_chain_kernel), or -1
     // cross-layer tile dependencies (see ConvParams::sig_flags)
     bool signals = false;         // every stored form leaves by TMA and a consumer waits on the counters
     int wait_on = -1;             // index (in h->layers) of the producer whose counters gate this layer's tiles, or -1
@@ -479,6 +481,9 @@ struct fvy_handle {
     };
     std::map<GraphKey, cudaGraphExec_t> graphs;
     bool use_graph = true, capturing = false;
+    struct Chain { int first = 0, count = 0; ChainLayer* dev = nullptr; std::vector<ChainLayer> host; };
+    std::vector<Chain> chains; bool use_chain = true; int chain_batch = -1;
+    int chain_nb = 3, chain_a = 4, chain_b = 6; size_t chain_smem = 0;
     int* d_flags = nullptr; size_t flags_bytes = 0; bool use_flags = true, flags_live = false;
     int gh[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, head_c = 0;
     // post
@@ -862,6 +867,104 @@ static int build_plan(fvy_handle* h) {
                 if (L.signals) { L.flags = h->d_flags + off; off += (size_t)L.flag_blocks; }
         }
     }
+    // ---- chains: runs of consecutive layers of the 256-wide CTA-pair instance, each reading its predecessor's TMA-stored
+    // output, go out as ONE persistent launch (conv_chain_kernel)
+    {
+        h->use_chain = h->use_flags && env_int("FVY_CHAIN", 1) != 0;
+        auto eligible = [&](const Layer& L) {
+            if (!L.cta2 || L.BN != 256 || L.BK != 64 || L.s.stride != 1 || L.s.src < 0 || !L.s.bn) return false;
+            if (L.p.b_resident || L.p.b_cover != 1) return false;
+            if (L.taps == 9 ? L.p.a_slab != 1 : (L.taps != 1 || L.p.a_slab != 0 || L.p.a_cover != 1)) return false;
+            for (int o = 0; o < 2; ++o)
+                if (L.p.out[o].kind != OUT_NONE && !(L.p.out[o].kind == OUT_PADDED && L.p.out[o].tma)) return false;
+            return L.p.out[0].kind == OUT_PADDED;
+        };
+        const int n = (int)h->layers.size();
+        for (int i = 0; i < n && h->use_chain;) {
+            if (!eligible(h->layers[i])) { ++i; continue; }
+            int j = i + 1;
+            const int max_len = env_int("FVY_CHAIN_MAXLEN", 64);
+            while (j < n && j - i < max_len && eligible(h->layers[j]) && h->layers[j].wait_on == j - 1 && h->layers[j - 1].signals) ++j;
+            if (j - i >= 2) {
+                fvy_handle::Chain ch;
+                ch.first = i; ch.count = j - i;
+                ch.host.resize(ch.count);
+                if (int e = dev_alloc(h, (void**)&ch.dev, sizeof(ChainLayer) * ch.count, true)) return e;
+                for (int k = i; k < j; ++k) { h->layers[k].chain = (int)h->chains.size(); h->layers[k].chain_pos = k - i; }
+                h->chains.push_back(std::move(ch));
+            }
+            i = j;
+        }
+        if (!h->chains.empty()) {
+            // one shared-memory carve-up for every layer of a chain: slab-sized A slots, per-tap B slots, nb staging buffers per group
+            h->chain_nb = env_int("FVY_CHAIN_NB", 3); h->chain_a = env_int("FVY_CHAIN_A", 4); h->chain_b = env_int("FVY_CHAIN_B", 6);
+            h->chain_smem = 1024 + kSmemRing + (size_t)2 * h->chain_nb * kChunkBytes + (size_t)h->chain_a * slab_rows<64>() * 64 * 2 +
+                            (size_t)h->chain_b * 128 * 64 * 2;
+            if (h->chain_smem > 232448) return fail(FVY_E_INVALID, "chain shared-memory plan %zu exceeds 227 KB", h->chain_smem);
+            CUDA_TRY(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            CUDA_TRY(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+    }
+    return FVY_OK;
+}
+
+// Per-call chain descriptors (batch-dependent fields), uploaded in stream order before the forward that uses them.
+static int prepare_chains(fvy_handle* h, int batch) {
+    if (h->chains.empty() || h->chain_batch == batch) return FVY_OK;
+    const int pairs = (h->num_sms & ~1) / 2;
+    for (fvy_handle::Chain& ch : h->chains) {
+        for (int k = 0; k < ch.count; ++k) {
+            Layer& L = h->layers[ch.first + k];
+            ChainLayer& c = ch.host[k];
+            memset(&c, 0, sizeof(c));
+            c.tmap_a = L.tmap_a; c.tmap_b = L.tmap_b; c.tmap_res = L.tmap_res; c.tmap_out0 = L.tmap_out[0]; c.tmap_out1 = L.tmap_out[1];
+            c.p = L.p;
+            c.p.m_total = batch * L.p.dom_plane;
+            c.p.num_m_tiles = (c.p.m_total + kBlockM - 1) / kBlockM;
+            c.p.epi_groups = 2; c.p.epi_split = 1; c.p.dbg = nullptr;
+            c.p.split_from = ((c.p.num_m_tiles + 1) / 2) * c.p.num_n_tiles;
+            c.p.sig_flags = L.signals ? L.flags : nullptr;
+            c.p.wait_flags = nullptr;
+            if (k > 0) {
+                const Layer& P = h->layers[L.wait_on];
+                c.p.wait_flags = P.flags;
+                c.p.wait_expected = P.num_n_tiles * 2;              // both epilogue groups store part of every tile
+                c.p.wait_margin = L.s.k == 3 ? L.Win + 3 : 0;
+                c.p.wait_blocks = (batch * P.p.dom_plane + 127) / 128;
+            }
+            c.res_flags = nullptr;
+            if (L.s.res >= 0)
+                for (int q = 0; q < k; ++q) {
+                    const Layer& R = h->layers[ch.first + q];
+                    if (R.s.idx == L.s.res && R.signals) {       // the residual rows come from a layer of this chain
+                        c.res_flags = R.flags; c.res_expected = R.num_n_tiles * 2; c.res_blocks = (batch * R.p.dom_plane + 127) / 128;
+                    }
+                }
+            c.rot = (k * 25) % pairs;
+        }
+        CUDA_TRY(cudaMemcpyAsync(ch.dev, ch.host.data(), sizeof(ChainLayer) * ch.count, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->chain_batch = batch;
+    return FVY_OK;
+}
+
+static int launch_chain(fvy_handle* h, const fvy_handle::Chain& ch) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(h->num_sms & ~1); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = h->chain_smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (h->use_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.attrs = at; cfg.numAttrs = na;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_chain_kernel, (const ChainLayer*)ch.dev, ch.count, h->chain_nb, h->chain_a, h->chain_b));
+    h->launches += 1;
     return FVY_OK;
 }
 
@@ -959,6 +1062,12 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
         }
     for (int i = first; i < last; ++i) {
         Layer& L = h->layers[i];
+        if (h->flags_live && h->use_chain && L.chain >= 0 && L.chain_pos == 0 && first == 0 && last == (int)h->layers.size()) {
+            const fvy_handle::Chain& ch = h->chains[L.chain];
+            if (int e = launch_chain(h, ch)) return e;
+            i += ch.count - 1;
+            continue;
+        }
         if (L.s.src == -1 && h->fused_stem) {
             if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
             if (h->stem_mode == 2) {
@@ -1024,7 +1133,8 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             L.p.wait_flags = nullptr;
             if (wait_live[i]) {
                 const Layer& P = h->layers[L.wait_on];
-                const int pgroups = (P.p.epi_groups == 2 && P.BN >= 64 && P.p.epi_split != 0) ? 2 : 1;
+                const bool p_chained = h->use_chain && P.chain >= 0 && first == 0 && last == (int)h->layers.size();   // conv_chain_kernel: always column-split
+                const int pgroups = p_chained ? 2 : ((P.p.epi_groups == 2 && P.BN >= 64 && P.p.epi_split != 0) ? 2 : 1);
                 L.p.wait_flags = P.flags;
                 L.p.wait_expected = P.num_n_tiles * pgroups;
                 L.p.wait_margin = L.s.k == 3 ? L.Win + 3 : 0;
@@ -1058,6 +1168,8 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
         if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
     }
     const int nl = (int)h->layers.size();
+    if (h->use_chain && h->use_flags && h->d_flags)
+        if (int e = prepare_chains(h, batch)) return e;
     auto run_all = [&]() -> int {          // one whole forward: the tile-dependency counters start at zero and are live
         if (h->use_flags && h->d_flags) {
             CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, h->flags_bytes, h->stream));
