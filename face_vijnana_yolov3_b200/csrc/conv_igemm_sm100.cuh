@@ -481,6 +481,46 @@ __device__ __forceinline__ int half_chunk_col(int c, int half) {
     return c < kQ ? half * (BN / 4) + c * 32 : BN / 2 + half * (BN / 4) + (c - kQ) * 32;
 }
 
+
+// ---- single-thread producer fast paths: raw shared-memory addresses, no per-iteration address conversion -------------------
+__device__ __forceinline__ bool mbar_try_u32(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, bool backoff) {
+    if (mbar_try_u32(bar, parity)) return;
+    for (uint32_t spin = 0;; ++spin) {
+        if (mbar_try_u32(bar, parity)) return;
+        if (backoff && spin > 8) __nanosleep(spin > 64 ? 64 : 20);
+        if (spin > (1u << 23)) {
+            printf("fvy: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// CTA2: cta_group::2 form, `bar` is the LEADER's barrier (shared::cluster address); else the CTA's own barrier
+template <bool CTA2>
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if constexpr (CTA2)
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                     "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                     "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                     : "memory");
+}
+
 // State handed to the MMA issue loop (one thread per CTA / CTA pair).
 struct MmaCtx {
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *tmem_full, *tmem_empty;
@@ -667,6 +707,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int a_load_tap = p.a_slab == 2 ? 2 : 1;                 // tap index distance between them
             int dep_ready = -1;
             long long dbg_wait = 0;
+            // Fast paths.  This loop is ONE thread's scalar code and its length is what a narrow layer's operand rate hangs on
+            // (measured on conv_1 / conv_3, ncu source view: ~100 SASS instructions and ~700 cycles per slot in the generic loop
+            // below, against ~250 for the TMA instruction itself), so the two common shapes - a slab slot per (filter row, K chunk)
+            // with one or two boxes, and one tile box per K chunk of a 1x1 layer - get loops with everything hoisted: row offsets
+            // in registers, raw shared-memory addresses advanced by addition, no parameter reloads.
+            const bool dbg = p.dbg != nullptr;
+            const int fast_mode = split_from < num_tiles ? 0
+                                  : (p.a_slab >= 1 && p.gt == 3 && p.a_cover == 3 && p.num_taps == 9) ? p.a_slab
+                                  : (p.a_slab == 0 && p.gt == 1 && p.a_cover == 1 && p.num_taps == 1) ? 3 : 0;
+            if (fast_mode != 0) {
+                const int nnt = p.num_n_tiles, kcn = p.k_chunks, a_choff = p.a_choff, stages = p.a_stages;
+                const int* wflags = p.wait_flags;
+                const int wexp = p.wait_expected, wmargin = p.wait_margin, wblocks = p.wait_blocks;
+                const int n_rows = fast_mode == 3 ? 1 : 3, n_box = fast_mode == 2 ? 2 : 1;
+                int off0[3], off1[3];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) { off0[g] = p.tap_off[fast_mode == 3 ? 0 : 3 * g]; off1[g] = p.tap_off[fast_mode == 3 ? 0 : 3 * g + 2]; }
+                const uint32_t ring0 = smem_u32(a_ring), empty0 = smem_u32(a_empty), full_own0 = smem_u32(a_full);
+                const uint32_t full_tx0 = CTA2 ? map_to_cta(full_own0, 0) : full_own0;
+                const uint32_t empty_end = empty0 + 8u * (uint32_t)stages;
+                uint32_t sa = ring0, be = empty0, bf = full_own0, bt = full_tx0, par = 1;     // parity of a free slot's `empty` barrier
+                constexpr int kTileRows = CTA2 ? 2 * kBlockM : kBlockM;
+                const int rank_off = (int)cta_rank * kBlockM;
+                for (int tile = cta_first; tile < num_tiles; tile += cta_step) {
+                    const int m0 = (nnt == 1 ? tile : tile / nnt) * kTileRows + rank_off;
+                    if (wflags != nullptr)
+                        wait_blocks_ready(wflags, wexp, max(0, (m0 - wmargin) >> 7), min(wblocks - 1, (m0 + kBlockM - 1 + wmargin) >> 7), dep_ready);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        if (g >= n_rows) break;
+                        const int row0 = m0 + off0[g], row1 = m0 + off1[g];
+                        for (int kc = 0, col = a_choff; kc < kcn; ++kc, col += BK) {
+                            const long long c0 = dbg ? clock64() : 0;
+                            mbar_wait_u32(be, par, bo);
+                            if (dbg) dbg_wait += clock64() - c0;
+                            if (arrives) mbar_expect_tx_u32(bf, tx);
+                            tma_load_2d_u32<CTA2>(sa, &tmap_a, bt, col, row0);
+                            if (n_box == 2) tma_load_2d_u32<CTA2>(sa + (uint32_t)kSlabBytes, &tmap_a, bt, col, row1);
+                            sa += (uint32_t)a_slot_bytes; be += 8; bf += 8; bt += 8;
+                            if (be == empty_end) { sa = ring0; be = empty0; bf = full_own0; bt = full_tx0; par ^= 1; }
+                        }
+                    }
+                }
+            } else
             for (int item = cta_first; item < num_items; item += cta_step) {
                 int tile, half;
                 decode_item(item, split_from, tile, half);
