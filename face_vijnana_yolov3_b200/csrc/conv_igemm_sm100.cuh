@@ -268,8 +268,12 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(map)), "r"(map_to_cta(smem_u32(bar), 0)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Remote arrival on the LEADER's barrier.  Relaxed: what the arrival orders is this warp's TMEM reads (complete after
+// tcgen05.wait::ld, fenced by tcgen05.fence::before_thread_sync) against the leader's next MMA into the stage - no generic
+// memory is handed over.  The .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrival, which with
+// the epilogue's stores in flight cost ~2000 cycles per tile in every CTA-pair layer (ncu source view / FVY_DBG, conv_7).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(smem_u32(bar), 0)) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(smem_u32(bar), 0)) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
