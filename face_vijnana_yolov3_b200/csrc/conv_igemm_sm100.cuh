@@ -60,12 +60,14 @@ enum OutKind : int {
 
 struct OutDesc {
     void* ptr;
+    const void* aux;   // tma == 2: seven CUtensorMaps (global memory) of the 5-D phase view, box = 1, 2, 4 ... 64 pixel pairs
     int kind;
     int pitch;    // elements per pixel row of the destination buffer
     int choff;    // first destination channel
     int nmax;     // batch capacity of the buffer (phase stride)
     int c_real;   // valid channels (heads: 18 / 255 / 6); others: >= BLOCK_N * num_n_tiles
     int tma;      // 1: stored with TMA (tmap_out[o]); rows of the compute domain coincide with rows of this buffer
+                  // 2: OUT_PHASE stored with TMA through the 5-D phase view, one store per image row the tile touches
 };
 
 struct ConvParams {
@@ -190,6 +192,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* smem_src, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -660,8 +667,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tma_prefetch_desc(&tmap_a);
             tma_prefetch_desc(&tmap_b);
             if (p.res != nullptr) tma_prefetch_desc(&tmap_res);
-            if (p.out[0].tma) tma_prefetch_desc(&tmap_out0);
-            if (p.out[1].tma) tma_prefetch_desc(&tmap_out1);
+            if (p.out[0].tma == 1) tma_prefetch_desc(&tmap_out0);
+            if (p.out[1].tma == 1) tma_prefetch_desc(&tmap_out1);
         }
         // all 152 barriers, 5 per lane (arrival counts: 1, except the accumulator-free and chunk-staged barriers)
         constexpr int kBars = 2 * kMaxA + 2 * kMaxB + 2 * kMaxAcc + 6 * kMaxRing;
@@ -1081,6 +1088,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 if (++pf_buf == nb) pf_buf = 0;
             };
+            // OUT_PHASE by TMA (OutDesc::tma == 2): the 128 staged rows are pixels m0 .. m0+127 of the padded domain (m0 and the row
+            // pitch are even: 64 pairs of the 5-D phase view).  Per image row the tile touches: a run that reaches the row's end is
+            // ONE 64-pair box (TMA clips the overrun); a run that ends with the tile is covered by two overlapping boxes of the
+            // largest power of two that fits (same data written twice where they overlap).  Box starts are never negative.
+            const int dom_h = p.dom_plane / p.dom_w, half_w = p.dom_w >> 1;
+            auto phase_store = [&](const uint8_t* sbuf, const OutDesc& od, int c0, int m0) {
+                const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(od.aux);
+                const int pairs = (min(m0 + kBlockM, p.m_total) - m0) >> 1;
+                const int R = (int)__umul64hi((unsigned long long)m0, p.magic_w);    // image row (over all images) of pixel m0
+                int img = (int)__umul64hi((unsigned long long)m0, p.magic_plane);
+                int y = R - img * dom_h;
+                int a = (m0 - R * p.dom_w) >> 1;                                     // first pair of the run inside its row
+                const int nmax2 = 2 * od.nmax;
+                for (int q = 0; q < pairs;) {
+                    const int n = min(half_w - a, pairs - q);
+                    const int yh = y >> 1, j = (y & 1) * nmax2 + img;
+                    if (a + n == half_w) {
+                        tma_store_5d(sbuf + q * 128, maps + 6, c0, 0, a, yh, j);
+                    } else {
+                        const int k = 31 - __clz(n), sz = 1 << k;
+                        tma_store_5d(sbuf + q * 128, maps + k, c0, 0, a, yh, j);
+                        if (n > sz) tma_store_5d(sbuf + (q + n - sz) * 128, maps + k, c0, 0, a + n - sz, yh, j);
+                    }
+                    q += n; a = 0;
+                    if (++y == dom_h) { y = 0; ++img; }
+                }
+            };
             if (has_res)
                 for (int i = 0; i < nb; ++i) prefetch_res();      // every buffer starts free
             int buf = 0, prev = -1; uint32_t sph = 0;
@@ -1096,8 +1130,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     mbar_wait(&staged[buf], sph);
                     if (any_tma) {
                         const uint8_t* sbuf = ring + buf * kChunkBytes;
-                        if (p.out[0].tma) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + col, m0);
-                        if (p.out[1].tma) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + col, m0);
+                        if (p.out[0].tma == 1) tma_store_2d(sbuf, &tmap_out0, p.out[0].choff + n0 + col, m0);
+                        else if (p.out[0].tma == 2) phase_store(sbuf, p.out[0], p.out[0].choff + n0 + col, m0);
+                        if (p.out[1].tma == 1) tma_store_2d(sbuf, &tmap_out1, p.out[1].choff + n0 + col, m0);
+                        else if (p.out[1].tma == 2) phase_store(sbuf, p.out[1], p.out[1].choff + n0 + col, m0);
                         bulk_commit();
                     }
                     if (prev >= 0) {

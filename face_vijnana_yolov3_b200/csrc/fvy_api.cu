@@ -90,6 +90,28 @@ static int make_tmap_b3(CUtensorMap* m, const void* base, uint64_t cin, uint64_t
     return FVY_OK;
 }
 
+// 4-phase buffer [rp][cp][n][H/2+2][W/2+2][C] (what a stride-2 consumer reads) seen from the PRODUCER's padded compute domain:
+// pixel (img, hp, wp) lives at phase (hp&1, wp&1), position (hp>>1, wp>>1).  A run of consecutive pixels of one image row is
+// the box (32 channels, cp = 0..1, 64 values of wp>>1) of the 5-D tensor (C, cp, wp>>1, hp>>1, rp*2*nmax + img): its layout in
+// shared memory - C fastest, then cp, then wp>>1 - is exactly 2 x box_pairs consecutive domain rows of a staged 32-channel
+// chunk.  TMA clips the part of a box that runs past (W+2)/2; a negative start raises "illegal instruction" and a run that
+// ends at the tile's end (not the row's) has nothing to clip it, so the store warp covers such a run with two (overlapping)
+// boxes of the largest power of two that fits - hence one map per box size 1, 2, 4 ... 64 pairs, kept in global memory
+// (tools/phase_tma_test.cu pins these properties).  Replaces 128 threads writing 16-byte pieces (conv_igemm_kernel, tma == 2).
+static int make_tmap_phase(CUtensorMap* m, const void* base, int nmax, int H, int W, int pitch_elems, int box_pairs) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const uint64_t pw = (uint64_t)(W / 2 + 2), plane = (uint64_t)(H / 2 + 2) * pw, eb = (uint64_t)pitch_elems * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)pitch_elems, 2, (cuuint64_t)((W + 2) / 2), (cuuint64_t)((H + 2) / 2), (cuuint64_t)(3 * nmax)};
+    cuuint64_t strides[4] = {(cuuint64_t)nmax * plane * eb, eb, pw * eb, plane * eb};
+    cuuint32_t box[5] = {32, 2, (cuuint32_t)box_pairs, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled (5-D phase view) failed with CUresult %d (H=%d W=%d C=%d)", (int)r, H, W, pitch_elems);
+    return FVY_OK;
+}
+
 // ------------------------------------------------------------------------------------------ small kernels
 // Stem operand: im2col of the 3x3 / pad 1 / stride 1 window of the RGB input, K index = (r*3+s)*3 + c,
 // padded 27 -> 32 (one 64-byte swizzle row per pixel).  yolov3_detect.py:221 (conv_0), :205 (ZeroPadding2D(1)).
@@ -812,9 +834,20 @@ static int build_plan(fvy_handle* h) {
         bool tmap_fail = false;
         const bool use_tma_store = env_int("FVY_TMA_STORE", 1) != 0;
         auto add_out = [&](void* ptr, int kind, int pitch, int choff, int c_real) {
-            OutDesc od; od.ptr = ptr; od.kind = kind; od.pitch = pitch; od.choff = choff; od.nmax = nmax; od.c_real = c_real;
+            OutDesc od; od.ptr = ptr; od.aux = nullptr; od.kind = kind; od.pitch = pitch; od.choff = choff; od.nmax = nmax; od.c_real = c_real;
             od.tma = (kind == OUT_PADDED && coincident && use_tma_store) ? 1 : 0;
             if (no < 2 && od.tma && make_tmap_2d(&L.tmap_out[no], ptr, (uint64_t)pitch, out_rows, (uint64_t)pitch, 32, kBlockM)) tmap_fail = true;
+            // 4-phase form of a stride-1 layer's output: TMA stores through the 5-D phase view (needs an even padded width, which
+            // every level with a stride-2 consumer has)
+            if (no < 2 && kind == OUT_PHASE && coincident && use_tma_store && env_int("FVY_TMA_PHASE", 1) != 0 && s.stride == 1 && (L.Wout & 1) == 0 &&
+                (L.Hout & 1) == 0) {
+                CUtensorMap maps[7];
+                bool ok = true;
+                for (int k = 0; k < 7 && ok; ++k) ok = make_tmap_phase(&maps[k], ptr, nmax, L.Hout, L.Wout, pitch, 1 << k) == FVY_OK;
+                void* dmaps = nullptr;
+                if (!ok || dev_alloc(h, &dmaps, sizeof(maps), false) || cudaMemcpy(dmaps, maps, sizeof(maps), cudaMemcpyHostToDevice) != cudaSuccess) tmap_fail = true;
+                else { od.tma = 2; od.aux = dmaps; L.tmap_out[no] = maps[6]; }
+            }
             if (no < 2) p.out[no] = od;
             ++no;
         };
