@@ -749,14 +749,19 @@ static int build_plan(fvy_handle* h) {
         if (!b_res) {
             // streaming: maximise the taps in flight of the scarcer operand, then the bytes in flight
             const size_t b_slot = b_cover * b_tile;
+            // Stride-2 layers: an A slot is two slabs (35 KB at BK = 64) and arrives from the 4-phase planes with the latency of a
+            // cold read, while the weights are shared by every CTA and hit L2 - with two A slots the next one can only be requested
+            // when the current one is consumed and the MMA issuer starves (FVY_DBG: conv_12 waits for operands 74 % of the time),
+            // so these layers take at least three A slots when that leaves two B slots.
             long best = -1;
-            for (int a = 2; a <= std::min(kMaxA, stages_cap); ++a)
-                for (int b = 2; b <= std::min(kMaxB, stages_cap * gt); ++b) {
-                    const size_t bytes = a * a_slot + b * b_slot;
-                    if (bytes > budget) break;
-                    const long score = (long)std::min(a * a_cover, b * b_cover) * 1000000 + (long)(bytes >> 10);
-                    if (score > best) { best = score; a_stages = a; b_stages = b; }
-                }
+            for (int min_a = slab2 ? env_int("FVY_S2_MINA", 3) : 2; best < 0 && min_a >= 2; --min_a)
+                for (int a = min_a; a <= std::min(kMaxA, stages_cap); ++a)
+                    for (int b = 2; b <= std::min(kMaxB, stages_cap * gt); ++b) {
+                        const size_t bytes = a * a_slot + b * b_slot;
+                        if (bytes > budget) break;
+                        const long score = (long)std::min(a * a_cover, b * b_cover) * 1000000 + (long)(bytes >> 10);
+                        if (score > best) { best = score; a_stages = a; b_stages = b; }
+                    }
             if (best < 0) return fail(FVY_E_INVALID, "conv_%d: no operand pipeline fits in shared memory", s.idx);
         }
         L.stages = a_stages; L.b_stages = b_stages; L.b_resident = b_res;
@@ -840,7 +845,7 @@ static int build_plan(fvy_handle* h) {
             // 4-phase form of a stride-1 layer's output: TMA stores through the 5-D phase view (needs an even padded width, which
             // every level with a stride-2 consumer has)
             if (no < 2 && kind == OUT_PHASE && coincident && use_tma_store && env_int("FVY_TMA_PHASE", 1) != 0 && s.stride == 1 && (L.Wout & 1) == 0 &&
-                (L.Hout & 1) == 0) {
+                (L.Hout & 1) == 0 && L.Wout >= env_int("FVY_TMA_PHASE_MIN_W", 32)) {   // narrower rows: too many stores per tile (conv_60 @26: 57 vs 56 us)
                 CUtensorMap maps[7];
                 bool ok = true;
                 for (int k = 0; k < 7 && ok; ++k) ok = make_tmap_phase(&maps[k], ptr, nmax, L.Hout, L.Wout, pitch, 1 << k) == FVY_OK;
