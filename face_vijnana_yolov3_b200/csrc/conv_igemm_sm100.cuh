@@ -400,7 +400,7 @@ struct SmemLayout {
     static constexpr int b_bytes = BN * BK * 2;
     static constexpr int stage_bytes = a_bytes + b_bytes;
 };
-__host__ __device__ constexpr int acc_stages(int bn) { return bn <= 64 ? 4 : 2; }
+__host__ __device__ constexpr int acc_stages(int bn) { return bn <= 128 ? 4 : 2; }   // 512 TMEM columns at BN = 128 and 256
 
 // Packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogue is instruction-issue bound, these halve its add / multiply count.
 // Each half is an ordinary IEEE round-to-nearest operation - same result as the scalar form.
