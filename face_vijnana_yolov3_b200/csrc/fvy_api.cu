@@ -502,6 +502,7 @@ struct fvy_handle {
         bool operator<(const GraphKey& o) const { return std::tie(batch, dtype, set, img) < std::tie(o.batch, o.dtype, o.set, o.img); }
     };
     std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, long long> graph_launches;   // kernels captured in each graph (what one replay launches)
     bool use_graph = true, capturing = false;
     struct Chain { int first = 0, count = 0; ChainLayer* dev = nullptr; std::vector<ChainLayer> host; };
     std::vector<Chain> chains; bool use_chain = true; int chain_batch = -1;
@@ -1256,7 +1257,7 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
     if (it == h->graphs.end()) {
         if (h->graphs.size() >= 16) {          // callers that keep changing device pointers: do not hoard graphs
             for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
-            h->graphs.clear();
+            h->graphs.clear(); h->graph_launches.clear();
         }
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ge = nullptr;
@@ -1271,11 +1272,12 @@ static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int bat
         const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
         if (ie != cudaSuccess) return fail(FVY_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        h->graph_launches[key] = h->launches - launches0;
         h->launches = launches0;
         it = h->graphs.emplace(key, ge).first;
     }
     CUDA_TRY(cudaGraphLaunch(it->second, h->stream));
-    h->launches += nl;
+    h->launches += h->graph_launches[key];
     if (h->last_slot >= 0) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
     return FVY_OK;
 }

@@ -349,7 +349,7 @@ def test_facedetector_test_csv_batched_equals_per_image(tmp_path):
 def test_full_size_batch_invariance_and_tile_dependency_equivalence():
     """BASELINE configs[1] size (batch 40 @416).  Size-independent properties of the conv stack: an image's head logits do not
     depend on the batch it travels in (bit-exact: tiles change, a row's dot products do not), and the cross-layer tile
-    dependencies / CUDA graph (which only engage at this size) change nothing."""
+    dependencies / layer chains / CUDA graph (which only engage at this size) and the TMA form of the 4-phase stores change nothing."""
     import os
     specs = arch.yolo3_table(1)
     stream = synth.darknet_stream(specs, 0, synth.INIT_KERAS_DEFAULT)
@@ -361,9 +361,9 @@ def test_full_size_batch_invariance_and_tile_dependency_equivalence():
     for a, b in zip(full, again):
         assert np.array_equal(a, b)
     eng.close()
-    old = {k: os.environ.get(k) for k in ("FVY_FLAGS", "FVY_GRAPH")}
+    old = {k: os.environ.get(k) for k in ("FVY_FLAGS", "FVY_GRAPH", "FVY_CHAIN", "FVY_TMA_PHASE")}
     try:
-        os.environ["FVY_FLAGS"] = "0"; os.environ["FVY_GRAPH"] = "0"
+        os.environ["FVY_FLAGS"] = "0"; os.environ["FVY_GRAPH"] = "0"; os.environ["FVY_CHAIN"] = "0"; os.environ["FVY_TMA_PHASE"] = "0"
         plain = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
         plain.load_weights(stream)
         ref = plain.forward(x)
