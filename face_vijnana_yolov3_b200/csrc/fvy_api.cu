@@ -433,6 +433,131 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
     }
 }
 
+// Third form of the fused stem (default, FVY_STEM=3): the same staged-row scheme and K order as stem_rows_kernel, but every
+// WARP owns a strip of 16 output columns over a segment of rows and keeps its own ring of staged rows (18 pixels x 3 channels,
+// two copies) - no block-wide barrier at all.  stem_rows_kernel spent 35 % of its stall samples in the two-row barrier; here a
+// warp only ever waits for its own loads (two rows ahead, in registers while the current row is computed), and 24 independent
+// warps per SM hide each other's latency.  The (image, strip, row) space is cut into one equal piece per resident warp.  Halo columns are re-read by the neighbouring strip (12 %, L1 / L2 hits).
+constexpr int kStripWarps = 8;
+constexpr int kStripLen = 64;          // staged elements per row copy: 18 pixels x 3 channels = 54, padded
+template <typename T>
+__global__ void __launch_bounds__(kStripWarps * 32, 3)
+stem_strip_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, const __nv_bfloat16* __restrict__ wgt /*[32][32], k = 10 r + j*/,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*4-phase*/) {
+    __shared__ __align__(16) uint16_t srows[kStripWarps][8][2][kStripLen];
+    __shared__ __align__(16) uint32_t stile[kStripWarps][16][20];
+    const int lane = threadIdx.x & 31, quad = lane & 3, grp = lane >> 2, wib = threadIdx.x >> 5;
+    // work = (image, strip, row) triples in that order; every warp of the grid takes one contiguous, equally long piece of it
+    // (a piece may continue in the next strip / image: the ring of staged rows is simply primed again there)
+    const int strips = W >> 4;
+    const long long total = (long long)batch * strips * H;
+    const long long nwarps = (long long)gridDim.x * kStripWarps;
+    const long long piece = (total + nwarps - 1) / nwarps;
+    long long pos = ((long long)blockIdx.x * kStripWarps + wib) * piece;
+    const long long pos_end = min(total, pos + piece);
+    if (pos >= pos_end) return;
+    uint32_t bfrag[4][2][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(wgt + (j * 8 + grp) * 32 + t * 16 + quad * 2);
+            bfrag[j][t][0] = __ldg(wr);
+            bfrag[j][t][1] = __ldg(wr + 4);
+        }
+    float bia[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bia[j][0] = __ldg(bias + j * 8 + quad * 2); bia[j][1] = __ldg(bias + j * 8 + quad * 2 + 1); }
+    // this lane's four (k, k+1) pairs of a pixel: k = ks*16 + half*8 + quad*2 -> filter row r = k / 10, window element j = k % 10
+    int pr[4], pj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (i >> 1) * 16 + (i & 1) * 8 + quad * 2;
+        pr[i] = k < 30 ? k / 10 : 0;             // k = 30, 31: zero weights, any valid address
+        pj[i] = k < 30 ? k % 10 : 0;
+    }
+    const int par = grp & 1;                     // parity of this lane's pixels: which copy gives 4-byte aligned pairs
+    const int pw = (W >> 1) + 2;
+    const long long plane = (long long)((H >> 1) + 2) * pw;
+    while (pos < pos_end) {
+    const long long col = pos / H;                           // (image, strip) column of this run of rows
+    const int h0 = (int)(pos - col * H);
+    const int h1 = (int)min((long long)H, (long long)h0 + (pos_end - pos));
+    const long long n = col / strips;
+    const int w0 = (int)(col - n * strips) << 4;
+    pos += h1 - h0;
+    // staged element i of a strip row = image element (w0 - 1) * 3 + i of that row (zero outside the image); lanes own i = lane, lane + 32
+    const int c0 = (w0 - 1) * 3 + lane, c1 = c0 + 32;
+    const bool ok0 = c0 >= 0 && c0 < W * 3, ok1 = lane + 32 < 54 && c1 < W * 3;
+    const T* base = img + (n * H) * (long long)W * 3;
+    auto fetch = [&](int hh, float& a, float& b) {
+        const bool in = hh >= 0 && hh < H;
+        const T* src = base + (long long)(in ? hh : 0) * W * 3;
+        a = (in && ok0) ? (float)__ldg(src + c0) : 0.f;
+        b = (in && ok1) ? (float)__ldg(src + c1) : 0.f;
+    };
+    auto stage = [&](int hh, float a, float b) {
+        uint16_t* E = srows[wib][hh & 7][0];
+        uint16_t* O = srows[wib][hh & 7][1];
+        const uint16_t x = __bfloat16_as_ushort(__float2bfloat16_rn(a)), y = __bfloat16_as_ushort(__float2bfloat16_rn(b));
+        E[lane] = x; E[lane + 32] = y;
+        if (lane >= 1) O[lane - 1] = x;
+        O[lane + 31] = y;
+    };
+    float p0a, p0b, p1a, p1b;                    // the two rows in flight
+    {
+        float a, b;
+        fetch(h0 - 1, a, b); stage(h0 - 1, a, b);
+        fetch(h0, a, b); stage(h0, a, b);
+        fetch(h0 + 1, a, b); stage(h0 + 1, a, b);
+        fetch(h0 + 2, p0a, p0b);
+        fetch(h0 + 3, p1a, p1b);
+    }
+    __syncwarp();
+    for (int h = h0; h < h1; ++h) {
+        uint32_t afrag[2][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint16_t* rp = srows[wib][(h - 1 + pr[i]) & 7][par] + pj[i] - par;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+                afrag[i >> 1][(i & 1) * 2 + rr] = *reinterpret_cast<const uint32_t*>(rp + (grp + rr * 8) * 3);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[j][0] = acc[j][2] = bia[j][0];
+            acc[j][1] = acc[j][3] = bia[j][1];
+            mma_m16n8k16_bf16(acc[j], afrag[0], bfrag[j][0][0], bfrag[j][0][1]);
+            mma_m16n8k16_bf16(acc[j], afrag[1], bfrag[j][1][0], bfrag[j][1][1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float a = acc[j][rr * 2 + 0], b = acc[j][rr * 2 + 1];
+                a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
+                __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
+                stile[wib][grp + rr * 8][j * 4 + quad] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+        // row h + 2 (loaded two iterations ago) goes into the slot of row h - 6; then the next load is issued
+        stage(h + 2, p0a, p0b);
+        p0a = p1a; p0b = p1b;
+        fetch(h + 4, p1a, p1b);
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const uint4 o = *reinterpret_cast<const uint4*>(&stile[wib][grp + rr * 8][quad * 4]);
+            const int wpix = w0 + grp + rr * 8;
+            const int hp = h + 1, wp = wpix + 1;
+            const long long orow = ((long long)((((hp & 1) << 1) | (wp & 1))) * nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
+            *reinterpret_cast<uint4*>(out + orow * 32 + quad * 8) = o;
+        }
+        __syncwarp();
+    }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ handle
 struct Layer {
     ConvSpec s;
@@ -475,7 +600,8 @@ struct fvy_handle {
     bool weights_loaded = false;
     bool use_pdl = true;
     bool fused_stem = true;              // conv_0 straight from the image (stem_conv_kernel) instead of im2col + GEMM
-    int stem_mode = 2;                   // 2: stem_rows_kernel (staged rows), 1: stem_conv_kernel (register gather)
+    int stem_blocks_per_sm = 3;          // resident blocks of stem_strip_kernel (occupancy query)
+    int stem_mode = 2;                   // 3: stem_strip_kernel (per-warp strips), 2: stem_rows_kernel (staged rows), 1: stem_conv_kernel (register gather)
     __nv_bfloat16* d_stem_w2 = nullptr;  // conv_0 weights in stem_rows_kernel's K order
     const void* cur_img = nullptr; int cur_dtype = FVY_F32;   // device image of the current forward (layer 0 re-runs)
     long long launches = 0;
@@ -640,13 +766,16 @@ static int build_plan(fvy_handle* h) {
         const char* v = getenv("FVY_FUSED_STEM");
         h->fused_stem = !(v && *v && atoi(v) == 0);
         const char* m = getenv("FVY_STEM");
-        h->stem_mode = (m && *m) ? atoi(m) : 2;
+        h->stem_mode = (m && *m) ? atoi(m) : 3;
         if (c.net_w % 16) h->stem_mode = 1;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_strip_kernel<float>, kStripWarps * 32, 0) == cudaSuccess && occ > 0) h->stem_blocks_per_sm = 2 * occ;   // two pieces per resident warp (161 vs 166 us)
+        if (const char* sb = getenv("FVY_STEM_BLOCKS")) if (*sb) h->stem_blocks_per_sm = atoi(sb);
     }
     if (int e = dev_alloc(h, (void**)&h->d_stem_w2, 32 * 32 * 2, true)) return e;
     {   // staged rows of stem_rows_kernel: 8 slots x 2 copies x (3 (W + 2) + 2) bf16 - beyond the 48 KB default for wide images
         const size_t need = (size_t)8 * 2 * ((((c.net_w + 2) * 3 + 2) + 7) & ~7) * 2;
-        if (need > 100 * 1024) h->stem_mode = 1;
+        if (need > 100 * 1024) { if (h->stem_mode == 2) h->stem_mode = 1; }
         else {                                   // static (transpose tiles) + dynamic exceed the 48 KB default
             CUDA_TRY(cudaFuncSetAttribute(stem_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             CUDA_TRY(cudaFuncSetAttribute(stem_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
@@ -733,12 +862,21 @@ static int build_plan(fvy_handle* h) {
         L.deep_k = k_iters * (L.BN / 32) > groups_kn;        // MMA-bound tiles: the epilogue has slack, its latency is what shows
         int nb = has_res ? nb_res : nb_plain, lead = 0;
         nb = std::max(2, std::min(nb, kMaxRing));
-        const size_t fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;
-        const size_t budget = 232448 - fixed;
+        size_t fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;
+        size_t budget = 232448 - fixed;
         // Resident weights: with a single N tile per CTA the whole [BN, K] weight tile is loaded once and every later
         // tile of the persistent CTA only streams A (half the operand bytes of a 1x1 layer, a quarter of a slab 3x3 layer).
         const size_t b_total = (size_t)L.taps * k_chunks * b_tile;
         int a_stages = 0, b_stages = 0, b_res = 0;
+        // conv_5 (stride 2, 64 -> 128): its 74 KB weight half-tile and three 35 KB A slots miss the budget by 6 KB with three
+        // staging buffers per group; streaming the weights instead re-reads 72 KB per tile from L2 next to 104 KB of A
+        // (~40 B/clk/SM, the MMA issuer starved 67 % of the time) - two staging buffers buy the residency.
+        if (L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot > budget && nb > 2 && !has_res &&
+            b_total + 3 * a_slot <= budget + (size_t)groups * (nb - 2) * kChunkBytes && env_int("FVY_RESIDENT_NB2", 1) != 0) {
+            nb = 2;
+            fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;
+            budget = 232448 - fixed;
+        }
         if (L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot <= budget) {
             if (L.taps * k_chunks / b_cover > kMaxB && a_cover == gt) b_cover = gt;
             if (L.taps * k_chunks / b_cover <= kMaxB) {
@@ -1109,7 +1247,16 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
         }
         if (L.s.src == -1 && h->fused_stem) {
             if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
-            if (h->stem_mode == 2) {
+            if (h->stem_mode == 3) {
+                const long long total = (long long)batch * (h->cfg.net_w / 16) * h->cfg.net_h;     // (image, strip, row) triples
+                const int blocks = (int)std::min<long long>((total + kStripWarps - 1) / kStripWarps, (long long)h->num_sms * h->stem_blocks_per_sm);
+                if (h->cur_dtype == FVY_F32)
+                    stem_strip_kernel<float><<<blocks, kStripWarps * 32, 0, h->stream>>>((const float*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
+                                                                                         h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
+                else
+                    stem_strip_kernel<double><<<blocks, kStripWarps * 32, 0, h->stream>>>((const double*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
+                                                                                          h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
+            } else if (h->stem_mode == 2) {
                 const long long total_rows = (long long)batch * h->cfg.net_h;
                 const int blocks = (int)std::min<long long>(total_rows, (long long)h->num_sms * 2);
                 const int rows_per_block = (int)(((total_rows + blocks - 1) / blocks + 1) & ~1LL);     // even: two rows per iteration
