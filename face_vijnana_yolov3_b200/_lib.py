@@ -41,7 +41,7 @@ class FvyPostParams(C.Structure):
 SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_load_weights", "fvy_weight_count", "fvy_forward",
            "fvy_decode", "fvy_correct_boxes", "fvy_nms", "fvy_bbox_iou", "fvy_postprocess", "fvy_detect", "fvy_num_layers",
            "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
-           "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step"]
+           "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step", "fvy_letterbox_u8", "fvy_staged_images", "fvy_read_staged"]
 
 _lib = None
 
@@ -77,6 +77,10 @@ def load():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [H, vp, C.c_int, C.c_int, C.POINTER(FvyPostParams), vp, C.c_int, vp, vp]
+    L.fvy_letterbox_u8.restype = C.c_int
+    L.fvy_letterbox_u8.argtypes = [H, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.fvy_staged_images.restype = C.c_void_p; L.fvy_staged_images.argtypes = [H]
+    L.fvy_read_staged.restype = C.c_int; L.fvy_read_staged.argtypes = [H, C.c_int, vp]
     L.fvy_num_layers.restype = C.c_int; L.fvy_num_layers.argtypes = [H]
     L.fvy_layer_info.restype = C.c_int; L.fvy_layer_info.argtypes = [H, C.c_int, ip]
     L.fvy_layer_output.restype = C.c_int; L.fvy_layer_output.argtypes = [H, C.c_int, C.c_int, vp]

@@ -558,6 +558,53 @@ stem_strip_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, 
     }
 }
 
+// ------------------------------------------------------------------------------------------ letterbox (face_detection.py:657-690)
+// cv.resize(image / 255, (w_p, h_p), INTER_CUBIC) + zero border, restated operation for operation (OpenCV resizeGeneric_ for
+// CV_64F: interpolateCubic with A = -0.75 in float, HResizeCubic then VResizeCubic accumulating in double left to right,
+// indices clamped to the image).  One thread per output pixel, three channels; -fmad=false keeps every product and sum
+// separately rounded as the C++ reference computes them.
+__device__ __forceinline__ void cubic_tab(int d, double scale, int src, int idx[4], float c[4]) {
+    const float f0 = (float)(((double)d + 0.5) * scale - 0.5);
+    const int s = (int)floorf(f0);
+    const float x = f0 - (float)s;
+    const float A = -0.75f;
+    c[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+    c[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    c[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) idx[k] = min(max(s + k - 1, 0), src - 1);
+}
+__global__ void letterbox_u8_kernel(const unsigned char* __restrict__ src, int src_h, int src_w, int w_p, int h_p, int pad_t, int pad_l,
+                                    int net_h, int net_w, float* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= net_w) return;
+    float* o = dst + ((size_t)y * net_w + x) * 3;
+    const int dx = x - pad_l, dy = y - pad_t;
+    if (dx < 0 || dx >= w_p || dy < 0 || dy >= h_p) { o[0] = o[1] = o[2] = 0.f; return; }
+    int xi[4], yi[4];
+    float xa[4], ya[4];
+    cubic_tab(dx, 1.0 / ((double)w_p / (double)src_w), src_w, xi, xa);
+    cubic_tab(dy, 1.0 / ((double)h_p / (double)src_h), src_h, yi, ya);
+    double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned char* row = src + (size_t)yi[k] * src_w * 3;
+        double r[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double v = ((double)row[xi[0] * 3 + c] / 255.0) * (double)xa[0];
+            v = v + ((double)row[xi[1] * 3 + c] / 255.0) * (double)xa[1];
+            v = v + ((double)row[xi[2] * 3 + c] / 255.0) * (double)xa[2];
+            v = v + ((double)row[xi[3] * 3 + c] / 255.0) * (double)xa[3];
+            r[c] = v * (double)ya[k];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] = k == 0 ? r[c] : acc[c] + r[c];
+    }
+    o[0] = (float)acc[0]; o[1] = (float)acc[1]; o[2] = (float)acc[2];
+}
+
 // ------------------------------------------------------------------------------------------ handle
 struct Layer {
     ConvSpec s;
@@ -600,6 +647,8 @@ struct fvy_handle {
     bool weights_loaded = false;
     bool use_pdl = true;
     bool fused_stem = true;              // conv_0 straight from the image (stem_conv_kernel) instead of im2col + GEMM
+    float* d_staged = nullptr;           // fvy_staged_images: [max_batch][net_h][net_w][3] float32, allocated on first use
+    unsigned char* d_lb_src = nullptr; size_t lb_src_bytes = 0;   // letterbox source scratch
     int stem_blocks_per_sm = 3;          // resident blocks of stem_strip_kernel (occupancy query)
     int stem_mode = 2;                   // 3: stem_strip_kernel (per-warp strips), 2: stem_rows_kernel (staged rows), 1: stem_conv_kernel (register gather)
     __nv_bfloat16* d_stem_w2 = nullptr;  // conv_0 weights in stem_rows_kernel's K order
@@ -1568,6 +1617,7 @@ void fvy_destroy(fvy_handle* h) {
     if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->d_lb_src) cudaFree(h->d_lb_src);
     for (void* p : h->d_input) if (p) cudaFree(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {h->ev_ready[0], h->ev_ready[1], h->ev_consumed[0], h->ev_consumed[1], h->ev_post, h->ev_d2h}) if (e) cudaEventDestroy(e);
@@ -1926,6 +1976,61 @@ int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host) {
     cudaFree(tmp);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(FVY_E_CUDA, "layer_output failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return FVY_OK;
+}
+
+float* fvy_staged_images(fvy_handle* h) {
+    if (!h) return nullptr;
+    if (!h->d_staged) {
+        cudaSetDevice(h->cfg.device);
+        const size_t bytes = (size_t)h->cfg.max_batch * h->cfg.net_h * h->cfg.net_w * 3 * sizeof(float);
+        void* p = nullptr;
+        if (dev_alloc(h, &p, bytes, true) != FVY_OK) return nullptr;
+        h->d_staged = (float*)p;
+    }
+    return h->d_staged;
+}
+
+int fvy_read_staged(fvy_handle* h, int batch, float* dst) {
+    if (!h || !dst) return fail(FVY_E_INVALID, "fvy_read_staged: NULL argument");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "fvy_read_staged: batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const float* staged = fvy_staged_images(h);
+    if (!staged) return fail(FVY_E_CUDA, "fvy_read_staged: staged batch allocation failed");
+    if (int e = copy_out(h, staged, dst, (size_t)batch * h->cfg.net_h * h->cfg.net_w * 3 * sizeof(float))) return e;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FVY_OK;
+}
+
+int fvy_letterbox_u8(fvy_handle* h, const unsigned char* src, int src_h, int src_w, int w_p, int h_p, int pad_t, int pad_l, int index) {
+    if (!h || !src) return fail(FVY_E_INVALID, "fvy_letterbox_u8: NULL argument");
+    if (src_h <= 0 || src_w <= 0 || w_p <= 0 || h_p <= 0 || pad_t < 0 || pad_l < 0 || pad_t + h_p > h->cfg.net_h || pad_l + w_p > h->cfg.net_w)
+        return fail(FVY_E_INVALID, "fvy_letterbox_u8: %dx%d -> %dx%d at (%d, %d) does not fit the %dx%d network input", src_w, src_h, w_p, h_p, pad_l, pad_t,
+                    h->cfg.net_w, h->cfg.net_h);
+    if (index < 0 || index >= h->cfg.max_batch) return fail(FVY_E_INVALID, "fvy_letterbox_u8: image slot %d outside [0, %d)", index, h->cfg.max_batch);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    float* staged = fvy_staged_images(h);
+    if (!staged) return fail(FVY_E_CUDA, "fvy_letterbox_u8: staged batch allocation failed");
+    const unsigned char* dsrc = src;
+    if (!is_device_ptr(src)) {
+        const size_t bytes = (size_t)src_h * src_w * 3;
+        if (bytes > h->lb_src_bytes) {                    // grows to the largest image seen (stream-ordered: earlier kernels have been enqueued)
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            if (h->d_lb_src) cudaFree(h->d_lb_src);
+            h->d_lb_src = nullptr; h->lb_src_bytes = 0;
+            CUDA_TRY(cudaMalloc((void**)&h->d_lb_src, bytes));
+            h->lb_src_bytes = bytes;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->d_lb_src, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));       // pageable source: the caller may reuse it, and the scratch is reused per image
+        dsrc = h->d_lb_src;
+    }
+    const dim3 grid((h->cfg.net_w + 127) / 128, h->cfg.net_h);
+    letterbox_u8_kernel<<<grid, 128, 0, h->stream>>>(dsrc, src_h, src_w, w_p, h_p, pad_t, pad_l, h->cfg.net_h, h->cfg.net_w,
+                                                     staged + (size_t)index * h->cfg.net_h * h->cfg.net_w * 3);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    if (!is_device_ptr(src)) CUDA_TRY(cudaStreamSynchronize(h->stream));   // the scratch is free for the next image
     return FVY_OK;
 }
 

@@ -21,6 +21,19 @@ DET_DTYPE = np.dtype([("xmin", "<i4"), ("ymin", "<i4"), ("xmax", "<i4"), ("ymax"
 assert DET_DTYPE.itemsize == C.sizeof(L.FvyDet) == 32
 
 
+class StagedImages:
+    """Device-resident float32 (B, H, W, 3) view of the handle's staged batch (fvy_staged_images)."""
+
+    def __init__(self, ptr, shape):
+        self._ptr, self.shape, self.dtype = int(ptr), tuple(shape), "float32"
+
+    def data_ptr(self):
+        return self._ptr
+
+    def is_contiguous(self):
+        return True
+
+
 def _ptr(x):
     if x is None:
         return None
@@ -202,6 +215,29 @@ class Engine:
         L.check(fn(self._h, _ptr(images), dtype, batch, C.byref(pp), _ptr(hw), max_out, _ptr(dets), _ptr(counts)))
         self._keep = (images, hw, dets, counts, pp)   # keep buffers alive for async use
         return dets, counts
+
+    # ---------------------------------------------------------------- FaceDetector.evaluate / test pre-processing (face_detection.py:657-690)
+    def letterbox(self, image_u8: np.ndarray, index: int, w_p: int, h_p: int, pad_t: int, pad_l: int) -> None:
+        """image/255 -> cv.resize(INTER_CUBIC) to (w_p, h_p) -> zero border, on the GPU, into slot ``index`` of the staged batch."""
+        if image_u8.dtype != np.uint8 or image_u8.ndim != 3 or image_u8.shape[2] != 3:
+            raise TypeError("letterbox expects a uint8 (H, W, 3) image")
+        image_u8 = np.ascontiguousarray(image_u8)
+        L.check(self.lib.fvy_letterbox_u8(self._h, _ptr(image_u8), image_u8.shape[0], image_u8.shape[1], int(w_p), int(h_p), int(pad_t), int(pad_l), int(index)))
+
+    def staged(self, batch: int) -> "StagedImages":
+        """The first ``batch`` images of the staged (letterboxed) batch as an ``images`` argument of detect / forward."""
+        if not 1 <= batch <= self.max_batch:
+            raise ValueError("batch out of range")
+        ptr = self.lib.fvy_staged_images(self._h)
+        if not ptr:
+            raise L.FvyError(-2, "the staged batch could not be allocated")
+        return StagedImages(ptr, (batch, self.net_h, self.net_w, 3))
+
+    def staged_to_host(self, batch: int) -> np.ndarray:
+        """Host copy of the staged batch (tests / inspection)."""
+        out = np.empty((batch, self.net_h, self.net_w, 3), np.float32)
+        L.check(self.lib.fvy_read_staged(self._h, int(batch), _ptr(out)))
+        return out
 
     def timer_start(self):
         L.check(self.lib.fvy_timer_start(self._h))

@@ -127,6 +127,18 @@ class FaceDetector(object):
         return [self._to_boxes(dets[b], int(counts[b])) for b in range(images.shape[0])]
 
     # ------------------------------------------------------------------ host image loop (:645-735, :788-883)
+    def _letterbox_geom(self, w, h):
+        """Resized extent and top / left padding exactly as the reference computes them (:664-688): Python float arithmetic."""
+        S = self.nn_arch['image_size']
+        pad_t = pad_l = 0
+        if w >= h:
+            w_p, h_p = S, int(h / w * S)
+            pad_t = (S - h_p) // 2
+        else:
+            h_p, w_p = S, int(w / h * S)
+            pad_l = (S - w_p) // 2
+        return w_p, h_p, pad_t, pad_l
+
     def _letterbox(self, image):
         import cv2 as cv
         S = self.nn_arch['image_size']
@@ -162,25 +174,30 @@ class FaceDetector(object):
                 box.ymax = np.min([box.ymax * h / S, h])
 
     def _run_files(self, draw_dir=None):
-        """The reference's per-file loop (:645-735, :788-883) with the detector call batched: files are letterboxed on the
-        host exactly as the reference does (cv2 cubic resize + zero border), ``max_batch`` of them go through ONE
-        ``detect_batch`` call, and rows are written in the reference's file order.  ``max_batch = 1`` is the reference."""
+        """The reference's per-file loop (:645-735, :788-883) with the pre-processing and the detector call on the GPU: each
+        file's pixels go to the device as uint8 and are letterboxed there (``fvy_letterbox_u8``: image/255, cv.resize INTER_CUBIC,
+        zero border - bit-identical to the reference's host code, which `_letterbox` keeps for comparison), ``max_batch`` of them
+        go through ONE detect call, and rows are written in the reference's file order.  ``max_batch = 1`` is the reference."""
         import cv2 as cv
         test_path = self.conf['test_path']
         output_file_path = self.conf['output_file_path']
         file_names = glob.glob(os.path.join(test_path, '*.jpg'))
         bs = max(1, int(self.max_batch))
+        eng = self.engine
         with open(output_file_path, 'w') as f:
             for start in range(0, len(file_names), bs):
                 chunk = file_names[start:start + bs]
-                originals, images, geoms = [], [], []
-                for count1, file_name in enumerate(chunk, start + 1):
+                originals, geoms = [], []
+                for i, file_name in enumerate(chunk):
                     if DEBUG:
-                        print(count1, '/', len(file_names), file_name)
-                    image_o = cv.imread(file_name, cv.IMREAD_COLOR)[:, :, ::-1]   # RGB like skimage.io.imread
-                    image, geom = self._letterbox(image_o / 255)
-                    originals.append(image_o); images.append(image[0]); geoms.append(geom)
-                all_boxes = self.detect_batch(np.stack(images)) if len(images) > 1 else [self.detect(images[0][np.newaxis])]
+                        print(start + i + 1, '/', len(file_names), file_name)
+                    image_o = np.ascontiguousarray(cv.imread(file_name, cv.IMREAD_COLOR)[:, :, ::-1])   # RGB like skimage.io.imread
+                    h, w = image_o.shape[0], image_o.shape[1]
+                    w_p, h_p, pad_t, pad_l = self._letterbox_geom(w, h)
+                    eng.letterbox(image_o, i, w_p, h_p, pad_t, pad_l)
+                    originals.append(image_o); geoms.append((w, h, pad_t, pad_l))
+                dets, counts = eng.detect(eng.staged(len(chunk)), pp=self._pp())
+                all_boxes = [self._to_boxes(dets[b], int(counts[b])) for b in range(len(chunk))]
                 for file_name, image_o, geom, boxes in zip(chunk, originals, geoms, all_boxes):
                     self._unletterbox(boxes, geom)
                     base = file_name.split('\\')[-1] if platform.system() == 'Windows' else file_name.split('/')[-1]

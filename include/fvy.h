@@ -175,6 +175,20 @@ int fvy_detect_async(fvy_handle* h, const void* images, int dtype, int batch, co
  * per-GPU gradients into multi_gpu_model's whole-batch mean (face_detection.py:369). */
 int fvy_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta_1, float beta_2,
                   float epsilon, float grad_scale, void* cuda_stream);
+/* Pre-processing of FaceDetector.evaluate / FaceDetector.test (src/space/face_detection.py:657-690 and :798-835):
+ *   image = imread(file) / 255;  image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC);
+ *   image = cv.copyMakeBorder(image, pad_t, pad_b, pad_l, pad_r, cv.BORDER_CONSTANT, value=[0, 0, 0])
+ * for one uint8 [src_h][src_w][3] image (host or device memory), on the GPU: OpenCV's separable bicubic (a = -0.75, float
+ * coefficients, float64 accumulation, horizontal pass first, replicated borders, source coordinate (d + 0.5) * scale - 0.5)
+ * followed by the cast to float32 that Keras applies to its input.  The result - bit-identical to float32(reference image) -
+ * is written to image slot `index` (0 <= index < max_batch) of the handle's staged batch, a DEVICE buffer
+ * float32 [max_batch][net_h][net_w][3] returned by fvy_staged_images(); pass that pointer as `images` (dtype FVY_F32) to
+ * fvy_detect / fvy_forward.  w_p, h_p, pad_t, pad_l are the caller's (the reference computes them with Python float
+ * arithmetic, face_detection.py:664-688); rows / columns outside [pad_t, pad_t + h_p) x [pad_l, pad_l + w_p) are zero. */
+int fvy_letterbox_u8(fvy_handle* h, const unsigned char* src, int src_h, int src_w, int w_p, int h_p, int pad_t, int pad_l, int index);
+float* fvy_staged_images(fvy_handle* h);
+/* Copies the first `batch` staged images to dst (host or device float32 [batch][net_h][net_w][3]); synchronous. */
+int fvy_read_staged(fvy_handle* h, int batch, float* dst);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void* fvy_host_alloc(size_t bytes);
 void fvy_host_free(void* p);

@@ -318,6 +318,29 @@ def test_capacity_error():
     eng.close()
 
 
+def test_letterbox_gpu_bit_exact_vs_oracle():
+    """fvy_letterbox_u8 (image/255, cv.resize INTER_CUBIC, zero border on the GPU) equals float32(oracle) bit for bit; the oracle is
+    pinned on the reference's own loop output and on cv2 (tests/test_oracle_letterbox.py)."""
+    from oracle import letterbox as LB
+    eng = Engine(416, 416, head=L.HEAD_FD6, max_batch=3)
+    rng = np.random.default_rng(8)
+    sizes = [(640, 480), (375, 500), (97, 131), (1500, 200), (416, 416), (131, 1000)]
+    for start in range(0, len(sizes), 3):
+        imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (w, h) in sizes[start:start + 3]]
+        for i, im in enumerate(imgs):
+            w_p, h_p, pad_t, _, pad_l, _ = LB.geometry(im.shape[1], im.shape[0], 416)
+            eng.letterbox(im, i, w_p, h_p, pad_t, pad_l)
+        got = eng.staged_to_host(len(imgs))
+        for i, im in enumerate(imgs):
+            want = LB.letterbox(im, 416).astype(np.float32)
+            assert np.array_equal(got[i], want), f"image {start + i} ({im.shape[1]}x{im.shape[0]}): max diff {np.abs(got[i] - want).max()}"
+    with pytest.raises(ValueError):
+        eng.letterbox(imgs[0], 3, 416, 312, 52, 0)          # slot outside the staged batch
+    with pytest.raises(ValueError):
+        eng.letterbox(imgs[0], 0, 416, 400, 52, 0)          # does not fit the network input
+    eng.close()
+
+
 def test_facedetector_test_csv_batched_equals_per_image(tmp_path):
     """FaceDetector.test() (reference :783-883): the batched file loop writes the same CSV as the reference's batch-1 loop."""
     cv = pytest.importorskip("cv2")
@@ -342,6 +365,21 @@ def test_facedetector_test_csv_batched_equals_per_image(tmp_path):
         outs.append(open(conf["output_file_path"]).read())
         fd.engine.close()
     assert outs[0] == outs[1] and outs[0].count("\n") > 0
+    # the reference's host form of the loop (cv2 letterbox in float64, one detect per file) writes the same rows
+    fd = FaceDetector(conf, max_batch=1)
+    fd.set_weight_stream(stream)
+    import glob
+    rows = []
+    for file_name in glob.glob(os.path.join(str(img_dir), "*.jpg")):
+        image_o = cv.imread(file_name, cv.IMREAD_COLOR)[:, :, ::-1]
+        image, geom = fd._letterbox(image_o / 255)
+        boxes = fd.detect(image)
+        fd._unletterbox(boxes, geom)
+        for box in boxes[:60]:
+            rows.append(",".join([os.path.basename(file_name), str(box.xmin), str(box.ymin), str(box.xmax - box.xmin), str(box.ymax - box.ymin),
+                                  str(box.get_score())]))
+    fd.engine.close()
+    assert "\n".join(rows) + "\n" == outs[0]
     first = outs[0].splitlines()[0].split(",")
     assert len(first) == 6 and first[0].endswith(".jpg")
 

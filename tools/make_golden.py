@@ -11,6 +11,8 @@ as small fixtures (this script is their provenance):
   post_fd6.npz            reference FaceDetector.detect (src/space/face_detection.py:885-949) on seeded
                           (1,13,13,6) maps through a fake model.predict.
   iou_cases.json          bbox_iou / _interval_overlap known answers computed by the reference code.
+  letterbox.npz           the image the reference's own FaceDetector.test() loop (src/space/face_detection.py:798-835, cv2 of this
+                          image) hands to detect(), for seeded uint8 images written as PNG-exact BMP files, image_size 64
   gt_tensor.npz           reference TrainingSequence.__getitem__ ground-truth tensors (src/space/face_detection.py:98-310)
                           for synthetic images / training.csv rows (letterbox geometry + cell assignment).
 
@@ -155,6 +157,44 @@ def gt_tensor_cases():
     print("gt tensors", len(targets), "positive cells", int(sum((t[..., 0] > 0).sum() for t in targets)))
 
 
+def letterbox_cases():
+    """Reference FaceDetector.test() (src/space/face_detection.py:783-883) run with a capturing detect(): its own imread / 255,
+    cv.resize(INTER_CUBIC) and cv.copyMakeBorder lines produce the images stored here."""
+    import tempfile
+    import cv2 as cv
+    fdm = R.load_face_detection()
+    fdm.DEBUG = False
+    fdm.imread = lambda path: cv.imread(path, cv.IMREAD_COLOR)[:, :, ::-1]
+    sizes = [(131, 97), (97, 131), (80, 80), (200, 60), (33, 150)]          # (w, h): down- and up-scaling, both orientations
+    rng = np.random.default_rng(11)
+    captured = {}
+    fd = fdm.FaceDetector.__new__(fdm.FaceDetector)
+    fd.nn_arch = {"image_size": 64, "bb_info_c_size": 6}
+    fd.hps = {"face_conf_th": 0.5, "nms_iou_th": 0.5, "num_cands": 60}
+    srcs = []
+    with tempfile.TemporaryDirectory() as d:
+        fd.conf = {"test_path": d, "output_file_path": os.path.join(d, "out.csv")}
+        for k, (w, h) in enumerate(sizes):
+            im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            cv.imwrite(os.path.join(d, f"im{k}.bmp.jpg"), im[:, :, ::-1], [cv.IMWRITE_JPEG_QUALITY, 100])
+            srcs.append(cv.imread(os.path.join(d, f"im{k}.bmp.jpg"), cv.IMREAD_COLOR)[:, :, ::-1].copy())     # the pixels the loop will see
+        order = []
+
+        def fake_detect(image):
+            captured[len(order)] = np.array(image[0]); order.append(1)
+            return []
+        fd.detect = fake_detect
+        import glob as _glob
+        names = _glob.glob(os.path.join(d, "*.jpg"))
+        fd.test()
+        idx = [int(os.path.basename(n)[2]) for n in names]
+    out = {}
+    for pos, k in enumerate(idx):
+        out[f"src{k}"] = srcs[k]; out[f"dst{k}"] = captured[pos]
+    np.savez_compressed(os.path.join(OUT, "letterbox.npz"), **out)
+    print("letterbox cases", len(idx), [captured[i].shape for i in range(len(idx))])
+
+
 if __name__ == "__main__":
     if not R.available():
         raise SystemExit("/root/reference is not available: golden fixtures can only be generated in the build container")
@@ -166,3 +206,4 @@ if __name__ == "__main__":
     post_fd6()
     iou_cases()
     gt_tensor_cases()
+    letterbox_cases()
