@@ -440,13 +440,29 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
 // warps per SM hide each other's latency.  The (image, strip, row) space is cut into one equal piece per resident warp.  Halo columns are re-read by the neighbouring strip (12 %, L1 / L2 hits).
 constexpr int kStripWarps = 8;
 constexpr int kStripLen = 64;          // staged elements per row copy: 18 pixels x 3 channels = 54, padded
+#ifndef FVY_STRIP_MINB
+#define FVY_STRIP_MINB 4
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kStripWarps * 32, 3)
+__global__ void __launch_bounds__(kStripWarps * 32, FVY_STRIP_MINB)
 stem_strip_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, const __nv_bfloat16* __restrict__ wgt /*[32][32], k = 10 r + j*/,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*4-phase*/) {
     __shared__ __align__(16) uint16_t srows[kStripWarps][8][2][kStripLen];
     __shared__ __align__(16) uint32_t stile[kStripWarps][16][20];
     const int lane = threadIdx.x & 31, quad = lane & 3, grp = lane >> 2, wib = threadIdx.x >> 5;
+    // weight / bias fragments live in shared memory, one 16-byte + one 8-byte entry per (n-tile, lane): 24 registers less per thread
+    // buys the fourth resident block per SM (with them in registers: 80 registers and three blocks, or spills)
+    __shared__ __align__(16) uint4 swf[4][32];
+    __shared__ __align__(8) float2 sbf[4][32];
+    if (wib < 4) {
+        const int j = wib;
+        uint4 f;
+        const uint32_t* wr0 = reinterpret_cast<const uint32_t*>(wgt + (j * 8 + grp) * 32 + quad * 2);
+        f.x = __ldg(wr0); f.y = __ldg(wr0 + 4); f.z = __ldg(wr0 + 8); f.w = __ldg(wr0 + 12);
+        swf[j][lane] = f;
+        sbf[j][lane] = make_float2(__ldg(bias + j * 8 + quad * 2), __ldg(bias + j * 8 + quad * 2 + 1));
+    }
+    __syncthreads();
     // work = (image, strip, row) triples in that order; every warp of the grid takes one contiguous, equally long piece of it
     // (a piece may continue in the next strip / image: the ring of staged rows is simply primed again there)
     const int strips = W >> 4;
@@ -456,18 +472,6 @@ stem_strip_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, 
     long long pos = ((long long)blockIdx.x * kStripWarps + wib) * piece;
     const long long pos_end = min(total, pos + piece);
     if (pos >= pos_end) return;
-    uint32_t bfrag[4][2][2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const uint32_t* wr = reinterpret_cast<const uint32_t*>(wgt + (j * 8 + grp) * 32 + t * 16 + quad * 2);
-            bfrag[j][t][0] = __ldg(wr);
-            bfrag[j][t][1] = __ldg(wr + 4);
-        }
-    float bia[4][2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { bia[j][0] = __ldg(bias + j * 8 + quad * 2); bia[j][1] = __ldg(bias + j * 8 + quad * 2 + 1); }
     // this lane's four (k, k+1) pairs of a pixel: k = ks*16 + half*8 + quad*2 -> filter row r = k / 10, window element j = k % 10
     int pr[4], pj[4];
 #pragma unroll
@@ -523,23 +527,21 @@ stem_strip_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, 
             for (int rr = 0; rr < 2; ++rr)
                 afrag[i >> 1][(i & 1) * 2 + rr] = *reinterpret_cast<const uint32_t*>(rp + (grp + rr * 8) * 3);
         }
-        float acc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            acc[j][0] = acc[j][2] = bia[j][0];
-            acc[j][1] = acc[j][3] = bia[j][1];
-            mma_m16n8k16_bf16(acc[j], afrag[0], bfrag[j][0][0], bfrag[j][0][1]);
-            mma_m16n8k16_bf16(acc[j], afrag[1], bfrag[j][1][0], bfrag[j][1][1]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
+            const uint4 wf = swf[j][lane];
+            const float2 bj = sbf[j][lane];
+            float acc[4] = {bj.x, bj.y, bj.x, bj.y};
+            mma_m16n8k16_bf16(acc, afrag[0], wf.x, wf.y);
+            mma_m16n8k16_bf16(acc, afrag[1], wf.z, wf.w);
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-                float a = acc[j][rr * 2 + 0], b = acc[j][rr * 2 + 1];
+                float a = acc[rr * 2 + 0], b = acc[rr * 2 + 1];
                 a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
                 __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
                 stile[wib][grp + rr * 8][j * 4 + quad] = *reinterpret_cast<uint32_t*>(&pk);
             }
+        }
         // row h + 2 (loaded two iterations ago) goes into the slot of row h - 6; then the next load is issued
         stage(h + 2, p0a, p0b);
         p0a = p1a; p0b = p1b;
