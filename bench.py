@@ -225,7 +225,7 @@ def main():
     flops_step = 2.0 * eng.macs_per_image() * B                      # algorithmic, un-padded
     peaks = _peaks()
     achieved = flops_step / (fwd_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": f"conv stack of one forward: {n_conv} conv layers in {n_fwd_launches} launches (stem_rows_kernel, conv_igemm_kernel, conv_chain_kernel)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": f"conv stack of one forward: {n_conv} conv layers in {n_fwd_launches} launches (stem_strip_kernel, conv_igemm_kernel, conv_chain_kernel)", "achieved": achieved,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "frac_of_burst_peak": achieved / peaks["tf_burst"], "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_step": flops_step, "avg_launch_ms": fwd_ms / max(1, n_fwd_launches), "forward_ms": fwd_ms,

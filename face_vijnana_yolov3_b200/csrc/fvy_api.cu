@@ -922,7 +922,7 @@ static int build_plan(fvy_handle* h) {
         // conv_5 (stride 2, 64 -> 128): its 74 KB weight half-tile and three 35 KB A slots miss the budget by 6 KB with three
         // staging buffers per group; streaming the weights instead re-reads 72 KB per tile from L2 next to 104 KB of A
         // (~40 B/clk/SM, the MMA issuer starved 67 % of the time) - two staging buffers buy the residency.
-        if (L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot > budget && nb > 2 && !has_res &&
+        if (slab2 && L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot > budget && nb > 2 && !has_res &&
             b_total + 3 * a_slot <= budget + (size_t)groups * (nb - 2) * kChunkBytes && env_int("FVY_RESIDENT_NB2", 1) != 0) {
             nb = 2;
             fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;

@@ -17,7 +17,7 @@ def launches(src, dst):
     h, rows = read_ncu(src)
     iN, iV, iG, iB = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("Block Size")
     L = [(r[iN].split("(")[0].replace("void ", "").replace("fvy::", ""), r[iG], r[iB], float(r[iV].replace(",", "")) / 1e3) for r in rows if len(r) > iV]
-    stems = [i for i, l in enumerate(L) if l[0].startswith("stem_rows")]
+    stems = [i for i, l in enumerate(L) if l[0].startswith("stem_")]
     a, b = stems[1], stems[2]            # second step of the run (the first is the warm-up)
     share = collections.OrderedDict()
     for l in L[a:b]:
@@ -43,7 +43,7 @@ def traffic(src, dst_csv, dst_json):
         d = per.setdefault(int(r[iI]), {"k": r[iN].split("(")[0].replace("void ", "").replace("fvy::", "")})
         d[r[iM]] = float(r[iV].replace(",", ""))
     ids = list(per)
-    stems = [i for i in ids if per[i]["k"].startswith("stem_rows")]
+    stems = [i for i in ids if per[i]["k"].startswith("stem_")]
     sel = [i for i in ids if i >= stems[-1]]          # the last forward
     unit = {r[iM]: r[h.index("Metric Unit")] for r in rows if len(r) > iV}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
