@@ -120,11 +120,24 @@ def run_reference(args, rank):
                              "sample": f"{sample} of the {args.batch} images per step x {args.steps} steps; torch-CPU fp32 restatement of the Keras graph "
                                        "+ C restatement of decode/NMS (Keras/TF not installable; reference is pure Python)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     return 0
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout when the
+    process group comes up), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the real stdout."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_OUT = sys.stdout
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -288,7 +301,7 @@ def main():
                            "l2": "no explicit flush: each step streams ~3.4 GB of activations (>> 126 MB L2) between reuses of the input"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "kept_boxes_last_step": kept}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
