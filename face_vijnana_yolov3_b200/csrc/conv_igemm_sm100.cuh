@@ -20,7 +20,7 @@
 //
 // Warp roles (416 threads): warp 0 = A producer, warp 10 = B producer, warp 1 = TMEM allocator + MMA issuer (one elected
 // lane each), warps 2..5 / 6..9 = epilogue groups 0 / 1 (TMEM lane quarter = warp_idx & 3), warps 11 / 12 = the store warps
-// of the groups (every TMA store and residual prefetch).  Accumulators are 2 (BN >= 128) or 4 (BN <= 64) TMEM stages deep.
+// of the groups (every TMA store and residual prefetch).  Accumulators are 2 (BN = 256) or 4 (BN <= 128) TMEM stages deep.
 // Persistent: grid = min(#tiles, #SMs); tiles are strided by gridDim.x.  CTA2 = true: two CTAs of a cluster share one
 // 256-row tile (cta_group::2), each staging its own 128 rows of A and half of the B tile.
 //
@@ -35,7 +35,9 @@
 //     (in place: each thread reads and rewrites its own 64-byte row),
 //   * layers whose compute-domain rows ARE rows of the padded output (every layer but the stem) store the chunk with one
 //     TMA store per output (halo rows are stored as zeros, which keeps the padding invariant),
-//   * the other output forms (4-phase, 2x up-sample) are written from the staged chunk with 4 threads per 64-byte row.
+//   * the 4-phase form a stride-2 consumer reads leaves by TMA too, through a 5-D view of the phase planes (one box per image row
+//     the tile touches, OutDesc::tma == 2); only narrow rows (< 32 pixels) and the 2x up-sampled form are written from the staged
+//     chunk with 4 threads per 64-byte row.
 // Two groups either split every tile by columns (short drain) or alternate tiles (per-tile set-up amortised).
 //
 // Layers are chained with programmatic dependent launch; where producer and consumer share a geometry the kernel boundary
