@@ -101,3 +101,19 @@ def test_reference_config_schema_loads():
     assert fd._stream.size == 40675942
     with pytest.raises(FileNotFoundError):           # train() reads raw_data_path/training.csv like the reference (:82)
         fd.train(device="cpu")
+
+
+def test_facedetector_letterbox_geometry_follows_reference():
+    """FaceDetector._letterbox_geom (what the file loop hands to fvy_letterbox_u8) = the reference's arithmetic
+    (face_detection.py:664-688), restated in oracle/letterbox.py and pinned there on the reference's own loop."""
+    from face_vijnana_yolov3_b200.space.face_detection import FaceDetector
+    from oracle import letterbox as LB
+    fd = FaceDetector.__new__(FaceDetector)
+    rng = np.random.default_rng(2)
+    for size in (416, 608):
+        fd.nn_arch = {"image_size": size, "bb_info_c_size": 6}
+        for _ in range(200):
+            w, h = int(rng.integers(16, 3000)), int(rng.integers(16, 3000))
+            w_p, h_p, pad_t, pad_b, pad_l, pad_r = LB.geometry(w, h, size)
+            assert fd._letterbox_geom(w, h) == (w_p, h_p, pad_t, pad_l)
+            assert pad_t + h_p + pad_b == size and pad_l + w_p + pad_r == size
