@@ -13,6 +13,7 @@
 // IoU is int64 arithmetic followed by one correctly rounded double divide, exactly the
 // reference's `float(intersect) / union`.
 #pragma once
+#include <climits>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -315,6 +316,21 @@ __device__ __forceinline__ bool iou_ge_fast(const int4 a, long long area_a, floa
     if (x < __dmul_rn(t, 1.0 - 0x1p-51)) return false;
     return __ddiv_rn(x, u) >= th;
 }
+// The same pre-filter on float copies of the boxes (no int -> float conversions, one fused disjointness test) for tiles whose
+// coordinates are all below 2^23 in magnitude: every coordinate, every width / height and hence every decision is exactly the
+// one iou_ge_fast takes.  0 = below the band, 1 = above, 2 = inside the 1 % band (the caller runs the exact int64 / fp64 test).
+__device__ __forceinline__ int iou_prefilter_f(const float4 a, float area_a_f, const float4 b, float area_b_f, float th_lo, float th_hi) {
+    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    if (iw <= 0.f || ih <= 0.f) return 0;           // disjoint or touching (well-formed boxes): IoU 0 < th
+    const float xf = iw * ih;
+    const float uf = area_a_f + area_b_f - xf;
+    if (uf > 0.f && area_a_f < 1e30f && area_b_f < 1e30f) {
+        if (xf < th_lo * uf) return 0;
+        if (xf > th_hi * uf) return 1;
+    }
+    return 2;
+}
 __global__ void bbox_iou_kernel(const int4* a, const int4* b, int n, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -403,10 +419,11 @@ struct MaskArgs {
 // produces the 64-bit word of column block c (bit j set <=> IoU(row, c*64+j) >= th and c*64+j > row).
 __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
     __shared__ int4 cbox[64];
+    __shared__ float4 cboxf[64];
     __shared__ long long carea[64];
     __shared__ float careaf[64];
     __shared__ int tile_prefix[1025];   // batch <= 1024
-    __shared__ int all_wellformed;
+    __shared__ int all_wellformed, all_small;
     for (int b = threadIdx.x; b < a.batch; b += blockDim.x) {
         const int n = min(a.counts[b], a.seg_stride);
         const int nb = (n + 63) >> 6;
@@ -436,9 +453,17 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
         cbox[threadIdx.x] = cb;
         carea[threadIdx.x] = ((long long)cb.z - cb.x) * ((long long)cb.w - cb.y);
         careaf[threadIdx.x] = (float)carea[threadIdx.x];
-        all_wellformed = 1;
+        cboxf[threadIdx.x] = make_float4((float)cb.x, (float)cb.y, (float)cb.z, (float)cb.w);
+        all_wellformed = 1; all_small = 1;
         __syncthreads();
         if (cb.z < cb.x || cb.w < cb.y || me.z < me.x || me.w < me.y) all_wellformed = 0;
+        {
+            constexpr int kLim = 1 << 23;       // float copies and their differences stay exact
+            const int m = max(max(max(abs(cb.x), abs(cb.y)), max(abs(cb.z), abs(cb.w))), max(max(abs(me.x), abs(me.y)), max(abs(me.z), abs(me.w))));
+            if (m >= kLim || cb.x == INT_MIN || cb.y == INT_MIN || cb.z == INT_MIN || cb.w == INT_MIN || me.x == INT_MIN || me.y == INT_MIN ||
+                me.z == INT_MIN || me.w == INT_MIN)
+                all_small = 0;
+        }
         __syncthreads();
         if (row < n) {
             unsigned long long word = 0;
@@ -449,6 +474,14 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
                 const float my_area_f = (float)my_area;
                 // thresholds of the float pre-filter: 1 % either side (th in (0, 1]: the margin dwarfs the float rounding)
                 const float th_lo = (float)(a.th * 0.99), th_hi = (float)(a.th * 1.01);
+                if (all_small) {
+                    const float4 mef = make_float4((float)me.x, (float)me.y, (float)me.z, (float)me.w);
+                    for (int j = j0; j < jmax; ++j) {
+                        int d = iou_prefilter_f(mef, my_area_f, cboxf[j], careaf[j], th_lo, th_hi);
+                        if (d == 2) d = iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi) ? 1 : 0;
+                        if (d) word |= 1ull << j;
+                    }
+                } else
                 for (int j = j0; j < jmax; ++j)
                     if (iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi)) word |= 1ull << j;
             } else {
