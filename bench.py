@@ -111,7 +111,7 @@ def run_reference(args, rank):
         dt, _ = cpu_reference_pass(sample, args.size, s, threads)
         t += dt
     v = sample * args.steps / t
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC.replace("@416", f"@{args.size}"), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"YOLOv3 face detector (nb_class=1) inference batch {args.batch} @{args.size}x{args.size}: forward+decode_netout+do_nms",
@@ -291,7 +291,7 @@ def main():
                         "sample": f"{n} images of the same workload (torch-CPU fp32 restatement of the Keras graph + C restatement of decode/NMS), {dt:.1f} s"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC.replace("@416", f"@{args.size}"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": f"YOLOv3 face detector (nb_class=1, 18-ch heads) inference batch {B} @{S}x{S} per GPU: forward+decode_netout+correct_yolo_boxes+do_nms",
