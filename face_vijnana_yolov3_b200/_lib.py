@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("FVY_LIB_PATH") or os.path.join(_HERE, "libfvy.so")   
 FVY_OK = 0
 FVY_E_INVALID, FVY_E_CUDA, FVY_E_STATE, FVY_E_CAPACITY, FVY_E_RANGE = -1, -2, -3, -4, -5
 HEAD_YOLO3, HEAD_FD6, HEAD_NONE = 0, 1, 2
-F32, F64 = 0, 1
+F32, F64, U8 = 0, 1, 2
 ARITH_F64, ARITH_F32 = 0, 1
 ANCHOR_MASK_REFERENCE = 0x0AA   # src/space/yolov3_detect.py:354-362
 ANCHOR_MASK_ALL = 0x1FF

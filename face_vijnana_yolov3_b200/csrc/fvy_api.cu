@@ -438,6 +438,9 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
 // two copies) - no block-wide barrier at all.  stem_rows_kernel spent 35 % of its stall samples in the two-row barrier; here a
 // warp only ever waits for its own loads (two rows ahead, in registers while the current row is computed), and 24 independent
 // warps per SM hide each other's latency.  The (image, strip, row) space is cut into one equal piece per resident warp.  Halo columns are re-read by the neighbouring strip (12 %, L1 / L2 hits).
+__device__ __forceinline__ float stem_px(float v) { return v; }
+__device__ __forceinline__ float stem_px(double v) { return (float)v; }                         // Keras casts its input to float32
+__device__ __forceinline__ float stem_px(unsigned char v) { return (float)((double)v / 255.0); }   // image / 255 in float64, then that cast
 constexpr int kStripWarps = 8;
 constexpr int kStripLen = 64;          // staged elements per row copy: 18 pixels x 3 channels = 54, padded
 #ifndef FVY_STRIP_MINB
@@ -497,8 +500,8 @@ stem_strip_kernel(const T* __restrict__ img, int batch, int H, int W, int nmax, 
     auto fetch = [&](int hh, float& a, float& b) {
         const bool in = hh >= 0 && hh < H;
         const T* src = base + (long long)(in ? hh : 0) * W * 3;
-        a = (in && ok0) ? (float)__ldg(src + c0) : 0.f;
-        b = (in && ok1) ? (float)__ldg(src + c1) : 0.f;
+        a = (in && ok0) ? stem_px(__ldg(src + c0)) : 0.f;
+        b = (in && ok1) ? stem_px(__ldg(src + c1)) : 0.f;
     };
     auto stage = [&](int hh, float a, float b) {
         uint16_t* E = srows[wib][hh & 7][0];
@@ -1249,7 +1252,7 @@ static int build_post(fvy_handle* h) {
 
 // ------------------------------------------------------------------------------------------ forward
 static int stage_input(fvy_handle* h, const void* images, int dtype, int batch, const void** dev_images) {
-    const size_t es = dtype == FVY_F64 ? 8 : 4;
+    const size_t es = dtype == FVY_F64 ? 8 : (dtype == FVY_U8 ? 1 : 4);
     const size_t bytes = (size_t)batch * h->cfg.net_h * h->cfg.net_w * 3 * es;
     h->last_slot = -1;
     if (is_device_ptr(images)) { *dev_images = images; return FVY_OK; }
@@ -1304,6 +1307,9 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
                 if (h->cur_dtype == FVY_F32)
                     stem_strip_kernel<float><<<blocks, kStripWarps * 32, 0, h->stream>>>((const float*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
                                                                                          h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
+                else if (h->cur_dtype == FVY_U8)
+                    stem_strip_kernel<unsigned char><<<blocks, kStripWarps * 32, 0, h->stream>>>((const unsigned char*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w,
+                                                                                                 h->cfg.max_batch, h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
                 else
                     stem_strip_kernel<double><<<blocks, kStripWarps * 32, 0, h->stream>>>((const double*)h->cur_img, batch, h->cfg.net_h, h->cfg.net_w, h->cfg.max_batch,
                                                                                           h->d_stem_w2, L.bias, (__nv_bfloat16*)L.p.out[0].ptr);
@@ -1389,7 +1395,9 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
 static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int batch) {
     if (!h->weights_loaded) return fail(FVY_E_STATE, "fvy_forward before fvy_load_weights");
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
-    if (dtype != FVY_F32 && dtype != FVY_F64) return fail(FVY_E_INVALID, "dtype %d", dtype);
+    if (dtype != FVY_F32 && dtype != FVY_F64 && dtype != FVY_U8) return fail(FVY_E_INVALID, "dtype %d", dtype);
+    if (dtype == FVY_U8 && !(h->fused_stem && h->stem_mode == 3))
+        return fail(FVY_E_INVALID, "uint8 images need the strip stem (FVY_STEM=3, network width a multiple of 16)");
     const void* dimg = nullptr;
     if (int e = stage_input(h, images, dtype, batch, &dimg)) return e;
     h->cur_img = dimg; h->cur_dtype = dtype;

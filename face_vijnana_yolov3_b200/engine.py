@@ -125,13 +125,15 @@ class Engine:
                 dtype = L.F32
             elif images.dtype == np.float64:
                 dtype = L.F64
+            elif images.dtype == np.uint8:
+                dtype = L.U8
             else:
-                raise TypeError("images must be float32 or float64 in [0,1]")
+                raise TypeError("images must be float32 / float64 in [0,1] or uint8 in 0..255")
         else:
             s = str(images.dtype)
-            dtype = L.F32 if s.endswith("float32") else L.F64 if s.endswith("float64") else None
+            dtype = L.F32 if s.endswith("float32") else L.F64 if s.endswith("float64") else L.U8 if s.endswith("uint8") else None
             if dtype is None:
-                raise TypeError("images must be float32 or float64 in [0,1]")
+                raise TypeError("images must be float32 / float64 in [0,1] or uint8 in 0..255")
         return dtype, int(shape[0])
 
     # ---------------------------------------------------------------- decode_netout + correct_yolo_boxes (yolov3_detect.py:335-404)

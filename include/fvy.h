@@ -38,7 +38,10 @@ typedef enum {
 } fvy_status;
 
 enum { FVY_HEAD_YOLO3 = 0, FVY_HEAD_FD6 = 1, FVY_HEAD_NONE = 2 };   /* NONE: post-processing only */
-enum { FVY_F32 = 0, FVY_F64 = 1 };                                 /* dtype of the image tensor */
+enum { FVY_F32 = 0, FVY_F64 = 1, FVY_U8 = 2 };                      /* dtype of the image tensor */
+/* FVY_U8: uint8 pixels 0..255 as imread returns them; the device forms float32(pixel / 255.0 evaluated in float64), i.e. the value
+ * `image / 255` (face_detection.py:660, :800) has after Keras casts its input to float32 - same logits, a quarter of the float32
+ * bytes on the host-to-device path. */
 enum { FVY_ARITH_F64 = 0, FVY_ARITH_F32 = 1 };                     /* decode scalar arithmetic (see fvy_decode) */
 
 /* The fork's anchor mask in decode_netout (src/space/yolov3_detect.py:354-362): bit (3*scale+b). */
@@ -94,7 +97,7 @@ int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats);
 long long fvy_weight_count(const fvy_handle* h);
 
 /* Forward.  Replaces Model.predict (yolov3_detect.py:593, face_detection.py:899).
- *   images: (batch, net_h, net_w, 3) NHWC, dtype FVY_F32 / FVY_F64, values in [0,1].
+ *   images: (batch, net_h, net_w, 3) NHWC, dtype FVY_F32 / FVY_F64, values in [0,1] (or FVY_U8, values 0..255).
  *   out0/out1/out2: yolo3 -> (batch, H/32, W/32, C), (batch, H/16, W/16, C), (batch, H/8, W/8, C) fp32;
  *                   fd6   -> out0 = (batch, H/32, W/32, bb_info_c_size), out1 = out2 = NULL.
  *   Any out pointer may be NULL: the logits then stay in the handle for fvy_postprocess. */

@@ -318,6 +318,17 @@ def test_capacity_error():
     eng.close()
 
 
+def test_uint8_images_equal_image_over_255(yolo_engine):
+    """FVY_U8 input: the device forms float32(pixel / 255.0 in float64), so the logits equal those of `image / 255` (float64) bit for bit."""
+    rng = np.random.default_rng(12)
+    x8 = rng.integers(0, 256, (2, 416, 416, 3), dtype=np.uint8)
+    yolo_engine.load_weights(synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT))
+    a = yolo_engine.forward(x8)
+    b = yolo_engine.forward(x8 / 255)
+    for p, q in zip(a, b):
+        assert np.array_equal(p, q)
+
+
 def test_letterbox_gpu_bit_exact_vs_oracle():
     """fvy_letterbox_u8 (image/255, cv.resize INTER_CUBIC, zero border on the GPU) equals float32(oracle) bit for bit; the oracle is
     pinned on the reference's own loop output and on cv2 (tests/test_oracle_letterbox.py)."""
