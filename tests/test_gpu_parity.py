@@ -105,6 +105,22 @@ def test_forward_608():
     eng.close()
 
 
+def test_forward_rectangular_net():
+    """A non-square network input (320 rows x 480 columns, grids 10x15 / 20x30 / 40x60): row pitches, phase planes and stem strips are
+    computed from the height and the width separately."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    rng = np.random.default_rng(6)
+    x = rng.random((2, 320, 480, 3), dtype=np.float32)
+    eng = Engine(320, 480, nb_class=1, max_batch=2)
+    eng.load_weights(stream)
+    outs = eng.forward(x)
+    ref = D.forward(stream, x, 1)
+    assert [o.shape for o in outs] == [(2, 10, 15, 18), (2, 20, 30, 18), (2, 40, 60, 18)]
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) <= HEAD_TOL
+    eng.close()
+
+
 def test_forward_requires_weights_and_valid_batch():
     eng = Engine(416, 416, nb_class=1, max_batch=1)
     with pytest.raises(L.FvyError):
