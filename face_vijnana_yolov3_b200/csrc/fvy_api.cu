@@ -1568,7 +1568,8 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
         SweepArgs w;
         w.mask = h->d_mask; w.order = h->d_order; w.counts = d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
         w.nb_class = nb_class; w.cls = c; w.classes = d_cls; w.rowflag = h->d_rowflag;
-        nms_sweep_kernel<<<batch, 1024, (size_t)h->words * 8, h->ps>>>(w);
+        static const int sweep_threads = [] { const char* v = getenv("FVY_SWEEP_THREADS"); const int t = v && *v ? atoi(v) : 1024; return t >= 128 && t <= 1024 && t % 32 == 0 ? t : 1024; }();
+        nms_sweep_kernel<<<batch, sweep_threads, (size_t)h->words * 8, h->ps>>>(w);
         CUDA_TRY(cudaGetLastError());
         h->launches += 3;
     }
