@@ -475,11 +475,33 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
                 // thresholds of the float pre-filter: 1 % either side (th in (0, 1]: the margin dwarfs the float rounding)
                 const float th_lo = (float)(a.th * 0.99), th_hi = (float)(a.th * 1.01);
                 if (all_small) {
+                    // branch-free over all 64 columns (constant shifts, no loop-carried control flow): the same decisions as
+                    // iou_prefilter_f, collected as two bit sets - "at or above the threshold" and "inside the 1 % band" - and masked to
+                    // the valid columns afterwards; the rare band bits then take the exact int64 / fp64 test one by one
                     const float4 mef = make_float4((float)me.x, (float)me.y, (float)me.z, (float)me.w);
-                    for (int j = j0; j < jmax; ++j) {
-                        int d = iou_prefilter_f(mef, my_area_f, cboxf[j], careaf[j], th_lo, th_hi);
-                        if (d == 2) d = iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi) ? 1 : 0;
-                        if (d) word |= 1ull << j;
+                    const bool my_ok = my_area_f < 1e30f;
+                    unsigned long long yes = 0, band = 0;
+#pragma unroll 16
+                    for (int j = 0; j < 64; ++j) {
+                        const float4 b = cboxf[j];
+                        const float ab = careaf[j];
+                        const float iw = fminf(mef.z, b.z) - fmaxf(mef.x, b.x);
+                        const float ih = fminf(mef.w, b.w) - fmaxf(mef.y, b.y);
+                        const float xf = iw * ih;
+                        const float uf = my_area_f + ab - xf;
+                        const bool pos = iw > 0.f && ih > 0.f;
+                        const bool ok = uf > 0.f && my_ok && ab < 1e30f;
+                        const bool above = xf > th_hi * uf, below = xf < th_lo * uf;
+                        yes |= (unsigned long long)(pos && ok && above && !below) << j;
+                        band |= (unsigned long long)(pos && !(ok && (above || below))) << j;
+                    }
+                    const unsigned long long upto = jmax >= 64 ? ~0ull : ((1ull << jmax) - 1ull);
+                    const unsigned long long from = j0 >= 64 ? 0ull : ~((1ull << j0) - 1ull);
+                    const unsigned long long valid = upto & from;
+                    word = yes & valid;
+                    for (unsigned long long todo = band & valid; todo; todo &= todo - 1) {
+                        const int j = __ffsll((long long)todo) - 1;
+                        if (iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi)) word |= 1ull << j;
                     }
                 } else
                 for (int j = j0; j < jmax; ++j)
