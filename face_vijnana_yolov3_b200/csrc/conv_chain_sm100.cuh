@@ -42,8 +42,46 @@ __device__ __forceinline__ void chain_mma_tap(uint32_t tmem_d, uint64_t da, uint
     }
 }
 
+// The sequence of (layer, tile) work items of one CTA pair.  Two sources: the static rotation (tile = (pair + rot) % n_pairs,
+// + n_pairs, ... layer after layer) or a schedule table written by the host (FVY_CHAIN_SCHED=1: a list schedule over the known
+// tile durations and row dependencies; entries (layer << 20) | tile, layer-monotonic per pair - which is what keeps the chain
+// deadlock-free: a pair only ever waits for items that precede its own in every other pair's list - terminated by -1).
+// Every role of a CTA walks the same sequence with its own copy of this cursor.
+struct ChainWalk {
+    const ChainLayer* chain;
+    const int* sched;
+    int n_layers, n_pairs, pair, i, li, tile;
+    __device__ __forceinline__ ChainWalk(const ChainLayer* c, int nl, int np, int p, const int* s, int stride)
+        : chain(c), sched(s != nullptr ? s + (size_t)p * stride : nullptr), n_layers(nl), n_pairs(np), pair(p), i(0), li(-1), tile(-1) {}
+    __device__ __forceinline__ int tiles_of(int l) const {
+        const ConvParams& p = chain[l].p;
+        return ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    }
+    __device__ __forceinline__ bool next() {
+        if (sched != nullptr) {
+            const int e = __ldg(sched + i);
+            ++i;
+            if (e < 0) return false;
+            li = e >> 20; tile = e & 0xFFFFF;
+            return true;
+        }
+        if (li < 0) {
+            if (n_layers <= 0) return false;
+            li = 0; tile = (pair + chain[0].rot) % n_pairs;
+        } else {
+            tile += n_pairs;
+        }
+        while (tile >= tiles_of(li)) {
+            if (++li >= n_layers) return false;
+            tile = (pair + chain[li].rot) % n_pairs;
+        }
+        return true;
+    }
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
-conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, const int nb, const int a_stages, const int b_stages) {
+conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, const int nb, const int a_stages, const int b_stages,
+                  const int* __restrict__ sched, const int sched_stride) {
     constexpr int BN = kChainBN, BK = kChainBK;
     constexpr int kAcc = 2;
     constexpr uint32_t kTmemCols = kAcc * BN;
@@ -101,33 +139,36 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
         if (elect_one()) {
             int as_ = 0; uint32_t aph = 0;
             const bool arrives = cta_rank == 0;
-            for (int li = 0; li < n_layers; ++li) {
-                const ChainLayer& L = chain[li];
-                const ConvParams& p = L.p;
-                const int nnt = p.num_n_tiles, gt = p.gt, kcn = p.k_chunks, ntaps = p.num_taps, a_choff = p.a_choff;
-                const bool slab = p.a_slab != 0;
-                const int num_tiles = ((p.num_m_tiles + 1) / 2) * nnt;
-                const uint32_t tx = 2u * (uint32_t)(slab ? kSlabBytes : kABytes);
-                const int* wflags = p.wait_flags;
-                const int wexp = p.wait_expected, wmargin = p.wait_margin, wblocks = p.wait_blocks;
-                int toff[9];
+            ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
+            int cur = -1, nnt = 1, gt = 1, kcn = 1, ntaps = 1, a_choff = 0, wexp = 0, wmargin = 0, wblocks = 0, dep_ready = -1;
+            uint32_t tx = 0;
+            const int* wflags = nullptr;
+            const ChainLayer* L = chain;
+            int toff[9];
+            while (w.next()) {
+                if (w.li != cur) {
+                    cur = w.li; L = chain + cur;
+                    const ConvParams& p = L->p;
+                    nnt = p.num_n_tiles; gt = p.gt; kcn = p.k_chunks; ntaps = p.num_taps; a_choff = p.a_choff;
+                    tx = 2u * (uint32_t)(p.a_slab != 0 ? kSlabBytes : kABytes);
+                    wflags = p.wait_flags; wexp = p.wait_expected; wmargin = p.wait_margin; wblocks = p.wait_blocks;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) toff[i] = p.tap_off[i];
-                tma_prefetch_desc(&L.tmap_a);
-                int dep_ready = -1;
-                for (int tile = (pair + L.rot) % n_pairs; tile < num_tiles; tile += n_pairs) {
-                    const int m0 = (tile / nnt) * kTileM + (int)cta_rank * kBlockM;
-                    if (wflags != nullptr)
-                        wait_blocks_ready(wflags, wexp, max(0, (m0 - wmargin) >> 7), min(wblocks - 1, (m0 + kBlockM - 1 + wmargin) >> 7), dep_ready);
-                    for (int tap0 = 0; tap0 < ntaps; tap0 += gt)
-                        for (int kc = 0; kc < kcn; ++kc) {
-                            // slab: one box serves the gt column taps; 1x1: one 128-row tile per K chunk
-                            mbar_wait(&a_empty[as_], aph ^ 1, true);
-                            if (arrives) mbar_expect_tx(&a_full[as_], tx);
-                            tma_load_2d_pair(a_ring + as_ * kSlabBytes, &L.tmap_a, &a_full[as_], a_choff + kc * BK, m0 + toff[tap0]);
-                            if (++as_ == a_stages) { as_ = 0; aph ^= 1; }
-                        }
+                    for (int i = 0; i < 9; ++i) toff[i] = p.tap_off[i];
+                    tma_prefetch_desc(&L->tmap_a);
+                    dep_ready = -1;
                 }
+                const int tile = w.tile;
+                const int m0 = (tile / nnt) * kTileM + (int)cta_rank * kBlockM;
+                if (wflags != nullptr)
+                    wait_blocks_ready(wflags, wexp, max(0, (m0 - wmargin) >> 7), min(wblocks - 1, (m0 + kBlockM - 1 + wmargin) >> 7), dep_ready);
+                for (int tap0 = 0; tap0 < ntaps; tap0 += gt)
+                    for (int kc = 0; kc < kcn; ++kc) {
+                        // slab: one box serves the gt column taps; 1x1: one 128-row tile per K chunk
+                        mbar_wait(&a_empty[as_], aph ^ 1, true);
+                        if (arrives) mbar_expect_tx(&a_full[as_], tx);
+                        tma_load_2d_pair(a_ring + as_ * kSlabBytes, &L->tmap_a, &a_full[as_], a_choff + kc * BK, m0 + toff[tap0]);
+                        if (++as_ == a_stages) { as_ = 0; aph ^= 1; }
+                    }
             }
         }
     } else if (warp == kBProducerWarp) {
@@ -135,22 +176,24 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
         if (elect_one()) {
             int bs = 0; uint32_t bph = 0;
             const bool arrives = cta_rank == 0;
-            for (int li = 0; li < n_layers; ++li) {
-                const ChainLayer& L = chain[li];
-                const ConvParams& p = L.p;
-                const int nnt = p.num_n_tiles, gt = p.gt, kcn = p.k_chunks, ntaps = p.num_taps;
-                const int num_tiles = ((p.num_m_tiles + 1) / 2) * nnt;
-                for (int tile = (pair + L.rot) % n_pairs; tile < num_tiles; tile += n_pairs) {
-                    const int n0 = (tile % nnt) * BN + (int)cta_rank * (BN / 2);
-                    for (int tap0 = 0; tap0 < ntaps; tap0 += gt)
-                        for (int kc = 0; kc < kcn; ++kc)
-                            for (int t = 0; t < gt; ++t) {
-                                mbar_wait(&b_empty[bs], bph ^ 1, true);
-                                if (arrives) mbar_expect_tx(&b_full[bs], 2u * kBBytes);
-                                tma_load_2d_pair(b_ring + bs * kBBytes, &L.tmap_b, &b_full[bs], ((tap0 + t) * kcn + kc) * BK, n0);
-                                if (++bs == b_stages) { bs = 0; bph ^= 1; }
-                            }
+            ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
+            int cur = -1, nnt = 1, gt = 1, kcn = 1, ntaps = 1;
+            const ChainLayer* L = chain;
+            while (w.next()) {
+                if (w.li != cur) {
+                    cur = w.li; L = chain + cur;
+                    const ConvParams& p = L->p;
+                    nnt = p.num_n_tiles; gt = p.gt; kcn = p.k_chunks; ntaps = p.num_taps;
                 }
+                const int n0 = (w.tile % nnt) * BN + (int)cta_rank * (BN / 2);
+                for (int tap0 = 0; tap0 < ntaps; tap0 += gt)
+                    for (int kc = 0; kc < kcn; ++kc)
+                        for (int t = 0; t < gt; ++t) {
+                            mbar_wait(&b_empty[bs], bph ^ 1, true);
+                            if (arrives) mbar_expect_tx(&b_full[bs], 2u * kBBytes);
+                            tma_load_2d_pair(b_ring + bs * kBBytes, &L->tmap_b, &b_full[bs], ((tap0 + t) * kcn + kc) * BK, n0);
+                            if (++bs == b_stages) { bs = 0; bph ^= 1; }
+                        }
             }
         }
     } else if (warp == 1) {
@@ -161,33 +204,33 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
             const uint64_t desc_hi = make_smem_desc<BK>(0);
             const uint32_t a_ring16 = (smem_u32(a_ring) & 0x3FFFF) >> 4, b_ring16 = (smem_u32(b_ring) & 0x3FFFF) >> 4;
             constexpr uint32_t a_slot16 = (uint32_t)kSlabBytes >> 4, b_slot16 = (uint32_t)kBBytes >> 4, row16 = (uint32_t)kRowBytes >> 4;
-            for (int li = 0; li < n_layers; ++li) {
-                const ChainLayer& L = chain[li];
-                const ConvParams& p = L.p;
-                const int gt = p.gt;
-                const int units = p.num_taps * p.k_chunks / gt;
-                const int num_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
-                for (int tile = (pair + L.rot) % n_pairs; tile < num_tiles; tile += n_pairs) {
-                    mbar_wait(&tmem_empty[acc], acc_ph ^ 1, true);
-                    const uint32_t tmem_d = tmem_base + acc * BN;
-                    uint32_t accum = 0;
-#pragma unroll 1
-                    for (int u = 0; u < units; ++u) {
-                        mbar_wait(&a_full[as_], aph, true);
-                        const uint64_t da0 = desc_hi | (uint64_t)(a_ring16 + (uint32_t)as_ * a_slot16);
-                        for (int t = 0; t < gt; ++t) {       // gt = 3: the slab read t rows further; gt = 1: the tile
-                            mbar_wait(&b_full[bs], bph, true);
-                            tc_fence_after();
-                            chain_mma_tap(tmem_d, da0 + (uint32_t)t * row16, desc_hi | (uint64_t)(b_ring16 + (uint32_t)bs * b_slot16), kIdesc, accum);
-                            umma_commit_pair(&b_empty[bs]);
-                            if (++bs == b_stages) { bs = 0; bph ^= 1; }
-                        }
-                        umma_commit_pair(&a_empty[as_]);
-                        if (++as_ == a_stages) { as_ = 0; aph ^= 1; }
-                    }
-                    umma_commit_pair(&tmem_full[acc]);
-                    if (++acc == kAcc) { acc = 0; acc_ph ^= 1; }
+            ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
+            int cur = -1, gt = 1, units = 1;
+            while (w.next()) {
+                if (w.li != cur) {
+                    cur = w.li;
+                    const ConvParams& p = chain[cur].p;
+                    gt = p.gt; units = p.num_taps * p.k_chunks / gt;
                 }
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1, true);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                uint32_t accum = 0;
+#pragma unroll 1
+                for (int u = 0; u < units; ++u) {
+                    mbar_wait(&a_full[as_], aph, true);
+                    const uint64_t da0 = desc_hi | (uint64_t)(a_ring16 + (uint32_t)as_ * a_slot16);
+                    for (int t = 0; t < gt; ++t) {       // gt = 3: the slab read t rows further; gt = 1: the tile
+                        mbar_wait(&b_full[bs], bph, true);
+                        tc_fence_after();
+                        chain_mma_tap(tmem_d, da0 + (uint32_t)t * row16, desc_hi | (uint64_t)(b_ring16 + (uint32_t)bs * b_slot16), kIdesc, accum);
+                        umma_commit_pair(&b_empty[bs]);
+                        if (++bs == b_stages) { bs = 0; bph ^= 1; }
+                    }
+                    umma_commit_pair(&a_empty[as_]);
+                    if (++as_ == a_stages) { as_ = 0; aph ^= 1; }
+                }
+                umma_commit_pair(&tmem_full[acc]);
+                if (++acc == kAcc) { acc = 0; acc_ph ^= 1; }
             }
         }
     } else if (warp < 10) {
@@ -206,17 +249,23 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
         const int m_rank_off = (int)cta_rank * kBlockM;
         int buf = 0; uint32_t buf_ph = 0;
         int acc = 0; uint32_t acc_ph = 0;
-        for (int li = 0; li < n_layers; ++li) {
-            const ChainLayer& L = chain[li];
-            const ConvParams& p = L.p;
-            const int nnt = p.num_n_tiles;
-            const bool has_res = p.res != nullptr, leaky = p.leaky != 0;
-            const int num_tiles = ((p.num_m_tiles + 1) / 2) * nnt;
-            // this layer's bias: the group's own copy (its previous contents were last read in the group's previous tile)
-            named_bar_sync(bar_id, kEpiThreads);
-            for (int i = et; i < nnt * BN; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
-            named_bar_sync(bar_id, kEpiThreads);
-            for (int tile = (pair + L.rot) % n_pairs; tile < num_tiles; tile += n_pairs) {
+        ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
+        int cur = -1, nnt = 1;
+        bool has_res = false, leaky = false;
+        const ConvParams* pp = &chain[0].p;
+        while (w.next()) {
+            if (w.li != cur) {
+                cur = w.li;
+                pp = &chain[cur].p;
+                nnt = pp->num_n_tiles; has_res = pp->res != nullptr; leaky = pp->leaky != 0;
+                // this layer's bias: the group's own copy (its previous contents were last read in the group's previous tile)
+                named_bar_sync(bar_id, kEpiThreads);
+                for (int i = et; i < nnt * BN; i += kEpiThreads) sbias[i] = __ldg(pp->bias + i);
+                named_bar_sync(bar_id, kEpiThreads);
+            }
+            const ConvParams& p = *pp;
+            {
+                const int tile = w.tile;
                 const int mt = tile / nnt;
                 const int m0 = mt * kTileM + m_rank_off;
                 const int m = m0 + r;
@@ -309,33 +358,29 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
             // A buffer whose residual rows are not complete yet stays OWED (`pending`) and is retried: the store warp must never
             // block here, or two pairs that wait for each other's rows of an earlier layer would both stop storing the tiles
             // the other one needs.
-            int pl = 0, ptile = -1, pchunk = g, pbuf = 0, pdep = -1, pending = 0;
+            ChainWalk pw(chain, n_layers, n_pairs, pair, sched, sched_stride);
+            bool p_has = pw.next();
+            int p_cur = -1, pchunk = g, pbuf = 0, pdep = -1, pending = 0;
             auto try_prepare = [&]() -> bool {
-                for (;;) {
-                    if (pl >= n_layers) { if (++pbuf == nb) pbuf = 0; return true; }      // past the end: nothing to prepare
-                    const ChainLayer& L = chain[pl];
-                    const int num_tiles = ((L.p.num_m_tiles + 1) / 2) * L.p.num_n_tiles;
-                    if (ptile < 0) { ptile = (pair + L.rot) % n_pairs; pdep = -1; }
-                    if (ptile >= num_tiles) { ++pl; ptile = -1; continue; }               // this pair has no (more) tiles in the layer
-                    break;
-                }
-                const ChainLayer& L = chain[pl];
+                if (!p_has) { if (++pbuf == nb) pbuf = 0; return true; }      // past the end: nothing to prepare
+                const ChainLayer& L = chain[pw.li];
                 const ConvParams& p = L.p;
+                if (pw.li != p_cur) { p_cur = pw.li; pdep = -1; }
                 if (p.res != nullptr) {
-                    const int rm0 = (ptile / p.num_n_tiles) * kTileM + m_rank_off;
+                    const int rm0 = (pw.tile / p.num_n_tiles) * kTileM + m_rank_off;
                     if (L.res_flags != nullptr &&
                         !blocks_ready_now(L.res_flags, L.res_expected, rm0 >> 7, min(L.res_blocks - 1, (rm0 + kBlockM - 1) >> 7), pdep))
                         return false;
                     mbar_expect_tx(&ready[pbuf], kChunkBytes);
                     tma_load_2d(ring + pbuf * kChunkBytes, &L.tmap_res, &ready[pbuf],
-                                p.res_choff + (ptile % p.num_n_tiles) * BN + pchunk * 32, rm0);
+                                p.res_choff + (pw.tile % p.num_n_tiles) * BN + pchunk * 32, rm0);
                 } else {
                     mbar_arrive(&ready[pbuf]);
                 }
                 if (++pbuf == nb) pbuf = 0;
                 if ((pchunk += 2) >= kChunks) {
                     pchunk = g;
-                    ptile += n_pairs;
+                    p_has = pw.next();
                 }
                 return true;
             };
@@ -343,15 +388,22 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
             pending = nb;                                              // every buffer starts free
             service_pending();
             int buf = 0, prev = -1; uint32_t sph = 0;
-            for (int li = 0; li < n_layers; ++li) {
-                const ChainLayer& L = chain[li];
-                const ConvParams& p = L.p;
-                const int nnt = p.num_n_tiles;
-                const int num_tiles = ((p.num_m_tiles + 1) / 2) * nnt;
-                const bool o0 = p.out[0].tma != 0, o1 = p.out[1].tma != 0;
-                const int ch0 = p.out[0].choff, ch1 = p.out[1].choff;
-                int* sig = p.sig_flags;
-                for (int tile = (pair + L.rot) % n_pairs; tile < num_tiles; tile += n_pairs) {
+            ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
+            int cur = -1, nnt = 1, ch0 = 0, ch1 = 0;
+            bool o0 = false, o1 = false;
+            int* sig = nullptr;
+            const ChainLayer* L = chain;
+            while (w.next()) {
+                if (w.li != cur) {
+                    cur = w.li; L = chain + cur;
+                    const ConvParams& p = L->p;
+                    nnt = p.num_n_tiles;
+                    o0 = p.out[0].tma != 0; o1 = p.out[1].tma != 0;
+                    ch0 = p.out[0].choff; ch1 = p.out[1].choff;
+                    sig = p.sig_flags;
+                }
+                {
+                    const int tile = w.tile;
                     const int m0 = (tile / nnt) * kTileM + m_rank_off;
                     const int n0 = (tile % nnt) * BN;
 #pragma unroll 1
@@ -361,8 +413,8 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
                             if (spin > (1u << 24)) { printf("fvy: chain store warp timed out (block %d)\n", blockIdx.x); __trap(); }
                         }
                         const uint8_t* sbuf = ring + buf * kChunkBytes;
-                        if (o0) tma_store_2d(sbuf, &L.tmap_out0, ch0 + n0 + c * 32, m0);
-                        if (o1) tma_store_2d(sbuf, &L.tmap_out1, ch1 + n0 + c * 32, m0);
+                        if (o0) tma_store_2d(sbuf, &L->tmap_out0, ch0 + n0 + c * 32, m0);
+                        if (o1) tma_store_2d(sbuf, &L->tmap_out1, ch1 + n0 + c * 32, m0);
                         bulk_commit();
                         if (prev >= 0) {
                             bulk_wait_read(1);                     // the previous chunk's store has read its buffer: it is owed its next use

@@ -684,7 +684,9 @@ struct fvy_handle {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, long long> graph_launches;   // kernels captured in each graph (what one replay launches)
     bool use_graph = true, capturing = false;
-    struct Chain { int first = 0, count = 0; ChainLayer* dev = nullptr; std::vector<ChainLayer> host; };
+    struct Chain { int first = 0, count = 0; ChainLayer* dev = nullptr; std::vector<ChainLayer> host;
+                   int* d_sched = nullptr; int sched_stride = 0; std::vector<int> sched_host; };   // FVY_CHAIN_SCHED: per-pair work lists
+    bool chain_sched = false;
     std::vector<Chain> chains; bool use_chain = true; int chain_batch = -1;
     int chain_nb = 3, chain_a = 4, chain_b = 6; size_t chain_smem = 0;
     int* d_flags = nullptr; size_t flags_bytes = 0; bool use_flags = true, flags_live = false;
@@ -1102,6 +1104,7 @@ static int build_plan(fvy_handle* h) {
     // output, go out as ONE persistent launch (conv_chain_kernel)
     {
         h->use_chain = h->use_flags && env_int("FVY_CHAIN", 1) != 0;
+        h->chain_sched = env_int("FVY_CHAIN_SCHED", 0) != 0;
         auto eligible = [&](const Layer& L) {
             if (!L.cta2 || L.BN != 256 || L.BK != 64 || L.s.stride != 1 || L.s.src < 0 || !L.s.bn) return false;
             if (L.p.b_resident || L.p.b_cover != 1) return false;
@@ -1136,6 +1139,69 @@ static int build_plan(fvy_handle* h) {
             CUDA_TRY(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
+    return FVY_OK;
+}
+
+// FVY_CHAIN_SCHED=1: a list schedule of the chain's tiles instead of the static rotation.  Every tile is one item of known length
+// (taps x K chunks, all of them 256 x 256 x 64 MMAs) that becomes ready when the row blocks of the previous layer its taps reach
+// (and the residual rows) are complete; layers are taken in order and, inside a layer, tiles in ascending order, each going to the
+// pair that can start it first.  Per pair the list is layer-monotonic, so a pair only ever waits for items that precede its own
+// in the other pairs' lists: no cycle.  Times are in units of one tap; `load` and `drain` model the first-operand latency and the
+// epilogue + store + counter visibility of a finished tile.
+static int schedule_chain(fvy_handle* h, fvy_handle::Chain& ch, int pairs) {
+    static const int load = [] { const char* v = getenv("FVY_SCHED_LOAD"); return v && *v ? atoi(v) : 5; }();
+    static const int drain = [] { const char* v = getenv("FVY_SCHED_DRAIN"); return v && *v ? atoi(v) : 10; }();
+    std::vector<std::vector<int>> lists(pairs);
+    std::vector<long long> free_at(pairs, 0);
+    std::vector<std::vector<long long>> done(ch.count);
+    size_t total = 0;
+    for (int k = 0; k < ch.count; ++k) {
+        const ConvParams& p = ch.host[k].p;
+        const Layer& L = h->layers[ch.first + k];
+        const int nnt = p.num_n_tiles, mt_count = (p.num_m_tiles + 1) / 2, tiles = mt_count * nnt;
+        const long long dur = (long long)p.num_taps * p.k_chunks;
+        if (tiles >= (1 << 20) || k >= (1 << 10)) return fail(FVY_E_INVALID, "chain schedule: %d tiles / layer %d do not fit the entry format", tiles, k);
+        done[k].assign(mt_count, 0);
+        int res_k = -1;
+        if (L.s.res >= 0)
+            for (int q = 0; q < k; ++q)
+                if (h->layers[ch.first + q].s.idx == L.s.res) res_k = q;
+        for (int t = 0; t < tiles; ++t) {
+            const int mt = t / nnt;
+            long long ready = 0;
+            if (k > 0) {
+                const long long m0 = (long long)mt * 2 * kBlockM, margin = p.wait_margin;
+                const int lo = (int)std::max<long long>(0, (m0 - margin) / (2 * kBlockM));
+                const int hi = (int)std::min<long long>((long long)done[k - 1].size() - 1, (m0 + 2 * kBlockM - 1 + margin) / (2 * kBlockM));
+                for (int b = lo; b <= hi; ++b) ready = std::max(ready, done[k - 1][b]);
+            }
+            if (res_k >= 0 && mt < (int)done[res_k].size()) ready = std::max(ready, done[res_k][mt]);
+            ready += load;
+            int best = 0;
+            long long best_start = -1, best_free = -1;
+            for (int q = 0; q < pairs; ++q) {
+                const long long st = std::max(free_at[q], ready);
+                if (best_start < 0 || st < best_start || (st == best_start && free_at[q] > best_free)) { best = q; best_start = st; best_free = free_at[q]; }
+            }
+            lists[best].push_back((k << 20) | t);
+            free_at[best] = best_start + dur;
+            done[k][mt] = std::max(done[k][mt], best_start + dur + drain);
+            ++total;
+        }
+    }
+    size_t longest = 0;
+    for (const auto& l : lists) longest = std::max(longest, l.size());
+    const int stride = (int)longest + 1;
+    if (ch.d_sched == nullptr || stride > ch.sched_stride) {
+        const int alloc_stride = stride + stride / 4 + 8;
+        void* pmem = nullptr;
+        if (int e = dev_alloc(h, &pmem, (size_t)pairs * alloc_stride * sizeof(int), false)) return e;
+        ch.d_sched = (int*)pmem; ch.sched_stride = alloc_stride;
+    }
+    ch.sched_host.assign((size_t)pairs * ch.sched_stride, -1);
+    for (int q = 0; q < pairs; ++q) std::copy(lists[q].begin(), lists[q].end(), ch.sched_host.begin() + (size_t)q * ch.sched_stride);
+    CUDA_TRY(cudaMemcpyAsync(ch.d_sched, ch.sched_host.data(), ch.sched_host.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    (void)total;
     return FVY_OK;
 }
 
@@ -1174,6 +1240,8 @@ static int prepare_chains(fvy_handle* h, int batch) {
             c.rot = (k * 25) % pairs;
         }
         CUDA_TRY(cudaMemcpyAsync(ch.dev, ch.host.data(), sizeof(ChainLayer) * ch.count, cudaMemcpyHostToDevice, h->stream));
+        if (h->chain_sched)
+            if (int e = schedule_chain(h, ch, pairs)) return e;
     }
     h->chain_batch = batch;
     return FVY_OK;
@@ -1194,7 +1262,8 @@ static int launch_chain(fvy_handle* h, const fvy_handle::Chain& ch) {
     at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
     ++na;
     cfg.attrs = at; cfg.numAttrs = na;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_chain_kernel, (const ChainLayer*)ch.dev, ch.count, h->chain_nb, h->chain_a, h->chain_b));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_chain_kernel, (const ChainLayer*)ch.dev, ch.count, h->chain_nb, h->chain_a, h->chain_b,
+                                (const int*)(h->chain_sched ? ch.d_sched : nullptr), ch.sched_stride));
     h->launches += 1;
     return FVY_OK;
 }
