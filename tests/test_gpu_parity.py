@@ -450,38 +450,6 @@ def test_full_size_batch_invariance_and_tile_dependency_equivalence():
     one.close()
 
 
-def test_full_size_chain_schedule_equivalence():
-    """FVY_CHAIN_SCHED=1 (the chain kernel's roles walk per-pair work lists from the host list schedule instead of the static
-    rotation): the order in which tiles are computed changes, the logits do not."""
-    import os
-    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
-    x = synth.images(40, 416, 416, 7)
-
-    def run(env):
-        old = {k: os.environ.get(k) for k in env}
-        try:
-            os.environ.update(env)
-            eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
-            eng.load_weights(stream)
-            first = eng.forward(x)
-            second = eng.forward(x)                 # graph replay
-            eng.close()
-        finally:
-            for k, v in old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
-        for a, b in zip(first, second):
-            assert np.array_equal(a, b)
-        return first
-
-    sched = run({"FVY_CHAIN_SCHED": "1"})
-    static = run({"FVY_CHAIN_SCHED": "0"})
-    for a, b in zip(sched, static):
-        assert np.array_equal(a, b)
-
-
 def test_full_size_detect_matches_oracle_per_image():
     """Batch 40 @416 through detect(): every image's kept boxes equal the C oracle run on that image's GPU logits."""
     specs = arch.yolo3_table(1)
@@ -521,3 +489,35 @@ def test_608_batch_invariance():
         for a, b in zip(full, single):
             assert a.shape[1:] == b.shape[1:] and np.array_equal(a[i], b[0])
     one.close()
+
+
+def test_full_size_chain_schedule_equivalence():
+    """FVY_CHAIN_SCHED=1 (the chain kernel's roles walk per-pair work lists from the host list schedule instead of the static
+    rotation): the order in which tiles are computed changes, the logits do not."""
+    import os
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(40, 416, 416, 7)
+
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        try:
+            os.environ.update(env)
+            eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
+            eng.load_weights(stream)
+            first = eng.forward(x)
+            second = eng.forward(x)                 # graph replay
+            eng.close()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        for a, b in zip(first, second):
+            assert np.array_equal(a, b)
+        return first
+
+    sched = run({"FVY_CHAIN_SCHED": "1"})
+    static = run({"FVY_CHAIN_SCHED": "0"})
+    for a, b in zip(sched, static):
+        assert np.array_equal(a, b)
