@@ -13,6 +13,9 @@
 // last one, and the tile -> CTA assignment is rotated from layer to layer so that the uneven tile counts average out over
 // the chain instead of costing a partial wave per layer.
 //
+// Which (layer, tile) items a pair works through, and in which order, is a table look-up (ChainWalk): the static rotation, or
+// - FVY_CHAIN_SCHED=1 - per-pair lists from a host list schedule over the known tile lengths and row dependencies.
+//
 // Same arithmetic as conv_igemm_kernel (same MMA shapes, K order and epilogue), so results are bit-identical.
 #pragma once
 
