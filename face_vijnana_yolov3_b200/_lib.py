@@ -41,7 +41,8 @@ class FvyPostParams(C.Structure):
 SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_load_weights", "fvy_weight_count", "fvy_forward",
            "fvy_decode", "fvy_correct_boxes", "fvy_nms", "fvy_bbox_iou", "fvy_postprocess", "fvy_detect", "fvy_num_layers",
            "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
-           "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step", "fvy_letterbox_u8", "fvy_staged_images", "fvy_read_staged"]
+           "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step", "fvy_letterbox_u8", "fvy_staged_images", "fvy_read_staged",
+           "fvy_bbox_iou_fp", "fvy_nms_fp", "fvy_netout_sigmoid"]
 
 _lib = None
 
@@ -71,6 +72,10 @@ def load():
     L.fvy_nms.restype = C.c_int
     L.fvy_nms.argtypes = [H, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp]
     L.fvy_bbox_iou.restype = C.c_int; L.fvy_bbox_iou.argtypes = [H, vp, vp, C.c_int, vp]
+    L.fvy_bbox_iou_fp.restype = C.c_int; L.fvy_bbox_iou_fp.argtypes = [H, vp, vp, C.c_int, C.c_int, vp]
+    L.fvy_nms_fp.restype = C.c_int
+    L.fvy_nms_fp.argtypes = [H, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, vp]
+    L.fvy_netout_sigmoid.restype = C.c_int; L.fvy_netout_sigmoid.argtypes = [H, vp, C.c_longlong, C.c_int]
     L.fvy_postprocess.restype = C.c_int
     L.fvy_postprocess.argtypes = [H, vp, vp, vp, C.c_int, C.POINTER(FvyPostParams), vp, C.c_int, vp, vp]
     for name in ("fvy_detect", "fvy_detect_async"):

@@ -338,6 +338,49 @@ __global__ void bbox_iou_kernel(const int4* a, const int4* b, int n, double* out
     out[i] = p.uni == 0 ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn((double)p.inter, (double)p.uni);
 }
 
+// ---------------------------------------------------------------- IoU of FLOAT boxes
+// bbox_iou / do_nms are type-generic in the reference (yolov3_detect.py:165-194, 426-444): called before correct_yolo_boxes, or from
+// evaluate.py:69,275, the BoundBox coordinates are floats and every operation is a float operation.  Two arithmetic modes, as for the
+// decode: FVY_ARITH_F64 = Python floats / np.float64 (every step a double operation, `float(intersect) / union` a double divide),
+// FVY_ARITH_F32 = np.float32 coordinates under NumPy >= 2 (every step a float operation; the Python float `float(intersect)` is a
+// weak scalar, so the divide is a float32 divide, and `>= nms_thresh` compares in float32).  Each operation is separately rounded.
+__device__ __forceinline__ double fp_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float fp_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double fp_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float fp_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double fp_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float fp_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double fp_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float fp_div(float a, float b) { return __fdiv_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T interval_overlap_fp(T x1, T x2, T x3, T x4) {      // :165-178; Python min(a, b) = b if b < a else a
+    if (x3 < x1) {
+        if (x4 < x1) return (T)0;
+        return fp_sub(x4 < x2 ? x4 : x2, x1);
+    }
+    if (x2 < x3) return (T)0;
+    return fp_sub(x4 < x2 ? x4 : x2, x3);
+}
+template <typename T>
+__device__ __forceinline__ T iou_fp(const T* a, const T* b) {                    // :183-194; union == 0 -> nan / inf like NumPy
+    const T iw = interval_overlap_fp(a[0], a[2], b[0], b[2]);
+    const T ih = interval_overlap_fp(a[1], a[3], b[1], b[3]);
+    const T inter = fp_mul(iw, ih);
+    const T w1 = fp_sub(a[2], a[0]), h1 = fp_sub(a[3], a[1]), w2 = fp_sub(b[2], b[0]), h2 = fp_sub(b[3], b[1]);
+    const T uni = fp_sub(fp_add(fp_mul(w1, h1), fp_mul(w2, h2)), inter);
+    return fp_div(inter, uni);
+}
+__global__ void bbox_iou_fp_kernel(const double* a, const double* b, int n, int arith, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (arith == 0) out[i] = iou_fp<double>(a + 4 * i, b + 4 * i);
+    else {
+        const float fa[4] = {(float)a[4 * i], (float)a[4 * i + 1], (float)a[4 * i + 2], (float)a[4 * i + 3]};
+        const float fb[4] = {(float)b[4 * i], (float)b[4 * i + 1], (float)b[4 * i + 2], (float)b[4 * i + 3]};
+        out[i] = (double)iou_fp<float>(fa, fb);
+    }
+}
+
 // ---------------------------------------------------------------- deterministic sort
 __device__ __forceinline__ uint32_t float_orderable(float f) {
     const uint32_t u = __float_as_uint(f);
@@ -513,6 +556,63 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
             a.mask[((size_t)img * a.capP + row) * a.words + c] = word;
             if (c > r && word) atomicOr(&a.rowflag[(size_t)img * a.words + r], 1ull << threadIdx.x);
         }
+    }
+}
+
+// The same bitmask for FLOAT boxes (fvy_nms_fp): boxes [..][4] double in candidate order, read through the sorted order; one
+// thread per sorted row, plain loop over the 64 columns of a tile (this path serves host-side callers, not the hot path).
+struct MaskFpArgs {
+    const double* box;      // [..][4], segment b at b * seg_stride
+    const int* order;       // [B][capP]
+    const int* counts;
+    int seg_stride, batch, capP, words, arith;
+    double th;
+    unsigned long long* mask; unsigned long long* rowflag;
+};
+__global__ void __launch_bounds__(64) nms_mask_fp_kernel(const MaskFpArgs a) {
+    __shared__ double cbox[64][4];
+    for (int img = 0; img < a.batch; ++img) {
+        const int n = min(a.counts[img], a.seg_stride);
+        const int nb = (n + 63) >> 6;
+        const double* bx = a.box + (size_t)img * a.seg_stride * 4;
+        const int* ord = a.order + (size_t)img * a.capP;
+        for (int t = blockIdx.x; t < nb * nb; t += gridDim.x) {
+            const int r = t / nb, c = t - r * nb;
+            if (c < r) continue;
+            const int col = c * 64 + threadIdx.x, row = r * 64 + threadIdx.x;
+            __syncthreads();
+            if (col < n) { const double* q = bx + 4 * (size_t)ord[col]; cbox[threadIdx.x][0] = q[0]; cbox[threadIdx.x][1] = q[1]; cbox[threadIdx.x][2] = q[2]; cbox[threadIdx.x][3] = q[3]; }
+            __syncthreads();
+            if (row >= n) continue;
+            const double* q = bx + 4 * (size_t)ord[row];
+            const double me[4] = {q[0], q[1], q[2], q[3]};
+            const float mef[4] = {(float)q[0], (float)q[1], (float)q[2], (float)q[3]};
+            const float thf = (float)a.th;
+            unsigned long long word = 0;
+            const int jmax = min(64, n - c * 64);
+            for (int j = (c == r ? threadIdx.x + 1 : 0); j < jmax; ++j) {
+                bool ge;
+                if (a.arith == 0) ge = iou_fp<double>(me, cbox[j]) >= a.th;
+                else {
+                    const float cf[4] = {(float)cbox[j][0], (float)cbox[j][1], (float)cbox[j][2], (float)cbox[j][3]};
+                    ge = iou_fp<float>(mef, cf) >= thf;
+                }
+                if (ge) word |= 1ull << j;
+            }
+            a.mask[((size_t)img * a.capP + row) * a.words + c] = word;
+            if (c > r && word) atomicOr(&a.rowflag[(size_t)img * a.words + r], 1ull << threadIdx.x);
+        }
+    }
+}
+
+// In-place sigmoid of one scale's netout as decode_netout applies it to the CALLER's array (yolov3_detect.py:343-344):
+// channels 0, 1 and 4.. of every (cell, anchor); tw, th stay raw.
+__global__ void netout_sigmoid_kernel(float* netout, long long n_boxes, int ch) {
+    const long long total = n_boxes * ch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ch);
+        if (c == 2 || c == 3) continue;
+        netout[i] = sigmoid_ref(netout[i]);
     }
 }
 

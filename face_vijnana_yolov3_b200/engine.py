@@ -184,6 +184,33 @@ class Engine:
         L.check(self.lib.fvy_bbox_iou(self._h, _ptr(a), _ptr(b), a.shape[0], _ptr(out)))
         return out
 
+    def bbox_iou_fp(self, a, b, arith=L.ARITH_F64) -> np.ndarray:
+        """bbox_iou on float boxes (yolov3_detect.py:183-194 before correct_yolo_boxes / evaluate.py:69); see fvy_bbox_iou_fp."""
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 4); b = np.ascontiguousarray(b, np.float64).reshape(-1, 4)
+        out = np.empty(a.shape[0], np.float64)
+        L.check(self.lib.fvy_bbox_iou_fp(self._h, _ptr(a), _ptr(b), a.shape[0], int(arith), _ptr(out)))
+        return out
+
+    def nms_fp(self, box, classes, counts, nms_thresh, arith=L.ARITH_F64, want_kept=True):
+        """do_nms on float boxes: box (B,S,4) float64, classes (B,S,nc) float32 (modified copy returned), counts (B,)."""
+        box = np.ascontiguousarray(box, np.float64)
+        classes = np.array(classes, np.float32, copy=True, order="C")
+        if classes.ndim == 2:
+            classes = classes[:, :, None]
+        B, S, nc = classes.shape
+        counts = np.ascontiguousarray(counts, np.int32)
+        kept = np.empty((B, S), np.int32) if want_kept else None
+        kc = np.empty(B, np.int32) if want_kept else None
+        L.check(self.lib.fvy_nms_fp(self._h, _ptr(box), _ptr(counts), B, S, nc, float(nms_thresh), int(arith), _ptr(classes), _ptr(kept), _ptr(kc)))
+        return classes, kept, kc
+
+    def netout_sigmoid(self, netout4: np.ndarray) -> None:
+        """In place: netout[..., :2] and netout[..., 4:] -> sigmoid, as decode_netout does to its argument (yolov3_detect.py:343-344)."""
+        if netout4.dtype != np.float32 or not netout4.flags["C_CONTIGUOUS"] or not netout4.flags["WRITEABLE"] or netout4.ndim != 4:
+            raise ValueError("netout_sigmoid expects a writable C-contiguous float32 (gh, gw, 3, 5+nb_class) array")
+        gh, gw, nb, ch = netout4.shape
+        L.check(self.lib.fvy_netout_sigmoid(self._h, _ptr(netout4), gh * gw * nb, ch - 5))
+
     # ---------------------------------------------------------------- whole path
     def postprocess(self, outs=None, batch=None, pp=None, image_hw=None, max_out=None):
         pp = pp or post_params()

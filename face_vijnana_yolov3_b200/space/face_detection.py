@@ -51,6 +51,7 @@ class FaceDetector(object):
         self.specs = arch.fd6_table(self.nn_arch['bb_info_c_size'])
         self._stream = self._initial_stream()
         self._engine = None
+        self._sharded = None
 
     # ------------------------------------------------------------------ weights
     def _initial_stream(self) -> np.ndarray:
@@ -80,6 +81,8 @@ class FaceDetector(object):
         self._stream = stream
         if self._engine is not None:
             self._engine.load_weights(stream)
+        if self._sharded is not None:
+            self._sharded.load_weights(stream)
 
     @property
     def engine(self) -> Engine:
@@ -115,9 +118,25 @@ class FaceDetector(object):
         return self._to_boxes(dets[0], int(counts[0]))
 
     def detect_batch(self, images):
+        """The same per image for a whole batch.  With ``conf['multi_gpu']`` and ``conf['num_gpus'] > 1`` the batch is sharded over
+        that many devices in this process (``shard.ShardedDetector``: the one-line replacement of the reference's
+        ``multi_gpu_model(self.model, gpus=num_gpus)``, :330, :369) - identical results, image order kept."""
         images = np.ascontiguousarray(images)
-        if images.dtype not in (np.float32, np.float64):
+        if images.dtype not in (np.float32, np.float64, np.uint8):
             images = images.astype(np.float64)
+        n_gpus = int(self.conf.get('num_gpus', 1)) if self.conf.get('multi_gpu') else 1
+        if n_gpus > 1:
+            from ..shard import ShardedDetector
+            per = -(-images.shape[0] // n_gpus)
+            if self._sharded is None or self._sharded.engines[0].max_batch < per:
+                if self._sharded is not None:
+                    self._sharded.close()
+                s = self.nn_arch['image_size']
+                self._sharded = ShardedDetector(list(range(n_gpus)), s, s, head=L.HEAD_FD6, max_batch_per_device=per,
+                                                bb_info_c_size=self.nn_arch['bb_info_c_size'])
+                self._sharded.load_weights(self._stream)
+            dets, counts = self._sharded.detect(images, pp=self._pp())
+            return [self._to_boxes(dets[b], int(counts[b])) for b in range(images.shape[0])]
         if images.shape[0] > self.max_batch:
             self.max_batch = int(images.shape[0])
             if self._engine is not None:

@@ -87,42 +87,83 @@ def _box_engine(n: int, nb_class: int) -> Engine:
     return _post_engine(size, size, nb_class)
 
 
+def _box_kind(boxes) -> str:
+    """Arithmetic type the reference's type-generic bbox_iou / do_nms would run in for these coordinates under this NumPy (>= 2:
+    Python scalars are weak): 'int' (pixel boxes after correct_yolo_boxes: exact integers, one double divide), 'f32' (np.float32
+    coordinates, float32 operations) or 'f64' (Python floats / np.float64)."""
+    has32 = has64 = hasf = False
+    for b in boxes:
+        for v in (b.xmin, b.ymin, b.xmax, b.ymax):
+            if isinstance(v, (bool, np.bool_)):
+                raise TypeError("boolean box coordinate")
+            if isinstance(v, (int, np.integer)):
+                continue
+            if isinstance(v, np.float32):
+                has32 = True
+            elif isinstance(v, np.floating):
+                has64 = True
+            elif isinstance(v, float):
+                hasf = True
+            else:
+                raise TypeError(f"unsupported box coordinate type {type(v)}")
+    if has64:
+        return "f64"
+    if has32:
+        return "f32"
+    return "f64" if hasf else "int"
+
+
 def _as_i32_boxes(boxes) -> np.ndarray:
     out = np.empty((len(boxes), 4), np.int32)
     for i, b in enumerate(boxes):
         for k, v in enumerate((b.xmin, b.ymin, b.xmax, b.ymax)):
-            if not isinstance(v, (int, np.integer)):
-                raise TypeError("do_nms / bbox_iou on the GPU need integer pixel boxes: call correct_yolo_boxes first "
-                                "(the reference pipeline does, yolov3_detect.py:601-604)")
             if not -(1 << 30) < int(v) < (1 << 30):
                 raise OverflowError("box coordinate outside +-2^30")
             out[i, k] = int(v)
     return out
 
 
+def _as_f64_boxes(boxes) -> np.ndarray:
+    return np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes], np.float64).reshape(len(boxes), 4)
+
+
 # ----------------------------------------------------------------------------------------------
 # reference functions
 # ----------------------------------------------------------------------------------------------
-def bbox_iou(box1, box2) -> float:
-    """float(intersect)/union on integer boxes, evaluated on the device (:183-194).  A zero union
-    raises ZeroDivisionError for Python ints exactly as the reference does; numpy ints give nan."""
-    ib = _as_i32_boxes([box1, box2])
-    v = float(_box_engine(2, 1).bbox_iou(ib[0:1], ib[1:2])[0])
-    if v != v and all(isinstance(c, int) for c in (box1.xmin, box1.xmax, box1.ymin, box1.ymax, box2.xmin, box2.xmax, box2.ymin, box2.ymax)):
-        raise ZeroDivisionError("float division by zero")
-    return v
+def bbox_iou(box1, box2):
+    """``float(intersect) / union`` evaluated on the device (:183-194), in the arithmetic the coordinates' types select
+    (integer pixel boxes: exact, one double divide; float boxes: every step a float operation, see fvy_bbox_iou_fp).  A zero
+    union raises ZeroDivisionError for Python numbers exactly as the reference does; numpy scalars give nan / inf."""
+    kind = _box_kind([box1, box2])
+    coords = (box1.xmin, box1.xmax, box1.ymin, box1.ymax, box2.xmin, box2.xmax, box2.ymin, box2.ymax)
+    python_only = all(isinstance(c, (int, float)) for c in coords)
+    if kind == "int":
+        ib = _as_i32_boxes([box1, box2])
+        v = float(_box_engine(2, 1).bbox_iou(ib[0:1], ib[1:2])[0])
+        if v != v and python_only:
+            raise ZeroDivisionError("float division by zero")
+        return v
+    fb = _as_f64_boxes([box1, box2])
+    v = _box_engine(2, 1).bbox_iou_fp(fb[0:1], fb[1:2], L.ARITH_F32 if kind == "f32" else L.ARITH_F64)[0]
+    if python_only:
+        if not np.isfinite(v):
+            raise ZeroDivisionError("float division by zero")
+        return float(v)
+    return np.float32(v) if kind == "f32" else np.float64(v)
 
 
 def decode_netout(netout, anchors, anchor_idx, obj_thresh, net_h, net_w, anchor_mask=None) -> List[BoundBox]:
     """One scale of one image -> BoundBox list in (row, col, anchor) order (:335-387).
 
-    ``anchor_mask`` (3 bits, bit b = anchor b decoded) defaults to the fork's mask for ``anchor_idx``
-    (:354-362).  Unlike the reference the caller's ``netout`` is not modified in place."""
-    netout = np.ascontiguousarray(netout, dtype=np.float32)
-    gh, gw = netout.shape[:2]
-    nb_class = netout.shape[-1] // 3 - 5
-    if netout.ndim != 3 or netout.shape[-1] != 3 * (5 + nb_class) or nb_class < 1:
-        raise ValueError(f"netout must be (grid_h, grid_w, 3*(5+nb_class)), got {netout.shape}")
+    ``anchor_mask`` (3 bits, bit b = anchor b decoded) defaults to the fork's mask for ``anchor_idx`` (:354-362).  As in the
+    reference, the caller's ``netout`` is modified IN PLACE - ``[..., :2]`` and ``[..., 4:]`` become their sigmoid (:343-344) -
+    and every box's ``classes`` is a VIEW into it (:366), so do_nms' zeroing writes through.  (An argument that is not a writable
+    C-contiguous float32 array cannot be updated in place; the views then point into a private copy.)"""
+    raw = np.array(netout, dtype=np.float32, copy=True, order="C")          # the logits the device decodes
+    gh, gw = raw.shape[:2]
+    nb_class = raw.shape[-1] // 3 - 5
+    if raw.ndim != 3 or raw.shape[-1] != 3 * (5 + nb_class) or nb_class < 1:
+        raise ValueError(f"netout must be (grid_h, grid_w, 3*(5+nb_class)), got {raw.shape}")
     if anchor_idx not in (0, 1, 2):
         raise ValueError("anchor_idx must be 0, 1 or 2")
     eng = _post_engine(net_h, net_w, nb_class)
@@ -133,17 +174,22 @@ def decode_netout(netout, anchors, anchor_idx, obj_thresh, net_h, net_w, anchor_
     anc = [0] * 18
     anc[6 * anchor_idx:6 * anchor_idx + 6] = [int(a) for a in anchors]
     pp = post_params(obj_thresh=obj_thresh, anchor_mask=(int(anchor_mask) & 7) << (3 * anchor_idx), anchors=anc, arith=DECODE_ARITH)
-    outs = [np.zeros((1, g[0], g[1], netout.shape[-1]), np.float32) for g in eng.grids]
-    outs[anchor_idx] = netout[None]
+    outs = [np.zeros((1, g[0], g[1], raw.shape[-1]), np.float32) for g in eng.grids]
+    outs[anchor_idx] = raw[None]
     d = eng.decode(outs, pp=pp, image_hw=None)
     n = int(d["counts"][0])
+    # the in-place half, on the caller's array when it can be written
+    inplace = isinstance(netout, np.ndarray) and netout.dtype == np.float32 and netout.flags["C_CONTIGUOUS"] and netout.flags["WRITEABLE"]
+    view = (netout if inplace else raw.copy()).reshape(gh, gw, 3, 5 + nb_class)
+    eng.netout_sigmoid(view)
     ftype = np.float64 if DECODE_ARITH == L.ARITH_F64 else np.float32
+    first = int(3 * sum(g[0] * g[1] for g in eng.grids[:anchor_idx]))        # all-anchor numbering of fvy_det.cand
     boxes = []
-    classes = d["classes"][0, :n].copy()
     for i in range(n):
         x0, y0, x1, y1 = (ftype(v) for v in d["nbox"][0, i])
-        b = int(d["cand"][0, i]) % 3
-        boxes.append(BoundBox(x0, y0, x1, y1, d["objness"][0, i], classes[i], (anchors[2 * b + 0], anchors[2 * b + 1])))
+        cell, b = divmod(int(d["cand"][0, i]) - first, 3)
+        row, col = divmod(cell, gw)
+        boxes.append(BoundBox(x0, y0, x1, y1, view[row, col, b, 4], view[row, col, b, 5:], (anchors[2 * b + 0], anchors[2 * b + 1])))
     return boxes
 
 
@@ -181,13 +227,19 @@ def _nms_inplace(boxes, nms_thresh, nb_class):
     n = len(boxes)
     eng = _box_engine(n, nb_class)
     S = eng.cap
-    ib = np.zeros((1, S, 4), np.int32)
-    ib[0, :n] = _as_i32_boxes(boxes)
     cls = np.zeros((1, S, nb_class), np.float32)
     for i, b in enumerate(boxes):
         for c in range(nb_class):
             cls[0, i, c] = b.classes[c]
-    out, _, _ = eng.nms(ib, cls, np.array([n], np.int32), nms_thresh, want_kept=False)
+    kind = _box_kind(boxes)
+    if kind == "int":          # the reference pipeline: pixel boxes after correct_yolo_boxes (:601-604)
+        ib = np.zeros((1, S, 4), np.int32)
+        ib[0, :n] = _as_i32_boxes(boxes)
+        out, _, _ = eng.nms(ib, cls, np.array([n], np.int32), nms_thresh, want_kept=False)
+    else:                      # float boxes: every IoU step a float operation of that type (fvy_nms_fp)
+        fb = np.zeros((1, S, 4), np.float64)
+        fb[0, :n] = _as_f64_boxes(boxes)
+        out, _, _ = eng.nms_fp(fb, cls, np.array([n], np.int32), nms_thresh, L.ARITH_F32 if kind == "f32" else L.ARITH_F64, want_kept=False)
     for i, b in enumerate(boxes):
         for c in range(nb_class):
             if out[0, i, c] == 0 and b.classes[c] != 0:

@@ -135,6 +135,20 @@ int fvy_nms(fvy_handle* h, const int32_t* ibox, const int32_t* counts, int batch
  * union == 0 -> NaN.  a, b: [n][4] int32, out[n]. */
 int fvy_bbox_iou(fvy_handle* h, const int32_t* a, const int32_t* b, int n, double* out);
 
+/* bbox_iou / do_nms on FLOAT boxes.  The reference's functions are type-generic (yolov3_detect.py:165-194, 426-444): called on
+ * BoundBox floats - before correct_yolo_boxes, or from evaluate.py:69,275 - every step is a float operation.  Boxes are passed
+ * as doubles; arith selects the operation type: FVY_ARITH_F64 = Python floats / np.float64 (double operations, double divide),
+ * FVY_ARITH_F32 = np.float32 coordinates under NumPy >= 2 (float operations; `float(intersect) / union` and `>= nms_thresh`
+ * are evaluated in float32 because Python scalars are weak there).  union == 0 gives nan / inf as NumPy does (never >= thresh
+ * for nan).  fvy_nms_fp: HOST pointers; box [batch][seg_stride][4]; otherwise as fvy_nms. */
+int fvy_bbox_iou_fp(fvy_handle* h, const double* a, const double* b, int n, int arith, double* out);
+int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batch, int seg_stride, int nb_class,
+               double nms_thresh, int arith, float* classes, int32_t* kept_idx, int32_t* kept_counts);
+/* The in-place part of decode_netout (yolov3_detect.py:343-344): netout[..., :2] and netout[..., 4:] of one scale's
+ * (grid_h, grid_w, 3, 5 + nb_class) array become their sigmoid (1 / (1 + exp(-x)) in float32, exp correctly rounded), in the
+ * caller's array (host or device), n_boxes = grid_h * grid_w * 3. */
+int fvy_netout_sigmoid(fvy_handle* h, float* netout, long long n_boxes, int nb_class);
+
 /* Post-processing of resident (or given) logits into detections.
  *   yolo3: decode -> correct_yolo_boxes -> do_nms -> boxes with a surviving class score, candidate order.
  *   fd6:   FaceDetector.detect after predict (face_detection.py:900-947): sigmoid, threshold, box math,

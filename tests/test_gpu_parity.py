@@ -162,7 +162,8 @@ def test_post_against_reference_vectors(post_engine, golden_dir, tag):
     d = post_engine.decode(outs, pp=pp, image_hw=g["image_hw"][None])
     n = int(d["counts"][0])
     assert n == g["ibox"].shape[0]
-    assert (d["ibox"][0, :n] != g["ibox"]).mean() <= 1e-3            # NumPy's float32 exp is a few ulp off correctly rounded
+    diff = np.abs(d["ibox"][0, :n].astype(np.int64) - g["ibox"])      # NumPy's float32 exp is a few ulp off correctly rounded:
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3            # a coordinate may straddle an integer, by one pixel, rarely
     assert np.abs(d["classes"][0, :n] - g["classes_before"]).max() <= 1e-6
     # NMS on the REFERENCE's candidates: kept set and order bit-exact
     S = post_engine.cap

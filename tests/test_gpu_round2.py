@@ -1,0 +1,262 @@
+"""GPU parity tests added in round 2 (-m gpu): the configurations and call patterns the round-1 suite left open.
+
+  * nb_class = 80 (the reference's literal 255-channel heads, yolov3_detect.py:278,294,308): logits vs the fp32 oracle and
+    detect vs the C oracle with 80 classes;
+  * multi-class do_nms (:431-444) on vectors produced by the reference's own code (nb_class = 3);
+  * BASELINE configs[2] per-GPU geometry: batch 160 @608 through detect(), sampled images vs the oracle;
+  * sharded inference (replaces multi_gpu_model, face_detection.py:330,369): identical records whether an image is processed
+    at N = 1 or on device floor(i N / B);
+  * asynchronous calls: deferred (sticky) errors, forward() after an odd number of asynchronous calls;
+  * reference call patterns the round-1 drop-in refused: bbox_iou / do_nms on float boxes, decode_netout's in-place sigmoid and
+    `classes` views.
+Tolerances as in test_gpu_parity.py: head logits relative L2 <= 1e-2 (Keras-default random init), everything else bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from face_vijnana_yolov3_b200 import _lib as L, arch, synth
+from face_vijnana_yolov3_b200.engine import Engine, post_params
+from face_vijnana_yolov3_b200.shard import ShardedDetector, owner_of, shard_bounds
+from oracle import darknet_ref as D, postproc as P
+
+HEAD_TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _oracle_detect(outs_b, nb_class, hw, obj_thresh, nms_thresh, net=416):
+    d = P.decode_image(outs_b, obj_thresh=obj_thresh, net_h=net, net_w=net)
+    ib = P.correct_yolo_boxes(d["box"], hw[0], hw[1], net, net)
+    cls = P.do_nms(ib, d["classes"], nms_thresh)
+    keep = np.nonzero((cls > 0).any(1))[0]
+    return d, ib, cls, keep
+
+
+# ------------------------------------------------------------------------------------------ nb_class = 80
+def test_forward_and_detect_nb_class_80():
+    """The 255 -> 256-wide head tile is a different kernel instance than the 18 -> 32 one of the face heads."""
+    specs = arch.yolo3_table(80)
+    stream = synth.darknet_stream(specs, 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(2, 416, 416, 3)
+    eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=80, max_batch=2)
+    eng.load_weights(stream)
+    outs = eng.forward(x)
+    ref = D.forward(stream, x, 80)
+    assert [o.shape for o in outs] == [(2, 13, 13, 255), (2, 26, 26, 255), (2, 52, 52, 255)]
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) <= HEAD_TOL
+    # detect with 80 classes vs the C oracle on the GPU's logits (obj_thresh just under 0.5: glorot logits are small)
+    hw = np.array([[416, 416], [360, 640]], np.int32)
+    pp = post_params(0.49, 0.45)
+    dets, counts = eng.detect(x, pp=pp, image_hw=hw)
+    for b in range(2):
+        d, ib, cls, keep = _oracle_detect([o[b] for o in outs], 80, hw[b], 0.49, 0.45)
+        n = int(counts[b])
+        assert len(ib) > 50, "the test needs candidates"
+        assert n == len(keep)
+        got = dets[b, :n]
+        assert np.array_equal(np.stack([got["xmin"], got["ymin"], got["xmax"], got["ymax"]], 1), ib[keep])
+        assert np.array_equal(got["label"], cls[keep].argmax(1))
+        assert np.array_equal(got["score"], np.minimum(cls[keep].max(1), 1.0).astype(np.float32))
+    eng.close()
+
+
+def test_multiclass_nms_against_reference_vectors(golden_dir):
+    """nb_class = 3 vectors produced by the reference's own decode_netout / correct_yolo_boxes / do_nms (tools/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "post_yolo3_mc.npz"))
+    eng = Engine(416, 416, head=L.HEAD_NONE, nb_class=3, max_batch=1)
+    outs = [g["out0"][None], g["out1"][None], g["out2"][None]]
+    pp = post_params(float(g["obj_thresh"]), float(g["nms_thresh"]), arith=L.ARITH_F32)
+    d = eng.decode(outs, pp=pp, image_hw=g["image_hw"][None])
+    n = int(d["counts"][0])
+    assert n == g["ibox"].shape[0]
+    diff = np.abs(d["ibox"][0, :n].astype(np.int64) - g["ibox"])
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3          # NumPy's float32 exp is a few ulp off correctly rounded
+    assert np.abs(d["classes"][0, :n] - g["classes_before"]).max() <= 1e-6
+    S = eng.cap
+    ib = np.zeros((1, S, 4), np.int32); ib[0, :n] = g["ibox"]
+    cl = np.zeros((1, S, 3), np.float32); cl[0, :n] = g["classes_before"]
+    out, kept, kc = eng.nms(ib, cl, np.array([n], np.int32), float(g["nms_thresh"]))
+    assert np.array_equal(out[0, :n], g["classes_after"])            # every class's suppression pattern, bit-exact
+    assert np.array_equal(kept[0, :kc[0]], np.nonzero((g["classes_after"] > 0).any(1))[0])
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs[2] per-GPU shape
+def test_608_batch_160_detect_matches_oracle_on_sampled_images():
+    """Batch 160 @608 (what each of 2 GPUs takes of BASELINE configs[2]): sampled images' logits vs the fp32 oracle and their kept
+    boxes vs the C oracle run on the GPU's logits."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    B, S = 160, 608
+    rng = np.random.default_rng(21)
+    x = rng.random((B, S, S, 3), dtype=np.float32)
+    eng = Engine(S, S, head=L.HEAD_YOLO3, nb_class=1, max_batch=B)
+    eng.load_weights(stream)
+    pp = post_params(0.5, 0.45)
+    hw = np.tile(np.array([[S, S]], np.int32), (B, 1))
+    outs = eng.forward(x)
+    dets, counts = eng.detect(x, pp=pp, image_hw=hw)
+    eng.close()
+    sample = (0, 77, 159)
+    ref = D.forward(stream, x[list(sample)], 1)
+    for k, b in enumerate(sample):
+        for o, r in zip(outs, ref):
+            assert rel_l2(o[b], r[k]) <= HEAD_TOL
+        d, ib, cls, keep = _oracle_detect([o[b] for o in outs], 1, (S, S), 0.5, 0.45, net=S)
+        n = int(counts[b])
+        assert n == len(keep)
+        got = dets[b, :n]
+        assert np.array_equal(np.stack([got["xmin"], got["ymin"], got["xmax"], got["ymax"]], 1), ib[keep])
+        assert np.array_equal(got["score"], np.minimum(cls[keep, 0], 1.0).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------ sharded inference
+def _sharded_identity(devices):
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    B = 16
+    x = synth.images(B, 416, 416, 31)
+    hw = np.array([[416, 416], [300, 400], [720, 1280], [500, 375]] * 4, np.int32)
+    pp = post_params(0.5, 0.45)
+    one = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=B, device=devices[0])
+    one.load_weights(stream)
+    d1, c1 = one.detect(x, pp=pp, image_hw=hw)
+    one.close()
+    sh = ShardedDetector(devices, 416, 416, nb_class=1, max_batch_per_device=-(-B // len(devices)))
+    sh.load_weights(stream)
+    dn, cn = sh.detect(x, pp=pp, image_hw=hw)
+    sh.close()
+    assert np.array_equal(c1, cn) and c1.sum() > 0
+    for b in range(B):
+        assert d1[b, :c1[b]].tobytes() == dn[b, :cn[b]].tobytes(), f"image {b} (device {devices[owner_of(b, B, len(devices))]})"
+    bounds = shard_bounds(B, len(devices))
+    assert bounds[0][0] == 0 and bounds[-1][1] == B and all(bounds[i][1] == bounds[i + 1][0] for i in range(len(devices) - 1))
+
+
+def test_sharded_detect_identity_one_device():
+    """Two handles on ONE device, run one after the other by ShardedDetector: the shard boundaries and the reassembly in image
+    order (runs on every box; the multi-device form below needs >= 2 GPUs)."""
+    _sharded_identity([0, 0])
+
+
+def test_sharded_detect_identity_multi_device():
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    _sharded_identity(list(range(min(n, 4))))
+
+
+# ------------------------------------------------------------------------------------------ asynchronous calls
+def test_async_errors_are_sticky_until_reported():
+    """fvy_detect_async returns before the decode ran: a capacity overflow must surface at fvy_sync (or at the next call that
+    reuses the logit set), not vanish."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(1, 416, 416, 7)
+    eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=1, max_cands=100)
+    eng.load_weights(stream)
+    pp = post_params(0.5, 0.45)
+    with pytest.raises(L.FvyError) as ei:                       # the synchronous path reports at once
+        eng.detect(x, pp=pp, sync=True, max_out=100)
+    assert ei.value.code == L.FVY_E_CAPACITY
+    eng.detect(x, pp=pp, sync=False, max_out=100)                # enqueued: no error yet
+    with pytest.raises(L.FvyError) as ei:
+        eng.sync()
+    assert ei.value.code == L.FVY_E_CAPACITY and "asynchronous" in str(ei.value)
+    eng.sync()                                                   # reported once
+    # without a sync in between, the third asynchronous call (same logit set as the first) reports it
+    eng.detect(x, pp=pp, sync=False, max_out=100)
+    eng.detect(x, pp=pp, sync=False, max_out=100)
+    with pytest.raises(L.FvyError):
+        eng.detect(x, pp=pp, sync=False, max_out=100)
+    with pytest.raises(L.FvyError):
+        eng.sync()                                               # the second call's report
+    eng.close()
+
+
+def test_forward_after_odd_number_of_async_calls_is_fresh():
+    """After an odd number of asynchronous detect calls the head logits of the last forward live in the alternate set:
+    fvy_forward must not hand out the previous call's logits."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    xa, xb = synth.images(2, 416, 416, 41), synth.images(2, 416, 416, 42)
+    eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=2)
+    eng.load_weights(stream)
+    eng.detect(xa, pp=post_params(0.5, 0.45), sync=False)
+    got = eng.forward(xb)
+    eng.sync()
+    fresh = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=2)
+    fresh.load_weights(stream)
+    want = fresh.forward(xb)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # and the resident logits post-processed afterwards are xb's
+    d1, c1 = eng.postprocess(batch=2, pp=post_params(0.5, 0.45), image_hw=np.array([[416, 416]] * 2, np.int32))
+    d2, c2 = fresh.detect(xb, pp=post_params(0.5, 0.45))
+    assert np.array_equal(c1, c2) and all(d1[b, :c1[b]].tobytes() == d2[b, :c2[b]].tobytes() for b in range(2))
+    eng.close(); fresh.close()
+
+
+# ------------------------------------------------------------------------------------------ reference call patterns
+def test_float_box_iou_and_nms_against_reference_vectors(golden_dir):
+    """bbox_iou / do_nms on un-corrected FLOAT boxes (the reference's functions are type-generic): np.float32 coordinates
+    (float32 arithmetic under NumPy >= 2) and Python floats (float64), vectors produced by the reference itself."""
+    from face_vijnana_yolov3_b200.space import yolov3_detect as yd
+    g = np.load(os.path.join(golden_dir, "post_float.npz"))
+    box, cls0, pairs = g["box"], g["classes_before"], g["pairs"]
+    eng = yd._box_engine(len(box), 1)
+    i32 = eng.bbox_iou_fp(box[pairs[:, 0]], box[pairs[:, 1]], L.ARITH_F32)
+    i64 = eng.bbox_iou_fp(box[pairs[:, 0]], box[pairs[:, 1]], L.ARITH_F64)
+    assert np.array_equal(i32, g["iou32"], equal_nan=True)
+    assert np.array_equal(i64, g["iou64"], equal_nan=True)
+    # through the drop-in, with the result types the reference returns
+    b32 = [yd.BoundBox(*box[k], objness=None, classes=np.array([cls0[k]], np.float32)) for k in range(len(box))]
+    v = yd.bbox_iou(b32[pairs[0, 0]], b32[pairs[0, 1]])
+    assert isinstance(v, np.float32) and (v == np.float32(g["iou32"][0]) or (np.isnan(v) and np.isnan(g["iou32"][0])))
+    bpy = [yd.BoundBox(*[float(c) for c in box[k]], objness=None, classes=np.array([cls0[k]], np.float32)) for k in range(len(box))]
+    k = int(np.nonzero(np.isfinite(g["iou64"]))[0][0])
+    v = yd.bbox_iou(bpy[pairs[k, 0]], bpy[pairs[k, 1]])
+    assert isinstance(v, float) and v == g["iou64"][k]
+    yd.do_nms(b32, float(g["nms_thresh"]))
+    yd.do_nms(bpy, float(g["nms_thresh"]))
+    assert np.array_equal(np.array([b.classes[0] for b in b32], np.float32), g["after32"])
+    assert np.array_equal(np.array([b.classes[0] for b in bpy], np.float32), g["after64"])
+
+
+def test_decode_netout_in_place_sigmoid_and_class_views():
+    """decode_netout applies the sigmoid to the CALLER's array (yolov3_detect.py:343-344) and `classes` is a view into it
+    (:366): do_nms' zeroing shows up in the array."""
+    from face_vijnana_yolov3_b200.space import yolov3_detect as yd
+    outs = synth.head_logits(1, 416, 416, 2, seed=17)
+    anchors = [30, 61, 62, 45, 59, 119]
+    net = outs[1][0].copy()
+    raw = net.copy()
+    boxes = yd.decode_netout(net, anchors, 1, 0.5, 416, 416)
+    v = net.reshape(26, 26, 3, 7)
+    r = raw.reshape(26, 26, 3, 7)
+    assert np.array_equal(v[..., 2:4], r[..., 2:4])                                   # tw, th stay raw
+    assert np.array_equal(v[..., :2], P.sigmoid(r[..., :2])) and np.array_equal(v[..., 4:], P.sigmoid(r[..., 4:]))
+    assert len(boxes) > 10 and all(np.shares_memory(b.classes, net) for b in boxes)
+    d = P.decode_netout(raw, anchors, 0b101, 0.5, 416, 416)
+    assert np.array_equal(np.array([b.objness for b in boxes], np.float32), d["objness"])
+    assert np.array_equal(np.stack([b.classes for b in boxes]), d["classes"])
+    yd.correct_yolo_boxes(boxes, 416, 416, 416, 416)
+    before = np.stack([b.classes for b in boxes]).copy()
+    yd.do_nms(boxes, 0.3)
+    after = np.stack([b.classes for b in boxes])
+    assert (after != before).any() and np.array_equal(after == 0, (after == 0) | (before == 0))
+    # the zeroing went through the views into the caller's array
+    zeroed = int((before != 0).sum() - (after != 0).sum())
+    assert zeroed > 0 and int((v[..., 5:] == 0).sum()) >= zeroed
+    # an argument that cannot be written in place still decodes (private copy)
+    ro = raw.copy(); ro.setflags(write=False)
+    assert len(yd.decode_netout(ro, anchors, 1, 0.5, 416, 416)) == len(boxes)

@@ -21,7 +21,7 @@ def _ulp_diff(a, b):
     return np.abs(a - b)
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "mc"])      # mc: nb_class = 3, pins the per-class loop of do_nms (:431-444)
 def test_yolo3_post_against_reference_vectors(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, f"post_yolo3_{tag}.npz"))
     outs = [g["out0"], g["out1"], g["out2"]]

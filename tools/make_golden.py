@@ -11,6 +11,9 @@ as small fixtures (this script is their provenance):
   post_fd6.npz            reference FaceDetector.detect (src/space/face_detection.py:885-949) on seeded
                           (1,13,13,6) maps through a fake model.predict.
   iou_cases.json          bbox_iou / _interval_overlap known answers computed by the reference code.
+  post_yolo3_mc.npz       the same pipeline with nb_class = 3: pins the per-class loop of do_nms (:431-444) on the reference itself.
+  post_float.npz          reference bbox_iou / do_nms called on FLOAT boxes (before correct_yolo_boxes): np.float32 coordinates as this
+                          NumPy's decode_netout returns them (float32 arithmetic) and the same boxes as Python floats (float64).
   letterbox.npz           the image the reference's own FaceDetector.test() loop (src/space/face_detection.py:798-835, cv2 of this
                           image) hands to detect(), for seeded uint8 images written as PNG-exact BMP files, image_size 64
   gt_tensor.npz           reference TrainingSequence.__getitem__ ground-truth tensors (src/space/face_detection.py:98-310)
@@ -121,6 +124,40 @@ def iou_cases():
     print("iou cases", len(out))
 
 
+def float_box_cases():
+    """bbox_iou / do_nms are type-generic (:165-194, :426-444): run them on un-corrected float boxes in both arithmetic types."""
+    Y = R.load_yolov3_detect()
+    outs = synth.head_logits(1, 416, 416, 1, seed=31)
+    boxes = []
+    for i in range(3):
+        boxes += Y.decode_netout(outs[i][0].copy(), ANCHORS[i], i, 0.6, 416, 416)
+    assert all(isinstance(b.xmin, np.float32) for b in boxes), "this NumPy returns float32 coordinates"
+    box32 = np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes], np.float32)
+    cls0 = np.array([b.classes[0] for b in boxes], np.float32)
+    rng = np.random.default_rng(3)
+    pairs = rng.integers(0, len(boxes), (96, 2))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        iou32 = np.array([Y.bbox_iou(boxes[i], boxes[j]) for i, j in pairs], np.float64)
+        assert all(isinstance(Y.bbox_iou(boxes[i], boxes[j]), np.float32) for i, j in pairs[:4])
+        pyb = [Y.BoundBox(float(b.xmin), float(b.ymin), float(b.xmax), float(b.ymax), b.objness, np.array(b.classes, np.float32)) for b in boxes]
+        iou64 = []
+        for i, j in pairs:
+            try:
+                iou64.append(Y.bbox_iou(pyb[i], pyb[j]))
+            except ZeroDivisionError:
+                iou64.append(np.nan)
+        b32 = [Y.BoundBox(b.xmin, b.ymin, b.xmax, b.ymax, b.objness, np.array(b.classes, np.float32)) for b in boxes]
+        Y.do_nms(b32, 0.45)
+        Y.do_nms(pyb, 0.45)
+    after32 = np.array([b.classes[0] for b in b32], np.float32)
+    after64 = np.array([b.classes[0] for b in pyb], np.float32)
+    np.savez_compressed(os.path.join(OUT, "post_float.npz"), box=box32, classes_before=cls0, pairs=pairs, iou32=iou32,
+                        iou64=np.array(iou64, np.float64), after32=after32, after64=after64, nms_thresh=0.45, numpy_version=np.__version__)
+    print("float boxes", len(boxes), "kept f32", int((after32 > 0).sum()), "kept f64", int((after64 > 0).sum()),
+          "differ", int(((after32 > 0) != (after64 > 0)).sum()))
+
+
 def gt_tensor_cases():
     """Reference TrainingSequence.__getitem__ (src/space/face_detection.py:98-310) on synthetic images + training.csv."""
     import tempfile
@@ -203,6 +240,8 @@ if __name__ == "__main__":
     post_yolo3("a", seed=21, image_hw=(416, 416), obj_thresh=0.5, nms_thresh=0.45)
     post_yolo3("b", seed=22, image_hw=(360, 640), obj_thresh=0.6, nms_thresh=0.5)
     post_yolo3("c", seed=23, image_hw=(500, 375), obj_thresh=0.5, nms_thresh=0.3)
+    post_yolo3("mc", seed=25, image_hw=(416, 416), obj_thresh=0.6, nms_thresh=0.45, nb_class=3)
+    float_box_cases()
     post_fd6()
     iou_cases()
     gt_tensor_cases()
