@@ -25,6 +25,8 @@ void fvy_destroy(fvy_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_lb_src) cudaFree(h->d_lb_src);
     for (int* p : h->h_async) if (p) cudaFreeHost(p);
+    for (auto& pr : h->ev_tf) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
+    for (auto& pr : h->ev_tp) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
     for (void* p : h->d_input) if (p) cudaFree(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {h->ev_ready[0], h->ev_ready[1], h->ev_consumed[0], h->ev_consumed[1], h->ev_post, h->ev_d2h}) if (e) cudaEventDestroy(e);
@@ -78,6 +80,8 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
         for (cudaEvent_t* ev : {&h->ev_ready[0], &h->ev_ready[1], &h->ev_consumed[0], &h->ev_consumed[1], &h->ev_post, &h->ev_d2h})
             ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { e = fail(FVY_E_CUDA, "cudaEventCreate failed"); break; }
+        for (auto& pr : h->ev_tf) for (cudaEvent_t& ev : pr) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+        for (auto& pr : h->ev_tp) for (cudaEvent_t& ev : pr) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
         for (int*& p : h->h_async)
             ok = ok && cudaHostAlloc((void**)&p, (size_t)(1 + cfg->max_batch) * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
         if (!ok) { e = fail(FVY_E_CUDA, "cudaHostAlloc (async status) failed"); break; }
@@ -378,7 +382,9 @@ static int postprocess_common(fvy_handle* h, const float* out0, const float* out
     if (int e = upload_image_hw(h, image_hw, batch, &d_hw)) return e;
     CUDA_TRY(cudaStreamWaitEvent(h->ps, h->ev_d2h, 0));          // the previous call's detections have left the device buffers
     CUDA_TRY(cudaEventRecord(h->ev[2], h->ps));
+    if (h->time_slot >= 0) CUDA_TRY(cudaEventRecord(h->ev_tp[h->time_slot][0], h->ps));
     if (int e = post_enqueue(h, dev, batch, pp, d_hw, max_out)) return e;
+    if (h->time_slot >= 0) CUDA_TRY(cudaEventRecord(h->ev_tp[h->time_slot][1], h->ps));
     CUDA_TRY(cudaEventRecord(h->ev[3], h->ps));
     CUDA_TRY(cudaEventRecord(h->ev_post, h->ps));
     CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_post, 0));
@@ -424,9 +430,13 @@ static int detect_common(fvy_handle* h, const void* images, int dtype, int batch
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_post_done[0], 0));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_post_done[1], 0));              // nothing of an earlier asynchronous call is still in flight
     }
+    const int slot = (int)(h->call_count++ % fvy_handle::kTimeRing);
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev_tf[slot][0], h->stream));
     if (int e = forward_enqueue(h, images, dtype, batch)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev_tf[slot][1], h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    h->time_slot = slot;
     int e = FVY_OK;
     if (overlap) {
         CUDA_TRY(cudaEventRecord(h->ev_fwd_done[h->logit_set], h->stream));
@@ -439,6 +449,7 @@ static int detect_common(fvy_handle* h, const void* images, int dtype, int batch
         e = postprocess_common(h, nullptr, nullptr, nullptr, batch, pp, image_hw, max_out, dets, det_counts, sync);
         if (e == FVY_OK && !sync) CUDA_TRY(cudaEventRecord(h->ev_post_done[0], h->stream));
     }
+    h->time_slot = -1;
     if (e) return e;
     if (sync) CUDA_TRY(cudaEventElapsedTime(&h->last_fwd_ms, h->ev[0], h->ev[1]));
     return FVY_OK;
@@ -535,6 +546,8 @@ int fvy_letterbox_u8(fvy_handle* h, const unsigned char* src, int src_h, int src
             CUDA_TRY(cudaStreamSynchronize(h->stream));
             if (h->d_lb_src) cudaFree(h->d_lb_src);
     for (int* p : h->h_async) if (p) cudaFreeHost(p);
+    for (auto& pr : h->ev_tf) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
+    for (auto& pr : h->ev_tp) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
             h->d_lb_src = nullptr; h->lb_src_bytes = 0;
             CUDA_TRY(cudaMalloc((void**)&h->d_lb_src, bytes));
             h->lb_src_bytes = bytes;
@@ -651,7 +664,28 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
 int fvy_timer_start(fvy_handle* h) {
     if (!h) return fail(FVY_E_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->timer_mark = h->call_count;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+    return FVY_OK;
+}
+int fvy_timer_breakdown(fvy_handle* h, float* forward_ms_mean, float* post_ms_mean, int* calls) {
+    if (!h) return fail(FVY_E_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->post_stream));
+    const long long first = std::max(h->timer_mark, h->call_count - fvy_handle::kTimeRing);
+    double f = 0.0, p = 0.0;
+    int n = 0;
+    for (long long c = first; c < h->call_count; ++c) {
+        const int slot = (int)(c % fvy_handle::kTimeRing);
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&a, h->ev_tf[slot][0], h->ev_tf[slot][1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, h->ev_tp[slot][0], h->ev_tp[slot][1]));
+        f += a; p += b; ++n;
+    }
+    if (forward_ms_mean) *forward_ms_mean = n ? (float)(f / n) : 0.f;
+    if (post_ms_mean) *post_ms_mean = n ? (float)(p / n) : 0.f;
+    if (calls) *calls = n;
     return FVY_OK;
 }
 int fvy_timer_stop(fvy_handle* h, float* ms) {

@@ -276,6 +276,12 @@ class Engine:
         L.check(self.lib.fvy_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def timer_breakdown(self):
+        """(mean forward ms, mean post-processing ms, calls) of the detect calls since timer_start, from CUDA events in the timed region."""
+        a, b, n = C.c_float(), C.c_float(), C.c_int()
+        L.check(self.lib.fvy_timer_breakdown(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def sync(self):
         L.check(self.lib.fvy_sync(self._h))
 

@@ -8,9 +8,11 @@
     main()                                  reference :951-985
 
 The model is the reference's: Darknet-53 base conv_0..conv_73 (:384-600) + Conv2D(6, 3x3, same, linear)
-(:348-352) -> (B,13,13,6) ``[obj, bx, by, bw, bh, cls]``.  Keras .h5 files cannot be read here (no h5py);
-weights come from a Darknet ``yolov3.weights`` file (backbone) and/or a flat ``face_detector.fvyw`` stream
-(``FaceDetector.save_weights``), else Keras-default random initialisation as in the reference's untrained model.
+(:348-352) -> (B,13,13,6) ``[obj, bx, by, bw, bh, cls]``.  Weights: the reference's own Keras files - ``face_detector.h5``
+(``model_loading``, :329/:337) and ``yolov3_base.h5`` (``yolov3_base_model_load``, :394) - are read with ``h5lite`` (a minimal
+HDF5 reader: h5py is not needed), a Darknet ``yolov3.weights`` file fills the backbone (:398-402), a flat
+``face_detector.fvyw`` stream (``FaceDetector.save_weights``) is the native format, else Keras-default random initialisation
+as in the reference's untrained model.  ``train()`` writes both ``face_detector.fvyw`` and a Keras-layout ``face_detector.h5``.
 """
 from __future__ import annotations
 
@@ -62,10 +64,16 @@ class FaceDetector(object):
                 if s.size != n:
                     raise ValueError(f"{self.WEIGHTS_PATH} holds {s.size} floats, model needs {n}")
                 return s
-            raise FileNotFoundError(f"model_loading is set but {self.WEIGHTS_PATH} does not exist "
-                                    f"({self.MODEL_PATH} is a Keras HDF5 file; h5py is not available in this build)")
+            if os.path.exists(self.MODEL_PATH):                                  # load_model(self.MODEL_PATH), :329 / :337
+                from .. import h5lite
+                return h5lite.keras_h5_to_stream(self.MODEL_PATH, self.specs)
+            raise FileNotFoundError(f"model_loading is set but neither {self.WEIGHTS_PATH} nor {self.MODEL_PATH} exists")
         stream = synth.darknet_stream(self.specs, 0, synth.INIT_KERAS_DEFAULT)   # Keras default init of the untrained model
-        if os.path.exists('yolov3.weights'):                                     # YOLOV3Base, :398-402
+        if self.conf.get('yolov3_base_model_load') and os.path.exists('yolov3_base.h5'):   # load_model('yolov3_base.h5'), :393-396
+            from .. import h5lite
+            base = [c for c in self.specs if c.idx <= 73]
+            stream[:arch.n_params(base)] = h5lite.keras_h5_to_stream('yolov3_base.h5', base)
+        elif os.path.exists('yolov3.weights'):                                   # YOLOV3Base, :398-402
             wr = WeightReader('yolov3.weights')
             n_base = arch.n_params([c for c in self.specs if c.idx <= 73])
             stream[:n_base] = wr.read_bytes(n_base)
@@ -73,6 +81,12 @@ class FaceDetector(object):
 
     def save_weights(self, path=None):
         np.asarray(self._stream, '<f4').tofile(path or self.WEIGHTS_PATH)
+
+    def save_model(self, path=None):
+        """``self.model.save(self.MODEL_PATH)`` (:630): the weights as a Keras 2.2.4 ``model_weights`` tree (nested Darknet-53 base
+        'model_1' + 'output' head), readable by Keras' ``load_weights`` and by this class (``model_loading``)."""
+        from .. import h5lite
+        h5lite.stream_to_keras_h5(path or self.MODEL_PATH, self._stream, self.specs, nested_base='model_1')
 
     def set_weight_stream(self, stream):
         stream = np.ascontiguousarray(stream, np.float32)
@@ -261,19 +275,19 @@ class FaceDetector(object):
         for epoch in range(self.hps['epochs']):
             for i in range(len(seq)):
                 images, gts = seq[i]
-                xs, ts = T.slice_for_rank(images, gts, rank, world)
-                if len(xs) == 0:       # a short last batch may leave a rank without images: it still joins the all-reduce
-                    xs, ts = images[:1], gts[:1]
-                loss = trainer.step(torch.from_numpy(np.ascontiguousarray(xs)), torch.from_numpy(np.ascontiguousarray(ts)))
+                xs, ts = T.slice_for_rank(images, gts, rank, world)      # a short last batch may leave a rank without images: it
+                loss = trainer.step(torch.from_numpy(np.ascontiguousarray(xs)), torch.from_numpy(np.ascontiguousarray(ts)),
+                                    global_batch=len(images))             # contributes zeros and still joins the all-reduce
                 if on_step is not None:
                     on_step(epoch, i, loss)
                 elif DEBUG and rank == 0:
                     print(f"epoch {epoch + 1}/{self.hps['epochs']} step {i + 1}/{len(seq)} loss {loss:.6f}")
         stream = trainer.weight_stream()
+        self.set_weight_stream(stream)
         if rank == 0:
             print('Save the model.')
-            np.asarray(stream, '<f4').tofile(self.WEIGHTS_PATH)
-        self.set_weight_stream(stream)
+            self.save_weights()
+            self.save_model()
 
 
 def main():

@@ -298,6 +298,7 @@ class DataParallelTrainer:
             for p in params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
         self.last_allreduce_bytes = 0
+        self.exchange = True       # False: skip the all-reduce (bench.py measures the exposed communication as the difference)
 
     # -- exchange: a bucket goes out as soon as its last gradient has been accumulated
     def _on_grad(self, p: torch.Tensor) -> None:
@@ -306,7 +307,19 @@ class DataParallelTrainer:
         if self._pending[bi] == 0:
             self._launch(bi)
 
+    def exchange_all(self) -> None:
+        """The step's exchange on its own (every bucket, same order and stream): bench.py times it for the bus bandwidth."""
+        self._handles = []
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        for h in self._handles:
+            h.wait()
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+
     def _launch(self, bi: int) -> None:
+        if not self.exchange:
+            return
         fg = self.flat_g[bi]
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -317,9 +330,24 @@ class DataParallelTrainer:
         self._handles.append(h)
         self.last_allreduce_bytes += fg.numel() * 4
 
-    def step(self, images: torch.Tensor, targets: torch.Tensor) -> float:
+    def step(self, images: torch.Tensor, targets: torch.Tensor, global_batch: Optional[int] = None) -> float:
         """One optimizer step on this rank's slice.  images (b, S, S, 3) NHWC float in [0,1]; targets (b, 13, 13, 6).
-        Returns this rank's loss (Keras 'mse': mean over every element of the slice)."""
+        Returns this rank's loss (Keras 'mse': mean over every element of the slice).
+
+        ``multi_gpu_model`` takes the loss mean over the WHOLE concatenated batch (face_detection.py:366, :369), so a rank whose
+        slice holds b of the B = ``global_batch`` images contributes its mean-loss gradient with weight b / B; with equal slices
+        (the default when ``global_batch`` is None) that is the plain average over ranks.  A rank with an empty slice (short last
+        batch) contributes zeros but still joins every all-reduce."""
+        b_local = int(images.shape[0])
+        weight = 1.0 if global_batch is None else b_local * self.world / float(global_batch)
+        if b_local == 0:
+            for g in self.flat_g:
+                g.zero_()
+            self._handles, self.last_allreduce_bytes = [], 0
+            if self.world > 1:
+                self.exchange_all()
+            self.opt.step(grad_scale=1.0 / self.world)
+            return 0.0
         x = images.to(self.device, non_blocking=True).permute(0, 3, 1, 2).float()
         if self.device.type == "cuda":
             x = x.contiguous(memory_format=torch.channels_last)
@@ -331,12 +359,12 @@ class DataParallelTrainer:
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
             y = self.model(x)
         loss = F.mse_loss(y.float(), t)
-        loss.backward()
+        (loss * weight if weight != 1.0 else loss).backward()
         for h in self._handles:
             h.wait()
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
-        # multi_gpu_model: the loss is the mean over the WHOLE batch -> average of the per-slice mean gradients (equal slices)
+        # multi_gpu_model: the loss is the mean over the WHOLE batch -> sum over ranks of (b_r / B) x the per-slice mean gradient
         self.opt.step(grad_scale=1.0 / self.world)
         return float(loss.detach())
 

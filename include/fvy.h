@@ -180,7 +180,12 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms);
  * synchronises the stream and returns the elapsed milliseconds.  bench.py brackets its K timed steps with it. */
 int fvy_timer_start(fvy_handle* h);
 int fvy_timer_stop(fvy_handle* h, float* ms);
-/* Blocks until all work queued on the handle's stream is done. */
+/* Mean device time (CUDA events inside the timed region, on the streams the kernels run on) of the forward part and of the
+ * post-processing part of the fvy_detect / fvy_detect_async calls made since fvy_timer_start (the last 512 at most): what
+ * bench.py's roofline entries are computed from.  Synchronises the handle's streams. */
+int fvy_timer_breakdown(fvy_handle* h, float* forward_ms_mean, float* post_ms_mean, int* calls);
+/* Blocks until all work queued on the handle's streams is done.  Returns the deferred error of an asynchronous call, if any
+ * (FVY_E_CAPACITY / FVY_E_RANGE: fvy_detect_async returns before the decode has run). */
 int fvy_sync(fvy_handle* h);
 /* Async variants for pipelined serving: enqueue only; results valid after fvy_sync. Host buffers must be pinned. */
 int fvy_detect_async(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp,
