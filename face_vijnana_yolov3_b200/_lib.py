@@ -42,7 +42,7 @@ SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_lo
            "fvy_decode", "fvy_correct_boxes", "fvy_nms", "fvy_bbox_iou", "fvy_postprocess", "fvy_detect", "fvy_num_layers",
            "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
            "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step", "fvy_letterbox_u8", "fvy_staged_images", "fvy_read_staged",
-           "fvy_bbox_iou_fp", "fvy_nms_fp", "fvy_netout_sigmoid", "fvy_timer_breakdown"]
+           "fvy_bbox_iou_fp", "fvy_nms_fp", "fvy_netout_sigmoid", "fvy_timer_breakdown", "fvy_map_match"]
 
 _lib = None
 
@@ -76,6 +76,7 @@ def load():
     L.fvy_nms_fp.restype = C.c_int
     L.fvy_nms_fp.argtypes = [H, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, vp]
     L.fvy_netout_sigmoid.restype = C.c_int; L.fvy_netout_sigmoid.argtypes = [H, vp, C.c_longlong, C.c_int]
+    L.fvy_map_match.restype = C.c_int; L.fvy_map_match.argtypes = [H, vp, vp, vp, vp, C.c_int, vp, vp]
     L.fvy_postprocess.restype = C.c_int
     L.fvy_postprocess.argtypes = [H, vp, vp, vp, C.c_int, C.POINTER(FvyPostParams), vp, C.c_int, vp, vp]
     for name in ("fvy_detect", "fvy_detect_async"):

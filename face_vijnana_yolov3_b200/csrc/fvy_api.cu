@@ -343,6 +343,49 @@ int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batc
     return FVY_OK;
 }
 
+int fvy_map_match(fvy_handle* h, const double* gt_box, const int32_t* gt_off, const double* det_box, const int32_t* det_off, int n_img,
+                  double* det_iou, int32_t* img_any) {
+    if (!h || !gt_off || !det_off || !det_iou || !img_any) return fail(FVY_E_INVALID, "NULL argument");
+    if (n_img < 0) return fail(FVY_E_INVALID, "n_img %d", n_img);
+    if (n_img == 0) return FVY_OK;
+    if (is_device_ptr(gt_off) || is_device_ptr(det_off) || is_device_ptr(det_iou)) return fail(FVY_E_INVALID, "fvy_map_match takes host pointers");
+    const int n_gt = gt_off[n_img], n_det = det_off[n_img];
+    if (gt_off[0] != 0 || det_off[0] != 0 || n_gt < 0 || n_det < 0 || (n_gt > 0 && !gt_box) || (n_det > 0 && !det_box)) return fail(FVY_E_INVALID, "bad offsets");
+    std::vector<long long> pair_off(n_img + 1, 0);
+    for (int i = 0; i < n_img; ++i) {
+        const long long G = gt_off[i + 1] - gt_off[i], D = det_off[i + 1] - det_off[i];
+        if (G < 0 || D < 0) return fail(FVY_E_INVALID, "offsets must be non-decreasing");
+        pair_off[i + 1] = pair_off[i] + G * D;
+    }
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    // transient device buffers: the scorer runs once per result file, off the hot path
+    const size_t b_gt = (size_t)std::max(1, n_gt) * 32, b_det = (size_t)std::max(1, n_det) * 32, b_off = (size_t)(n_img + 1) * 4;
+    const size_t b_po = (size_t)(n_img + 1) * 8, b_pairs = (size_t)std::max<long long>(1, pair_off[n_img]) * 8, b_iou = (size_t)std::max(1, n_det) * 8;
+    const size_t b_any = (size_t)n_img * 4;
+    char* d = nullptr;
+    const size_t offs[8] = {0, b_gt, b_gt + b_det, b_gt + b_det + b_off, b_gt + b_det + 2 * b_off, 0, 0, 0};
+    size_t total = b_gt + b_det + 2 * b_off;
+    total = (total + 7) & ~size_t(7); const size_t o_po = total; total += b_po;
+    const size_t o_pairs = total; total += b_pairs;
+    const size_t o_iou = total; total += b_iou;
+    const size_t o_any = total; total += b_any;
+    CUDA_TRY(cudaMalloc((void**)&d, total));
+    cudaError_t e = cudaSuccess;
+    auto up = [&](size_t off, const void* src, size_t bytes) { if (e == cudaSuccess && bytes && src) e = cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, h->stream); };
+    up(offs[0], gt_box, (size_t)n_gt * 32); up(offs[1], det_box, (size_t)n_det * 32); up(offs[2], gt_off, b_off); up(offs[3], det_off, b_off);
+    up(o_po, pair_off.data(), b_po);
+    MapMatchArgs a;
+    a.gt = (const double*)(d + offs[0]); a.det = (const double*)(d + offs[1]); a.gt_off = (const int*)(d + offs[2]); a.det_off = (const int*)(d + offs[3]);
+    a.pair_off = (const long long*)(d + o_po); a.pair_iou = (double*)(d + o_pairs); a.det_iou = (double*)(d + o_iou); a.img_any = (int*)(d + o_any);
+    if (e == cudaSuccess) { map_match_kernel<<<n_img, 256, 0, h->stream>>>(a); e = cudaGetLastError(); ++h->launches; }
+    if (e == cudaSuccess && n_det) e = cudaMemcpyAsync(det_iou, d + o_iou, (size_t)n_det * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(img_any, d + o_any, b_any, cudaMemcpyDeviceToHost, h->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(FVY_E_CUDA, "fvy_map_match failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return FVY_OK;
+}
+
 int fvy_netout_sigmoid(fvy_handle* h, float* netout, long long n_boxes, int nb_class) {
     if (!h || !netout) return fail(FVY_E_INVALID, "NULL argument");
     if (n_boxes < 0 || nb_class < 1) return fail(FVY_E_INVALID, "bad size");

@@ -616,6 +616,77 @@ __global__ void netout_sigmoid_kernel(float* netout, long long n_boxes, int ch) 
     }
 }
 
+// ---------------------------------------------------------------- cal_mAP_fd matching (evaluate.py:41-100)
+// Per image: IoU of every (ground-truth face i, detection j) pair with bbox_iou on the CSV's numbers (float64 arithmetic: pandas
+// hands np.int64 / np.float64 to BoundBox; integer-valued inputs are exact in double), pairs with IoU > 0 kept (:69-70), then the
+// reference's greedy assignment: repeatedly take the pair with the largest IoU, write it to detection j, drop every pair of
+// row i and of column j (:84-96).  Ties (equal IoU; the reference's sort is unstable): smaller (i, j) first.
+// One block per image; the pair matrix lives in global scratch (pair_off[img] .. pair_off[img + 1]).
+struct MapMatchArgs {
+    const double* gt;        // [n_gt][4]  x1, y1, x2, y2
+    const double* det;       // [n_det][4]
+    const int* gt_off;       // [n_img + 1]
+    const int* det_off;      // [n_img + 1]
+    const long long* pair_off;   // [n_img + 1]
+    double* pair_iou;        // scratch [pair_off[n_img]]
+    double* det_iou;         // [n_det] out: the IoU assigned to the detection, or -1 (the reference's initial value, :31)
+    int* img_any;            // [n_img] out: 1 if the image has at least one pair with IoU > 0 (else the reference skips it, :76)
+};
+__global__ void __launch_bounds__(256) map_match_kernel(const MapMatchArgs a) {
+    __shared__ double s_best[8];
+    __shared__ long long s_idx[8];
+    __shared__ long long s_pick;
+    const int img = blockIdx.x;
+    const int g0 = a.gt_off[img], G = a.gt_off[img + 1] - g0;
+    const int d0 = a.det_off[img], D = a.det_off[img + 1] - d0;
+    double* m = a.pair_iou + a.pair_off[img];
+    const long long n = (long long)G * D;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) a.det_iou[d0 + j] = -1.0;
+    int any = 0;
+    for (long long p = threadIdx.x; p < n; p += blockDim.x) {
+        const int i = (int)(p / D), j = (int)(p - (long long)i * D);
+        const double v = iou_fp<double>(a.gt + 4 * (size_t)(g0 + i), a.det + 4 * (size_t)(d0 + j));
+        const bool pos = v > 0.0;              // nan (zero union) and 0 are dropped
+        m[p] = pos ? v : -1.0;
+        any |= pos ? 1 : 0;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) a.img_any[img] = any;
+    if (!any) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        double best = -1.0; long long bi = -1;
+        for (long long p = threadIdx.x; p < n; p += blockDim.x) {       // ascending p: the first of equal values wins
+            const double v = m[p];
+            if (v > best) { best = v; bi = p; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_idx[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double b = s_best[0]; long long k = s_idx[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (s_best[w] > b || (s_best[w] == b && s_idx[w] >= 0 && (k < 0 || s_idx[w] < k))) { b = s_best[w]; k = s_idx[w]; }
+            s_pick = b > 0.0 ? k : -1;
+            if (b > 0.0) a.det_iou[d0 + (int)(k % D)] = b;                // rel_sol_df.iat[j, -1] = iou   (:92)
+        }
+        __syncthreads();
+        const long long pick = s_pick;
+        if (pick < 0) break;
+        const int pi = (int)(pick / D), pj = (int)(pick - (long long)pi * D);
+        for (long long p = threadIdx.x; p < n; p += blockDim.x) {       // remove assigned samples (:95-96)
+            const int i = (int)(p / D), j = (int)(p - (long long)i * D);
+            if (i == pi || j == pj) m[p] = -1.0;
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- greedy sweep
 struct SweepArgs {
     const unsigned long long* mask;

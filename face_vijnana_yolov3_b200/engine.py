@@ -211,6 +211,18 @@ class Engine:
         gh, gw, nb, ch = netout4.shape
         L.check(self.lib.fvy_netout_sigmoid(self._h, _ptr(netout4), gh * gw * nb, ch - 5))
 
+    def map_match(self, gt_box, gt_off, det_box, det_off):
+        """Matching half of evaluate.cal_mAP_fd (evaluate.py:41-100): -> (det_iou[n_det] float64, img_any[n_img] int32); see fvy_map_match."""
+        gt_box = np.ascontiguousarray(gt_box, np.float64).reshape(-1, 4); det_box = np.ascontiguousarray(det_box, np.float64).reshape(-1, 4)
+        gt_off = np.ascontiguousarray(gt_off, np.int32); det_off = np.ascontiguousarray(det_off, np.int32)
+        n_img = gt_off.size - 1
+        if det_off.size != n_img + 1 or gt_off[-1] != gt_box.shape[0] or det_off[-1] != det_box.shape[0]:
+            raise ValueError("offset arrays do not describe the box arrays")
+        det_iou = np.full(det_box.shape[0], -1.0, np.float64)
+        img_any = np.zeros(max(n_img, 0), np.int32)
+        L.check(self.lib.fvy_map_match(self._h, _ptr(gt_box), _ptr(gt_off), _ptr(det_box), _ptr(det_off), n_img, _ptr(det_iou), _ptr(img_any)))
+        return det_iou, img_any
+
     # ---------------------------------------------------------------- whole path
     def postprocess(self, outs=None, batch=None, pp=None, image_hw=None, max_out=None):
         pp = pp or post_params()

@@ -149,6 +149,15 @@ int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batc
  * caller's array (host or device), n_boxes = grid_h * grid_w * 3. */
 int fvy_netout_sigmoid(fvy_handle* h, float* netout, long long n_boxes, int nb_class);
 
+/* The matching half of evaluate.cal_mAP_fd (src/space/evaluate.py:41-100), row f-4: for each of n_img images, bbox_iou of every
+ * (ground-truth face, detection) pair in float64 (the CSV numbers as pandas hands them to BoundBox), pairs with IoU > 0 kept,
+ * then the greedy assignment "largest IoU first, drop its row and column" (:84-96).  gt_box / det_box: [..][4] x1, y1, x2, y2 with
+ * the boxes of image k at gt_off[k] .. gt_off[k+1] (det_off likewise); det_iou[n_det]: the IoU assigned to each detection or -1;
+ * img_any[n_img]: 1 if the image had any pair with IoU > 0 (the reference skips the others, :76).  Equal IoUs: smaller
+ * (face, detection) index first (the reference's sort leaves ties undefined).  HOST pointers. */
+int fvy_map_match(fvy_handle* h, const double* gt_box, const int32_t* gt_off, const double* det_box, const int32_t* det_off, int n_img,
+                  double* det_iou, int32_t* img_any);
+
 /* Post-processing of resident (or given) logits into detections.
  *   yolo3: decode -> correct_yolo_boxes -> do_nms -> boxes with a surviving class score, candidate order.
  *   fd6:   FaceDetector.detect after predict (face_detection.py:900-947): sigmoid, threshold, box math,

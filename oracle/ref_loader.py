@@ -104,3 +104,32 @@ def make_ref_face_detector(hps, image_size=416, predict_fn=None):
     fd.cell_image_size = image_size // fdm.FaceDetector.CELL_SIZE
     fd.model = types.SimpleNamespace(predict=predict_fn)
     return fd
+
+
+def load_evaluate():
+    """Return the reference ``evaluate`` module (for ``cal_mAP_fd``, evaluate.py:27-127), or None.  h5py is stubbed (only ``main``
+    writes with it).  One pandas shim is installed: the reference does ``sol_df.iat[:, 6] = -1.0`` (evaluate.py:31, :36), which the
+    pandas of its day accepted and pandas >= 1 rejects (``iat`` takes scalar positions); the shim routes a slice key of
+    ``.iat.__setitem__`` to ``.iloc`` - the assignment the line means.  Nothing of the reference's source is altered."""
+    y = load_yolov3_detect()
+    if y is None:
+        return None
+    if "e" in _cache:
+        return _cache["e"]
+    _stub("h5py")
+    import pandas.core.indexing as pci
+    if not getattr(pci._iAtIndexer, "__fvy_shim__", False):
+        orig = pci._iAtIndexer.__setitem__
+
+        def setitem(self, key, value):
+            if isinstance(key, tuple) and any(isinstance(k, slice) for k in key):
+                self.obj.iloc[key] = value
+                return
+            return orig(self, key, value)
+        pci._iAtIndexer.__setitem__ = setitem
+        pci._iAtIndexer.__fvy_shim__ = True
+    import importlib
+    mod = importlib.import_module("evaluate")
+    mod.DEBUG = False
+    _cache["e"] = mod
+    return mod

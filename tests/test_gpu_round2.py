@@ -260,3 +260,54 @@ def test_decode_netout_in_place_sigmoid_and_class_views():
     # an argument that cannot be written in place still decodes (private copy)
     ro = raw.copy(); ro.setflags(write=False)
     assert len(yd.decode_netout(ro, anchors, 1, 0.5, 416, 416)) == len(boxes)
+
+
+# ------------------------------------------------------------------------------------------ row f-4: cal_mAP_fd
+@pytest.mark.parametrize("tag", ["f", "i"])
+@pytest.mark.filterwarnings("ignore")
+def test_cal_mAP_fd_against_reference_vectors(golden_dir, tmp_path, tag):
+    """space.evaluate.cal_mAP_fd (IoU matrix + greedy matching on the GPU) vs the outputs of the reference's own function
+    (tests/golden/map_fd.npz, tools/make_golden.py::map_fd_cases): ps, rs and mAP bit for bit."""
+    from face_vijnana_yolov3_b200.space import evaluate as ev
+    g = np.load(os.path.join(golden_dir, "map_fd.npz"))
+    gt, sol = str(tmp_path / "gt.csv"), str(tmp_path / "sol.csv")
+    open(gt, "w").write(str(g[f"gt_csv_{tag}"])); open(sol, "w").write(str(g[f"sol_csv_{tag}"]))
+    for th in (0.5, 0.75):
+        ps, rs, mAP = ev.cal_mAP_fd(gt, sol, th)
+        k = int(th * 100)
+        assert np.array_equal(ps, g[f"ps_{tag}_{k}"]) and np.array_equal(rs, g[f"rs_{tag}_{k}"]) and mAP == float(g[f"mAP_{tag}_{k}"])
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_cal_mAP_fd_larger_case_matches_oracle(tmp_path):
+    """300 images, up to 40 faces x 60 detections each (the CSV writers cap at 60 rows per file): the GPU matching vs the CPU
+    oracle (itself pinned on the reference), and the reference's res_df quirk when the first image matches nothing."""
+    from face_vijnana_yolov3_b200.space import evaluate as ev
+    from oracle import map_fd as M
+    rng = np.random.default_rng(9)
+    gt_rows, det_rows, fid = ["FACE_ID,FILE,SUBJECT_ID,FACE_X,FACE_Y,FACE_WIDTH,FACE_HEIGHT"], [], 0
+    for k in range(300):
+        f = f"img{k:04d}.jpg"
+        faces = []
+        for _ in range(int(rng.integers(1, 41))):
+            x, y = rng.integers(0, 900, 2); w, h = rng.integers(15, 150, 2)
+            gt_rows.append(f"{fid},{f},{fid},{x},{y},{w},{h}"); fid += 1; faces.append((x, y, w, h))
+        for d in range(int(rng.integers(0, 61))):
+            if d < len(faces) and rng.random() < 0.7:
+                x, y, w, h = faces[d]
+                x, y, w, h = x + rng.normal(0, 8), y + rng.normal(0, 8), w * rng.uniform(0.7, 1.3), h * rng.uniform(0.7, 1.3)
+            else:
+                x, y = rng.uniform(0, 900, 2); w, h = rng.uniform(15, 150, 2)
+            det_rows.append(",".join([f] + [repr(float(v)) for v in (x, y, w, h, rng.random())]))
+    gt, sol = str(tmp_path / "gt.csv"), str(tmp_path / "sol.csv")
+    open(gt, "w").write("\n".join(gt_rows) + "\n"); open(sol, "w").write("\n".join(det_rows) + "\n")
+    for th in (0.5, 0.8):
+        a = ev.cal_mAP_fd(gt, sol, th); b = M.cal_mAP_fd(gt, sol, th)
+        assert len(a[0]) > 3000 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    # first image (sorted file order) has detections that overlap nothing, a later one matches: the reference hits an unbound res_df
+    open(gt, "w").write(gt_rows[0] + "\n0,a.jpg,0,10,10,50,50\n1,b.jpg,1,10,10,50,50\n")
+    open(sol, "w").write("a.jpg,500.0,500.0,20.0,20.0,0.9\nb.jpg,12.0,12.0,50.0,50.0,0.8\n")
+    with pytest.raises(UnboundLocalError):
+        ev.cal_mAP_fd(gt, sol, 0.5)
+    with pytest.raises(UnboundLocalError):
+        M.cal_mAP_fd(gt, sol, 0.5)

@@ -88,3 +88,34 @@ def test_live_reference_matches_oracle():
     Y.do_nms(bsub, 0.45)
     cls = P.do_nms(rib[sub], rc[sub], 0.45)
     assert np.array_equal(np.array([b.classes[0] for b in bsub], np.float32), cls[:, 0])
+
+
+def _write_map_case(g, tag, d):
+    gt, sol = os.path.join(d, "gt.csv"), os.path.join(d, "sol.csv")
+    open(gt, "w").write(str(g[f"gt_csv_{tag}"])); open(sol, "w").write(str(g[f"sol_csv_{tag}"]))
+    return gt, sol
+
+
+@pytest.mark.parametrize("tag", ["f", "i"])
+@pytest.mark.filterwarnings("ignore")
+def test_map_fd_oracle_against_reference_vectors(golden_dir, tmp_path, tag):
+    """oracle/map_fd.py vs the outputs of the reference's own cal_mAP_fd (evaluate.py:27-127): ps, rs and mAP bit for bit."""
+    from oracle import map_fd as M
+    g = np.load(os.path.join(golden_dir, "map_fd.npz"))
+    gt, sol = _write_map_case(g, tag, str(tmp_path))
+    for th in (0.5, 0.75):
+        ps, rs, mAP = M.cal_mAP_fd(gt, sol, th)
+        k = int(th * 100)
+        assert np.array_equal(ps, g[f"ps_{tag}_{k}"]) and np.array_equal(rs, g[f"rs_{tag}_{k}"]) and mAP == float(g[f"mAP_{tag}_{k}"])
+
+
+@pytest.mark.skipif(not R.available(), reason="needs /root/reference (build container only)")
+@pytest.mark.filterwarnings("ignore")
+def test_map_fd_oracle_against_live_reference(golden_dir, tmp_path):
+    from oracle import map_fd as M
+    E = R.load_evaluate()
+    g = np.load(os.path.join(golden_dir, "map_fd.npz"))
+    gt, sol = _write_map_case(g, "f", str(tmp_path))
+    for th in (0.5, 0.6, 0.9):
+        a = E.cal_mAP_fd(gt, sol, th); b = M.cal_mAP_fd(gt, sol, th)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]

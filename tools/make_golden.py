@@ -14,6 +14,9 @@ as small fixtures (this script is their provenance):
   post_yolo3_mc.npz       the same pipeline with nb_class = 3: pins the per-class loop of do_nms (:431-444) on the reference itself.
   post_float.npz          reference bbox_iou / do_nms called on FLOAT boxes (before correct_yolo_boxes): np.float32 coordinates as this
                           NumPy's decode_netout returns them (float32 arithmetic) and the same boxes as Python floats (float64).
+  map_fd.npz              reference evaluate.cal_mAP_fd (src/space/evaluate.py:27-127) on synthetic ground-truth / detection CSVs: the
+                          CSV texts and the (ps, rs, mAP) it returns for several IoU thresholds (run under the one-line pandas shim
+                          of oracle/ref_loader.py::load_evaluate).
   letterbox.npz           the image the reference's own FaceDetector.test() loop (src/space/face_detection.py:798-835, cv2 of this
                           image) hands to detect(), for seeded uint8 images written as PNG-exact BMP files, image_size 64
   gt_tensor.npz           reference TrainingSequence.__getitem__ ground-truth tensors (src/space/face_detection.py:98-310)
@@ -158,6 +161,50 @@ def float_box_cases():
           "differ", int(((after32 > 0) != (after64 > 0)).sum()))
 
 
+def map_fd_cases():
+    """Reference cal_mAP_fd on two synthetic result sets: float detections (what FaceDetector.test writes after the un-letterbox
+    scaling) and integer-valued ones (pandas parses int64: the integer IoU path).  Covers: several faces / detections per image,
+    an image without detections, an image whose detections overlap no face (skipped by the reference, evaluate.py:76), a detection
+    file absent from the ground truth."""
+    import tempfile
+    import pandas as pd
+    E = R.load_evaluate()
+    out = {}
+    for tag, as_int in (("f", False), ("i", True)):
+        rng = np.random.default_rng(3 if not as_int else 4)
+        rows, det, fid = [], [], 0
+        for k in range(12):
+            f = f"im{k:02d}.jpg"
+            gts = []
+            for _ in range(int(rng.integers(1, 6))):
+                x, y = rng.integers(0, 300, 2); w, h = rng.integers(20, 120, 2)
+                rows.append([fid, f, 1000 + fid, int(x), int(y), int(w), int(h)]); fid += 1; gts.append((x, y, w, h))
+            if k == 4:
+                continue                                            # no detections for this image
+            for d in range(int(rng.integers(1, 9))):
+                if k == 7:
+                    x, y, w, h = 1000 + 10 * d, 1000, 20, 20        # overlaps nothing: the image is skipped
+                elif d < len(gts) and rng.random() < 0.8:
+                    x, y, w, h = gts[d]; x = x + rng.normal(0, 6); y = y + rng.normal(0, 6); w = w * rng.uniform(0.8, 1.2); h = h * rng.uniform(0.8, 1.2)
+                else:
+                    x, y = rng.uniform(0, 300, 2); w, h = rng.uniform(20, 120, 2)
+                v = [int(round(x)), int(round(y)), int(round(w)), int(round(h))] if as_int else [float(x), float(y), float(w), float(h)]
+                det.append([f] + v + [float(rng.random())])
+        det.append(["not_in_gt.jpg", 5, 5, 50, 50, 0.9] if as_int else ["not_in_gt.jpg", 5.0, 5.0, 50.0, 50.0, 0.9])
+        with tempfile.TemporaryDirectory() as d:
+            gt_path, sol_path = os.path.join(d, "gt.csv"), os.path.join(d, "sol.csv")
+            pd.DataFrame(rows, columns=["FACE_ID", "FILE", "SUBJECT_ID", "FACE_X", "FACE_Y", "FACE_WIDTH", "FACE_HEIGHT"]).to_csv(gt_path, index=False)
+            pd.DataFrame(det).to_csv(sol_path, index=False, header=False)
+            out[f"gt_csv_{tag}"] = open(gt_path).read(); out[f"sol_csv_{tag}"] = open(sol_path).read()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for th in (0.5, 0.75):
+                    ps, rs, mAP = E.cal_mAP_fd(gt_path, sol_path, th)
+                    out[f"ps_{tag}_{int(th * 100)}"] = ps; out[f"rs_{tag}_{int(th * 100)}"] = rs; out[f"mAP_{tag}_{int(th * 100)}"] = mAP
+                    print("map_fd", tag, th, "rows", len(ps), "mAP", mAP)
+    np.savez_compressed(os.path.join(OUT, "map_fd.npz"), **out)
+
+
 def gt_tensor_cases():
     """Reference TrainingSequence.__getitem__ (src/space/face_detection.py:98-310) on synthetic images + training.csv."""
     import tempfile
@@ -242,6 +289,7 @@ if __name__ == "__main__":
     post_yolo3("c", seed=23, image_hw=(500, 375), obj_thresh=0.5, nms_thresh=0.3)
     post_yolo3("mc", seed=25, image_hw=(416, 416), obj_thresh=0.6, nms_thresh=0.45, nb_class=3)
     float_box_cases()
+    map_fd_cases()
     post_fd6()
     iou_cases()
     gt_tensor_cases()
