@@ -559,6 +559,10 @@ def run_train(args, D):
 
     sampler = ClockSampler(local)
     sampler.start()
+    tr_base = T.DataParallelTrainer(hps, device=f"cuda:{local}", stream=stream, bucket_mb=args.bucket_mb, autocast_bf16=False, fvy_bn=False)
+    ms_cudnn, _ = timed(tr_base, args.steps)       # the stated baseline: every layer on torch autograd / cuDNN
+    del tr_base
+    torch.cuda.empty_cache()
     tr = T.DataParallelTrainer(hps, device=f"cuda:{local}", stream=stream, bucket_mb=args.bucket_mb, autocast_bf16=False)
     sampler.mark()
     ms, loss = timed(tr, args.steps)
@@ -593,9 +597,12 @@ def run_train(args, D):
                 "exchange": {"allreduce_bytes_per_step": nbytes if world > 1 else 0, "buckets": n_buckets, "bucket_mb": args.bucket_mb,
                              "allreduce_alone_ms": ar_ms, "bus_GBps": (2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
                              "step_ms_without_exchange": ms_noex, "exposed_communication_ms": max(0.0, ms - ms_noex)},
+                "baseline_all_cudnn": {"ms_per_step": ms_cudnn, "value": GB / (ms_cudnn * 1e-3),
+                                       "note": "the same fp32 step with BatchNorm / LeakyReLU on torch's modules as well (everything library code)"},
                 "bf16_autocast": {"ms_per_step": ms16, "value": GB / (ms16 * 1e-3), "note": "narrower arithmetic than the reference's training; not the parity number"},
-                "compute": "conv / BatchNorm forward + backward: torch autograd over cuDNN (library code, the stated baseline of row f-1); hand-written: "
-                           "bucketed exchange + overlap, fvy_adam_step, BatchNorm batch-statistics kernels (fvy_bn_*), weight-stream interop",
+                "compute": "hand-written: BatchNorm (batch statistics) + LeakyReLU forward / backward for all 52 pairs (fvy_bn_leaky_train_*), Keras Adam "
+                           "(fvy_adam_step), bucketed exchange + overlap, weight-stream interop; conv forward / dgrad / wgrad: torch autograd over cuDNN "
+                           "(library code - the part of row f-1 still open)",
                 "roofline": None, "cpu_baseline": None, "e2e": {"value": GB / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(xs.numel() * 4 + ts.numel() * 4),
                                                                "d2h_bytes_per_step": 4, "note": "every step copies its images / targets from pinned host memory and reads the loss back"},
                 "gpu_launches": None, "clocks": clocks}

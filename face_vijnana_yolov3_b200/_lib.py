@@ -42,7 +42,8 @@ SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_lo
            "fvy_decode", "fvy_correct_boxes", "fvy_nms", "fvy_bbox_iou", "fvy_postprocess", "fvy_detect", "fvy_num_layers",
            "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
            "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step", "fvy_letterbox_u8", "fvy_staged_images", "fvy_read_staged",
-           "fvy_bbox_iou_fp", "fvy_nms_fp", "fvy_netout_sigmoid", "fvy_timer_breakdown", "fvy_map_match"]
+           "fvy_bbox_iou_fp", "fvy_nms_fp", "fvy_netout_sigmoid", "fvy_timer_breakdown", "fvy_map_match",
+           "fvy_bn_leaky_train_forward", "fvy_bn_leaky_train_backward"]
 
 _lib = None
 
@@ -100,6 +101,10 @@ def load():
     L.fvy_timer_breakdown.restype = C.c_int; L.fvy_timer_breakdown.argtypes = [H, fp, fp, ip]
     L.fvy_host_alloc.restype = C.c_void_p; L.fvy_host_alloc.argtypes = [C.c_size_t]
     L.fvy_host_free.restype = None; L.fvy_host_free.argtypes = [C.c_void_p]
+    L.fvy_bn_leaky_train_forward.restype = C.c_int
+    L.fvy_bn_leaky_train_forward.argtypes = [vp, C.c_longlong, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    L.fvy_bn_leaky_train_backward.restype = C.c_int
+    L.fvy_bn_leaky_train_backward.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp]
     L.fvy_adam_step.restype = C.c_int
     L.fvy_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     _lib = L

@@ -238,7 +238,7 @@ int fvy_nms(fvy_handle* h, const int32_t* ibox, const int32_t* counts, int batch
         d_ibox = h->d_ibox; d_cls = h->d_cls; d_counts = h->d_counts;
     }
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
-    if (int e = nms_enqueue(h, d_ibox, d_cls, d_counts, batch, seg_stride, nb_class, nms_thresh)) return e;
+    if (int e = nms_enqueue(h, d_ibox, d_cls, d_counts, batch, seg_stride, nb_class, nms_thresh, seg_stride)) return e;
     if (kept_idx || kept_counts) {
         AssembleArgs a;
         a.ibox = d_ibox; a.objness = nullptr; a.classes = d_cls; a.cand = nullptr; a.counts = d_counts;
@@ -323,8 +323,7 @@ int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batc
         SweepArgs w;
         w.mask = h->d_mask; w.order = h->d_order; w.counts = h->d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
         w.nb_class = nb_class; w.cls = c; w.classes = h->d_cls; w.rowflag = h->d_rowflag;
-        nms_sweep_kernel<<<batch, 1024, (size_t)h->words * 8, h->stream>>>(w);
-        CUDA_TRY(cudaGetLastError());
+        if (int e = launch_sweep(h, w, batch, seg_stride, h->stream)) return e;
         h->launches += 3;
     }
     if (kept_idx || kept_counts) {
@@ -756,6 +755,54 @@ int fvy_adam_step(float* param, const float* grad, float* m, float* v, long long
     const long long want = ((n >> 2) + 255) / 256;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
     adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(param, grad, m, v, n, lr_t, beta_1, beta_2, epsilon, grad_scale);
+    CUDA_TRY(cudaGetLastError());
+    return FVY_OK;
+}
+
+static int bn_check(const void* x, long long rows, int C, const void* ws) {
+    if (!x || !ws || rows < 1 || C < 4 || (C & 3)) return fail(FVY_E_INVALID, "fvy_bn_leaky_*: bad argument (rows %lld, C %d: C must be a positive multiple of 4)", rows, C);
+    if (!is_device_ptr(x) || !is_device_ptr(ws)) return fail(FVY_E_INVALID, "fvy_bn_leaky_* take device pointers (there is no CPU path)");
+    if (reinterpret_cast<uintptr_t>(x) & 15) return fail(FVY_E_INVALID, "fvy_bn_leaky_*: activations must be 16-byte aligned");
+    return FVY_OK;
+}
+static void bn_grids(long long rows, int C, dim3* sums, int* apply) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int cy = (C + 127) / 128;
+    const long long want = (rows + 7) / 8;
+    *sums = dim3((unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8 / cy + 1)), cy);
+    *apply = (int)std::max<long long>(1, std::min<long long>((rows * C / 4 + 255) / 256, (long long)sms * 16));
+}
+
+int fvy_bn_leaky_train_forward(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps, float momentum, float slope,
+                               float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd, double* workspace,
+                               void* cuda_stream) {
+    if (int e = bn_check(x, rows, C, workspace)) return e;
+    if (!gamma || !beta || !y || !save_mean || !save_invstd) return fail(FVY_E_INVALID, "fvy_bn_leaky_train_forward: NULL argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    dim3 gs; int ga;
+    bn_grids(rows, C, &gs, &ga);
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)2 * C * sizeof(double), st));
+    bn_sums_kernel<0><<<gs, kBnThreads, 0, st>>>(x, nullptr, rows, C, nullptr, nullptr, nullptr, nullptr, slope, workspace);
+    bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, rows, C, eps, momentum, running_mean, running_var, save_mean, save_invstd);
+    bn_fwd_apply_kernel<<<ga, 256, 0, st>>>(x, rows * C / 4, C, gamma, beta, save_mean, save_invstd, slope, y);
+    CUDA_TRY(cudaGetLastError());
+    return FVY_OK;
+}
+
+int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows, int C, const float* gamma, const float* beta, const float* save_mean,
+                                const float* save_invstd, float slope, float* dx, float* dgamma, float* dbeta, double* workspace, void* cuda_stream) {
+    if (int e = bn_check(x, rows, C, workspace)) return e;
+    if (!dy || !gamma || !beta || !save_mean || !save_invstd || !dx || !dgamma || !dbeta) return fail(FVY_E_INVALID, "fvy_bn_leaky_train_backward: NULL argument");
+    if (reinterpret_cast<uintptr_t>(dy) & 15) return fail(FVY_E_INVALID, "fvy_bn_leaky_train_backward: gradients must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    dim3 gs; int ga;
+    bn_grids(rows, C, &gs, &ga);
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)2 * C * sizeof(double), st));
+    bn_sums_kernel<1><<<gs, kBnThreads, 0, st>>>(x, dy, rows, C, gamma, beta, save_mean, save_invstd, slope, workspace);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, dgamma, dbeta);
+    bn_bwd_apply_kernel<<<ga, 256, 0, st>>>(x, dy, rows * C / 4, rows, C, gamma, beta, save_mean, save_invstd, slope, workspace, dx);
     CUDA_TRY(cudaGetLastError());
     return FVY_OK;
 }

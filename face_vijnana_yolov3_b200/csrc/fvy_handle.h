@@ -23,6 +23,7 @@
 
 #include "stem_kernel.cuh"
 #include "prepost_kernels.cuh"
+#include "train_kernels.cuh"
 
 namespace fvy {
 
@@ -197,7 +198,7 @@ struct fvy_handle {
     int cap = 0, capP = 0, words = 0, np2max = 0, smem_keys = 0;
     double* d_nbox = nullptr;
     int* d_ibox = nullptr; float* d_obj = nullptr; float* d_cls = nullptr; int* d_cand = nullptr; int* d_counts = nullptr;
-    int* d_status = nullptr; int* d_image_hw = nullptr;
+    int* d_status = nullptr; size_t status_bytes = 16; int* d_image_hw = nullptr;
     int* d_order = nullptr; int4* d_sbox = nullptr; unsigned long long* d_mask = nullptr; unsigned long long* d_gkeys = nullptr;
     unsigned long long* d_rowflag = nullptr;
     int* d_kept = nullptr; int* d_kept_counts = nullptr;

@@ -34,7 +34,11 @@ static int build_post(fvy_handle* h) {
     if (int e = dev_alloc(h, (void**)&h->d_cls, n * nc * 4, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_cand, n * 4, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_counts, (size_t)B * 4, true)) return e;
-    if (int e = dev_alloc(h, (void**)&h->d_status, 16, true)) return e;
+    // status word (16 bytes) + the decode kernel's per-image chunk tickets / counts, zeroed together before every decode
+    h->status_bytes = 16 + (size_t)B * (1 + kDecodeMaxChunks) * sizeof(int);
+    if (int e = dev_alloc(h, (void**)&h->d_status, h->status_bytes, true)) return e;
+    if ((total_cands(h) + kDecodeChunk - 1) / kDecodeChunk > kDecodeMaxChunks)
+        return fail(FVY_E_INVALID, "network input %dx%d has more candidate slots than the decode kernel's %d chunks cover", c.net_h, c.net_w, kDecodeMaxChunks);
     if (int e = dev_alloc(h, (void**)&h->d_image_hw, (size_t)B * 8, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_order, (size_t)B * h->capP * 4, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_sbox, (size_t)B * h->capP * 16, true)) return e;
@@ -49,6 +53,7 @@ static int build_post(fvy_handle* h) {
     if (int e = dev_alloc(h, (void**)&h->d_det_counts, (size_t)B * 4, true)) return e;
     // a function attribute is per device, not per handle: always raise it to the largest key buffer any handle may use
     CUDA_TRY(cudaFuncSetAttribute(sort_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    CUDA_TRY(cudaFuncSetAttribute(nms_sweep_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_small_smem(kSweepMaxBlocks)));
     return FVY_OK;
 }
 
@@ -83,7 +88,7 @@ static int upload_image_hw(fvy_handle* h, const int* image_hw, int batch, const 
 }
 
 static int decode_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy_post_params* pp, const int* d_hw, bool want_nbox) {
-    CUDA_TRY(cudaMemsetAsync(h->d_status, 0, 4, h->ps));
+    CUDA_TRY(cudaMemsetAsync(h->d_status, 0, h->status_bytes, h->ps));
     if (h->cfg.head == FVY_HEAD_FD6) {
         DecodeFd6Args a;
         a.cands = dev[0]; a.grid = h->gh[0]; a.image_size = h->cfg.net_h; a.cell_px = h->cfg.net_h / 13;
@@ -100,16 +105,32 @@ static int decode_enqueue(fvy_handle* h, const float* dev[3], int batch, const f
         a.image_hw = d_hw; a.cap = h->cap;
         a.nbox = want_nbox ? h->d_nbox : nullptr; a.ibox = h->d_ibox; a.objness = h->d_obj; a.classes = h->d_cls;
         a.cand = h->d_cand; a.counts = h->d_counts; a.status = h->d_status;
-        decode_yolo_kernel<<<batch, 1024, 0, h->ps>>>(a);
+        const int chunks = (total_cands(h) + kDecodeChunk - 1) / kDecodeChunk;
+        decode_yolo_kernel<<<dim3(chunks, batch), kDecodeThreads, 0, h->ps>>>(a, h->d_status + 4);
     }
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     return FVY_OK;
 }
 
+// The greedy sweep: segments of at most kSweepMaxBlocks x 64 boxes (the handle's capacity decides: headline configurations, fd6)
+// take nms_sweep_small_kernel (everything the per-block chain needs staged in shared memory), larger ones nms_sweep_kernel.
+static int launch_sweep(fvy_handle* h, const SweepArgs& w, int batch, int max_n, cudaStream_t st) {
+    static const int force_big = [] { const char* v = getenv("FVY_SWEEP_BIG"); return v && *v ? atoi(v) : 0; }();
+    const int nb_max = (std::min(std::min(w.seg_stride, h->cap), std::max(1, max_n)) + 63) / 64;      // max_n: a bound on the boxes per segment
+    if (nb_max <= kSweepMaxBlocks && !force_big) {
+        nms_sweep_small_kernel<<<batch, kSweepThreads, sweep_small_smem(nb_max), st>>>(w, nb_max);
+    } else {
+        static const int sweep_threads = [] { const char* v = getenv("FVY_SWEEP_THREADS"); const int t = v && *v ? atoi(v) : 1024; return t >= 128 && t <= 1024 && t % 32 == 0 ? t : 1024; }();
+        nms_sweep_kernel<<<batch, sweep_threads, (size_t)h->words * 8, st>>>(w);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FVY_OK;
+}
+
 // NMS over device-resident segments (ibox/classes with stride `seg_stride`, counts on device)
 static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int* d_counts, int batch, int seg_stride, int nb_class,
-                       double th) {
+                       double th, int max_n) {
     for (int c = 0; c < nb_class; ++c) {
         SortArgs s;
         s.ibox = d_ibox; s.classes = d_cls; s.counts = d_counts; s.seg_stride = seg_stride; s.nb_class = nb_class; s.cls = c;
@@ -126,9 +147,7 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
         SweepArgs w;
         w.mask = h->d_mask; w.order = h->d_order; w.counts = d_counts; w.seg_stride = seg_stride; w.capP = h->capP; w.words = h->words;
         w.nb_class = nb_class; w.cls = c; w.classes = d_cls; w.rowflag = h->d_rowflag;
-        static const int sweep_threads = [] { const char* v = getenv("FVY_SWEEP_THREADS"); const int t = v && *v ? atoi(v) : 1024; return t >= 128 && t <= 1024 && t % 32 == 0 ? t : 1024; }();
-        nms_sweep_kernel<<<batch, sweep_threads, (size_t)h->words * 8, h->ps>>>(w);
-        CUDA_TRY(cudaGetLastError());
+        if (int e = launch_sweep(h, w, batch, max_n, h->ps)) return e;
         h->launches += 3;
     }
     return FVY_OK;
@@ -137,7 +156,14 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
 static int post_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy_post_params* pp, const int* d_hw, int max_out) {
     if (int e = decode_enqueue(h, dev, batch, pp, d_hw, false)) return e;
     const int nc = h->cfg.head == FVY_HEAD_FD6 ? 1 : h->cfg.nb_class;
-    if (int e = nms_enqueue(h, h->d_ibox, h->d_cls, h->d_counts, batch, h->cap, nc, pp->nms_thresh)) return e;
+    // the most candidates the anchor mask lets an image have (the sweep sizes its shared memory from it)
+    int max_n = h->cap;
+    if (h->cfg.head != FVY_HEAD_FD6) {
+        max_n = 0;
+        for (int s = 0; s < 3; ++s) max_n += __builtin_popcount((pp->anchor_mask >> (3 * s)) & 7u) * h->gh[s] * h->gw[s];
+        max_n = std::min(max_n, h->cap);
+    }
+    if (int e = nms_enqueue(h, h->d_ibox, h->d_cls, h->d_counts, batch, h->cap, nc, pp->nms_thresh, max_n)) return e;
     AssembleArgs a;
     a.ibox = h->d_ibox; a.objness = h->d_obj; a.classes = h->d_cls; a.cand = h->d_cand; a.counts = h->d_counts;
     a.seg_stride = h->cap; a.nb_class = nc; a.max_out = max_out;

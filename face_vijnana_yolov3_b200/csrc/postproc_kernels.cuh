@@ -113,77 +113,146 @@ __device__ __forceinline__ int correct_coord(double v, double off, double scale,
     return trunc_to_i32((double)t, range_flag);
 }
 
-__global__ void __launch_bounds__(1024) decode_yolo_kernel(const DecodeArgs a) {
+// Grid (chunks, images): a block of 256 threads decodes kDecodeChunk consecutive candidate slots of one image (4 per thread, in the
+// reference's (scale, row, col, anchor) order), scans its pass flags and writes compacted records - so candidate order is the
+// reference's.  The position of a chunk's first survivor is the sum of the survivor counts of the image's earlier chunks: chunks take
+// a ticket when they START (so every earlier chunk of the image is resident or finished: no deadlock whatever else shares the GPU),
+// publish their count with a release store and read the earlier ones with acquire loads ("chained scan").  The six floats of a
+// face-head record (24 bytes, 8-byte aligned) are read as three float2.  `sync` = [images][1 + kDecodeMaxChunks] ints, zeroed by the
+// caller: [0] ticket, [1 + c] = (count << 1) | 1 once chunk c has published.
+constexpr int kDecodeThreads = 256, kDecodePer = 4, kDecodeChunk = kDecodeThreads * kDecodePer, kDecodeMaxChunks = 63;
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu_i(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(kDecodeThreads) decode_yolo_kernel(const DecodeArgs a, int* __restrict__ sync) {
     __shared__ int ws[33];
+    __shared__ int s_chunk, s_prefix;
     __shared__ LetterboxConst lb;
-    const int img = blockIdx.x;
+    const int img = blockIdx.y;
     const int ch = 5 + a.nb_class;
     const int C = 3 * ch;
     const int n0 = 3 * a.gh[0] * a.gw[0], n1 = n0 + 3 * a.gh[1] * a.gw[1], n2 = n1 + 3 * a.gh[2] * a.gw[2];
-    if (threadIdx.x == 0 && a.image_hw != nullptr)
-        lb = letterbox_const(a.image_hw[2 * img], a.image_hw[2 * img + 1], a.net_h, a.net_w);
-    __syncthreads();
-    int base = 0;
-    int range_flag = 0;
-    for (int start = 0; start < n2; start += blockDim.x) {
-        const int g = start + threadIdx.x;
-        bool pass = false;
-        const float* t = nullptr;
-        int s = 0, cell = 0, b = 0;
-        float obj = 0.f;
-        if (g < n2) {
-            s = g < n0 ? 0 : (g < n1 ? 1 : 2);
-            const int local = g - (s == 0 ? 0 : (s == 1 ? n0 : n1));
-            cell = local / 3; b = local - 3 * cell;
-            if ((a.anchor_mask >> (3 * s + b)) & 1u) {                                  // :354-362
-                t = a.out[s] + ((size_t)img * a.gh[s] * a.gw[s] + cell) * C + b * ch;
-                obj = sigmoid_ref(__ldg(t + 4));                                        // :344
-                const bool below = a.arith == 0 ? ((double)obj < a.obj_thresh) : (obj < (float)a.obj_thresh);
-                pass = !below;                                                          // :368
-            }
-        }
-        int total;
-        const int pos = base + block_scan_flag(pass, ws, &total);
-        if (pass && pos < a.cap) {
-            const int gw = a.gw[s], gh = a.gh[s];
-            const int row = cell / gw, col = cell - row * gw;                           // :349-350
-            const float sx = sigmoid_ref(__ldg(t + 0)), sy = sigmoid_ref(__ldg(t + 1)); // :343
-            const float ew = exp_cr_f32(__ldg(t + 2)), eh = exp_cr_f32(__ldg(t + 3));   // :375-376
-            const int aw = a.anchors[6 * s + 2 * b], ah = a.anchors[6 * s + 2 * b + 1];
-            double x0, y0, x1, y1;
-            if (a.arith == 0) {
-                const double x = __ddiv_rn(__dadd_rn((double)col, (double)sx), (double)gw);   // :373
-                const double y = __ddiv_rn(__dadd_rn((double)row, (double)sy), (double)gh);   // :374
-                const double w = __ddiv_rn(__dmul_rn((double)aw, (double)ew), (double)a.net_w);   // :375
-                const double h = __ddiv_rn(__dmul_rn((double)ah, (double)eh), (double)a.net_h);   // :376
-                const double hw = __ddiv_rn(w, 2.0), hh = __ddiv_rn(h, 2.0);
-                x0 = __dsub_rn(x, hw); y0 = __dsub_rn(y, hh); x1 = __dadd_rn(x, hw); y1 = __dadd_rn(y, hh);   // :383
-            } else {
-                const float x = __fdiv_rn(__fadd_rn((float)col, sx), (float)gw);
-                const float y = __fdiv_rn(__fadd_rn((float)row, sy), (float)gh);
-                const float w = __fdiv_rn(__fmul_rn((float)aw, ew), (float)a.net_w);
-                const float h = __fdiv_rn(__fmul_rn((float)ah, eh), (float)a.net_h);
-                const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-                x0 = __fsub_rn(x, hw); y0 = __fsub_rn(y, hh); x1 = __fadd_rn(x, hw); y1 = __fadd_rn(y, hh);
-            }
-            const size_t o = (size_t)img * a.cap + pos;
-            if (a.nbox) { double* d = a.nbox + 4 * o; d[0] = x0; d[1] = y0; d[2] = x1; d[3] = y1; }
-            if (a.ibox && a.image_hw) {
-                int4 q;
-                q.x = correct_coord(x0, lb.x_off, lb.x_scale, lb.image_w, a.arith, &range_flag);
-                q.y = correct_coord(y0, lb.y_off, lb.y_scale, lb.image_h, a.arith, &range_flag);
-                q.z = correct_coord(x1, lb.x_off, lb.x_scale, lb.image_w, a.arith, &range_flag);
-                q.w = correct_coord(y1, lb.y_off, lb.y_scale, lb.image_h, a.arith, &range_flag);
-                reinterpret_cast<int4*>(a.ibox)[o] = q;
-            }
-            if (a.objness) a.objness[o] = obj;
-            if (a.classes)
-                for (int c = 0; c < a.nb_class; ++c) a.classes[o * a.nb_class + c] = sigmoid_ref(__ldg(t + 5 + c));   // :344
-            if (a.cand) a.cand[o] = g;
-        }
-        base += total;
+    int* isync = sync + (size_t)img * (1 + kDecodeMaxChunks);
+    if (threadIdx.x == 0) {
+        s_chunk = atomicAdd(isync, 1);
+        if (a.image_hw != nullptr) lb = letterbox_const(a.image_hw[2 * img], a.image_hw[2 * img + 1], a.net_h, a.net_w);
     }
-    if (threadIdx.x == 0) a.counts[img] = base;
+    __syncthreads();
+    const int chunk = s_chunk;
+    const int g0 = chunk * kDecodeChunk + threadIdx.x * kDecodePer;
+    // pass flags of this thread's four slots (objectness only: one exp per masked-in slot)
+    const float* rec[kDecodePer];
+    float obj[kDecodePer];
+    int sc[kDecodePer], cell[kDecodePer], bb[kDecodePer];
+    unsigned pass = 0;
+#pragma unroll
+    for (int k = 0; k < kDecodePer; ++k) {
+        const int g = g0 + k;
+        rec[k] = nullptr; obj[k] = 0.f; sc[k] = 0; cell[k] = 0; bb[k] = 0;
+        if (g < n2) {
+            const int s = g < n0 ? 0 : (g < n1 ? 1 : 2);
+            const int local = g - (s == 0 ? 0 : (s == 1 ? n0 : n1));
+            const int c = local / 3, b = local - 3 * c;
+            if ((a.anchor_mask >> (3 * s + b)) & 1u) {                                  // :354-362
+                const float* t = a.out[s] + ((size_t)img * a.gh[s] * a.gw[s] + c) * C + b * ch;
+                const float o = sigmoid_ref(__ldg(t + 4));                              // :344
+                const bool below = a.arith == 0 ? ((double)o < a.obj_thresh) : (o < (float)a.obj_thresh);
+                if (!below) { pass |= 1u << k; rec[k] = t; obj[k] = o; sc[k] = s; cell[k] = c; bb[k] = b; }   // :368
+            }
+        }
+    }
+    // exclusive scan of the per-thread survivor counts inside the chunk
+    const int mine = __popc(pass);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = lane < kDecodeThreads / 32 ? ws[lane] : 0;
+        int in2 = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, in2, d);
+            if (lane >= d) in2 += t;
+        }
+        ws[lane] = in2 - v;
+        if (lane == 31) ws[32] = in2;
+        // publish this chunk's count, then add up the earlier chunks' (spinning until each has published)
+        if (lane == 0) st_release_gpu(isync + 1 + chunk, (in2 << 1) | 1);
+        int before = 0;
+        for (int c = lane; c < chunk; c += 32) {
+            int v2;
+            for (unsigned spin = 0; ((v2 = ld_acquire_gpu_i(isync + 1 + c)) & 1) == 0; ++spin) {
+                __nanosleep(40);
+                if (spin > (1u << 24)) { printf("fvy: decode chunk wait timed out (image %d chunk %d of %d)\n", img, c, chunk); __trap(); }
+            }
+            before += v2 >> 1;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+        if (lane == 0) s_prefix = before;
+    }
+    __syncthreads();
+    const int total = ws[32];
+    int pos = s_prefix + ws[warp] + (incl - mine);
+    if (threadIdx.x == 0 && (chunk + 1) * kDecodeChunk >= n2) a.counts[img] = s_prefix + total;      // the image's last chunk
+    int range_flag = 0;
+#pragma unroll
+    for (int k = 0; k < kDecodePer; ++k) {
+        if (!((pass >> k) & 1u)) continue;
+        const int my = pos++;
+        if (my >= a.cap) continue;
+        const float* t = rec[k];
+        const int s = sc[k], b = bb[k];
+        float r0, r1, r2, r3;
+        if (ch == 6) {                   // 24-byte record, 8-byte aligned: three 8-byte loads
+            const float2 p0 = __ldg(reinterpret_cast<const float2*>(t)), p1 = __ldg(reinterpret_cast<const float2*>(t) + 1);
+            r0 = p0.x; r1 = p0.y; r2 = p1.x; r3 = p1.y;
+        } else { r0 = __ldg(t); r1 = __ldg(t + 1); r2 = __ldg(t + 2); r3 = __ldg(t + 3); }
+        const int gw = a.gw[s], gh = a.gh[s];
+        const int row = cell[k] / gw, col = cell[k] - row * gw;                     // :349-350
+        const float sx = sigmoid_ref(r0), sy = sigmoid_ref(r1);                     // :343
+        const float ew = exp_cr_f32(r2), eh = exp_cr_f32(r3);                       // :375-376
+        const int aw = a.anchors[6 * s + 2 * b], ah = a.anchors[6 * s + 2 * b + 1];
+        double x0, y0, x1, y1;
+        if (a.arith == 0) {
+            const double x = __ddiv_rn(__dadd_rn((double)col, (double)sx), (double)gw);   // :373
+            const double y = __ddiv_rn(__dadd_rn((double)row, (double)sy), (double)gh);   // :374
+            const double w = __ddiv_rn(__dmul_rn((double)aw, (double)ew), (double)a.net_w);   // :375
+            const double h = __ddiv_rn(__dmul_rn((double)ah, (double)eh), (double)a.net_h);   // :376
+            const double hw = __ddiv_rn(w, 2.0), hh = __ddiv_rn(h, 2.0);
+            x0 = __dsub_rn(x, hw); y0 = __dsub_rn(y, hh); x1 = __dadd_rn(x, hw); y1 = __dadd_rn(y, hh);   // :383
+        } else {
+            const float x = __fdiv_rn(__fadd_rn((float)col, sx), (float)gw);
+            const float y = __fdiv_rn(__fadd_rn((float)row, sy), (float)gh);
+            const float w = __fdiv_rn(__fmul_rn((float)aw, ew), (float)a.net_w);
+            const float h = __fdiv_rn(__fmul_rn((float)ah, eh), (float)a.net_h);
+            const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+            x0 = __fsub_rn(x, hw); y0 = __fsub_rn(y, hh); x1 = __fadd_rn(x, hw); y1 = __fadd_rn(y, hh);
+        }
+        const size_t o = (size_t)img * a.cap + my;
+        if (a.nbox) { double* d = a.nbox + 4 * o; d[0] = x0; d[1] = y0; d[2] = x1; d[3] = y1; }
+        if (a.ibox && a.image_hw) {
+            int4 q;
+            q.x = correct_coord(x0, lb.x_off, lb.x_scale, lb.image_w, a.arith, &range_flag);
+            q.y = correct_coord(y0, lb.y_off, lb.y_scale, lb.image_h, a.arith, &range_flag);
+            q.z = correct_coord(x1, lb.x_off, lb.x_scale, lb.image_w, a.arith, &range_flag);
+            q.w = correct_coord(y1, lb.y_off, lb.y_scale, lb.image_h, a.arith, &range_flag);
+            reinterpret_cast<int4*>(a.ibox)[o] = q;
+        }
+        if (a.objness) a.objness[o] = obj[k];
+        if (a.classes)
+            for (int c = 0; c < a.nb_class; ++c) a.classes[o * a.nb_class + c] = sigmoid_ref(__ldg(t + 5 + c));   // :344
+        if (a.cand) a.cand[o] = g0 + k;
+    }
     if (range_flag) atomicOr(a.status, 1);
 }
 
@@ -387,20 +456,43 @@ __device__ __forceinline__ uint32_t float_orderable(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending uint order == ascending float order
 }
 
-// Bitonic sort of `np2` 64-bit keys (np2 = power of two) held in shared or global memory.
+// Bitonic sort of `np2` 64-bit keys (np2 = power of two >= 64) held in shared or global memory, by a block of whole warps.
+// Every warp owns aligned 64-key segments; the compare-exchange steps with partner distance j <= 32 stay inside a segment, so a
+// whole run of them (the tail j = 32 .. 1 of every stage, and all of the stages k <= 64) needs only __syncwarp; the block-wide
+// barrier is paid for the steps with j >= 64 alone: 21 instead of 78 barriers at np2 = 4096.
+__device__ __forceinline__ void bitonic_cmpx(unsigned long long* keys, int i, int j, int k) {
+    const int l = i ^ j;
+    if (l > i) {
+        const unsigned long long a = keys[i], b = keys[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+    }
+}
 __device__ void bitonic_sort_u64(unsigned long long* keys, int np2) {
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned long long a = keys[i], b = keys[l];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
-                }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // stages k = 2 .. 64: entirely inside 64-key segments
+    for (int seg = warp * 64; seg < np2; seg += nwarps * 64) {
+        for (int k = 2; k <= 64; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                bitonic_cmpx(keys, seg + lane, j, k);
+                bitonic_cmpx(keys, seg + lane + 32, j, k);
+                __syncwarp();
             }
+    }
+    __syncthreads();
+    for (int k = 128; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j >= 64; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) bitonic_cmpx(keys, i, j, k);
             __syncthreads();
         }
+        for (int seg = warp * 64; seg < np2; seg += nwarps * 64) {
+            for (int j = 32; j > 0; j >>= 1) {
+                bitonic_cmpx(keys, seg + lane, j, k);
+                bitonic_cmpx(keys, seg + lane + 32, j, k);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -518,31 +610,50 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
                 // thresholds of the float pre-filter: 1 % either side (th in (0, 1]: the margin dwarfs the float rounding)
                 const float th_lo = (float)(a.th * 0.99), th_hi = (float)(a.th * 1.01);
                 if (all_small) {
-                    // branch-free over all 64 columns (constant shifts, no loop-carried control flow): the same decisions as
-                    // iou_prefilter_f, collected as two bit sets - "at or above the threshold" and "inside the 1 % band" - and masked to
-                    // the valid columns afterwards; the rare band bits then take the exact int64 / fp64 test one by one
+                    // Two phases over the 64 columns.  Phase 1, branch-free: one bit per column whose box can overlap this row's at all
+                    // (four compares on float copies - a superset of "intersection > 0"); at the usual candidate densities a few per
+                    // cent of the pairs.  Phase 2 runs the float pre-filter (same decisions as iou_prefilter_f) on those bits only;
+                    // when a warp's rows overlap many columns (crowd scenes) it takes the branch-free form over all 64 instead, as
+                    // a loop over set bits would diverge.  Bits inside the 1 % band then take the exact int64 / fp64 test one by one.
                     const float4 mef = make_float4((float)me.x, (float)me.y, (float)me.z, (float)me.w);
                     const bool my_ok = my_area_f < 1e30f;
-                    unsigned long long yes = 0, band = 0;
-#pragma unroll 16
-                    for (int j = 0; j < 64; ++j) {
-                        const float4 b = cboxf[j];
-                        const float ab = careaf[j];
-                        const float iw = fminf(mef.z, b.z) - fmaxf(mef.x, b.x);
-                        const float ih = fminf(mef.w, b.w) - fmaxf(mef.y, b.y);
-                        const float xf = iw * ih;
-                        const float uf = my_area_f + ab - xf;
-                        const bool pos = iw > 0.f && ih > 0.f;
-                        const bool ok = uf > 0.f && my_ok && ab < 1e30f;
-                        const bool above = xf > th_hi * uf, below = xf < th_lo * uf;
-                        yes |= (unsigned long long)(pos && ok && above && !below) << j;
-                        band |= (unsigned long long)(pos && !(ok && (above || below))) << j;
-                    }
                     const unsigned long long upto = jmax >= 64 ? ~0ull : ((1ull << jmax) - 1ull);
                     const unsigned long long from = j0 >= 64 ? 0ull : ~((1ull << j0) - 1ull);
                     const unsigned long long valid = upto & from;
-                    word = yes & valid;
-                    for (unsigned long long todo = band & valid; todo; todo &= todo - 1) {
+                    unsigned long long ov = 0;
+#pragma unroll 16
+                    for (int j = 0; j < 64; ++j) {
+                        const float4 b = cboxf[j];
+                        ov |= (unsigned long long)(mef.z > b.x && b.z > mef.x && mef.w > b.y && b.w > mef.y) << j;
+                    }
+                    ov &= valid;
+                    unsigned long long yes = 0, band = 0;
+                    if (__any_sync(__activemask(), __popcll(ov) > 16)) {
+#pragma unroll 16
+                        for (int j = 0; j < 64; ++j) {
+                            const float4 b = cboxf[j];
+                            const float ab = careaf[j];
+                            const float iw = fminf(mef.z, b.z) - fmaxf(mef.x, b.x);
+                            const float ih = fminf(mef.w, b.w) - fmaxf(mef.y, b.y);
+                            const float xf = iw * ih;
+                            const float uf = my_area_f + ab - xf;
+                            const bool pos = iw > 0.f && ih > 0.f;
+                            const bool ok = uf > 0.f && my_ok && ab < 1e30f;
+                            const bool above = xf > th_hi * uf, below = xf < th_lo * uf;
+                            yes |= (unsigned long long)(pos && ok && above && !below) << j;
+                            band |= (unsigned long long)(pos && !(ok && (above || below))) << j;
+                        }
+                        yes &= valid; band &= valid;
+                    } else {
+                        for (unsigned long long todo = ov; todo; todo &= todo - 1) {
+                            const int j = __ffsll((long long)todo) - 1;
+                            const int d = iou_prefilter_f(mef, my_area_f, cboxf[j], careaf[j], th_lo, th_hi);
+                            yes |= (unsigned long long)(d == 1) << j;
+                            band |= (unsigned long long)(d == 2) << j;
+                        }
+                    }
+                    word = yes;
+                    for (unsigned long long todo = band; todo; todo &= todo - 1) {
                         const int j = __ffsll((long long)todo) - 1;
                         if (iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi)) word |= 1ull << j;
                     }
@@ -767,6 +878,116 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
                 if ((fl >> b) & 1ull) {
                     const unsigned long long m = mk[(size_t)(blk * 64 + b) * a.words + w];
                     if (m) atomicOr(&removed[w], m);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if ((removed[i >> 6] >> (i & 63)) & 1ull) a.classes[(seg + ord[i]) * a.nb_class + a.cls] = 0.f;   // :444
+}
+
+// The same sweep for segments of up to kSweepMaxBlocks x 64 boxes with every global round trip taken off the per-block chain.
+// nms_sweep_kernel pays, per block step, a dependent global read for the next block's "score != 0" bits (order -> classes) and
+// another for the later words of the kept rows (~1.9 us per step, 64 us for 2 100 boxes).  Here the diagonal words and the alive
+// bits of ALL blocks are read up front into shared memory (one parallel pass), and the later words of a block's flagged rows are
+// fetched one whole step before they are needed (registers -> a double buffer in shared memory), so a step is two barriers and
+// shared-memory work.  Same decisions in the same order: bit-identical result.
+constexpr int kSweepMaxBlocks = 96;          // 6 144 boxes: 147 KB of shared memory at the limit
+constexpr int kSweepThreads = 512;
+constexpr int kSweepPf = (64 * (kSweepMaxBlocks - 1) + kSweepThreads - 1) / kSweepThreads;    // words a thread may hold in flight
+__host__ __device__ inline size_t sweep_small_smem(int nb) { return (size_t)nb * 8 * (2 + 64 + 2 * 64); }
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_small_kernel(const SweepArgs a, int nb_max) {
+    extern __shared__ unsigned long long sm[];
+    __shared__ unsigned long long flagged_w;
+    const int img = blockIdx.x;
+    const int n = min(a.counts[img], a.seg_stride);
+    if (n <= 0) return;
+    const int nb = (n + 63) >> 6;
+    unsigned long long* removed = sm;                       // [nb_max]
+    unsigned long long* alive = sm + nb_max;                // [nb_max]
+    unsigned long long* diag = sm + 2 * nb_max;             // [nb_max][64]
+    unsigned long long* pre = diag + (size_t)nb_max * 64;   // [2][64][nb_max]: later words of the flagged rows of a block
+    const size_t seg = (size_t)img * a.seg_stride;
+    const int* ord = a.order + (size_t)img * a.capP;
+    const unsigned long long* mk = a.mask + (size_t)img * a.capP * a.words;
+    const unsigned long long* rf = a.rowflag + (size_t)img * a.words;
+    const int lane = threadIdx.x & 31;
+    for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
+    for (int i0 = (threadIdx.x >> 5) * 32; i0 < nb * 64; i0 += blockDim.x) {       // whole warps: i0 .. i0 + 31 share half a block
+        const int i = i0 + lane;
+        unsigned long long d = 0;
+        bool al = false;
+        if (i < n) {
+            d = mk[(size_t)i * a.words + (i >> 6)];
+            al = a.classes[(seg + ord[i]) * a.nb_class + a.cls] != 0.f;
+        }
+        diag[i] = d;
+        const unsigned bal = __ballot_sync(0xffffffffu, al);
+        if (lane == 0) reinterpret_cast<unsigned*>(alive)[i >> 5] = bal;
+    }
+    // later words of block c's flagged rows: entry e = b * later + (w - c - 1), e < 64 * later, later = nb - c - 1
+    unsigned long long pf[kSweepPf];
+    auto fetch_rows = [&](int c) {
+        const int later = nb - c - 1;
+        const unsigned long long fl = c < nb ? rf[c] : 0ull;
+#pragma unroll
+        for (int k = 0; k < kSweepPf; ++k) {
+            const int e = threadIdx.x + k * kSweepThreads;
+            unsigned long long v = 0;
+            if (later > 0 && e < 64 * later) {
+                const int b = e / later, w = c + 1 + (e - b * later);
+                if ((fl >> b) & 1ull) v = mk[(size_t)(c * 64 + b) * a.words + w];
+            }
+            pf[k] = v;
+        }
+    };
+    auto stash_rows = [&](int c) {
+        const int later = nb - c - 1;
+        unsigned long long* dst = pre + (size_t)(c & 1) * 64 * nb_max;
+#pragma unroll
+        for (int k = 0; k < kSweepPf; ++k) {
+            const int e = threadIdx.x + k * kSweepThreads;
+            if (later > 0 && e < 64 * later) dst[e] = pf[k];
+        }
+    };
+    fetch_rows(0);
+    stash_rows(0);
+    fetch_rows(1);
+    for (int blk = 0; blk < nb; ++blk) {
+        __syncthreads();        // diag / alive / pre[blk & 1] are in place; every OR into removed[blk] has been made
+        stash_rows(blk + 1);    // fetched one step ago; pre[(blk + 1) & 1] was last read in step blk - 1, before the barrier above
+        fetch_rows(blk + 2);
+        if (threadIdx.x < 32) {
+            const unsigned long long d_lo = diag[blk * 64 + lane], d_hi = diag[blk * 64 + lane + 32];
+            const unsigned long long al = alive[blk];
+            unsigned long long cr = removed[blk];
+            const unsigned long long cand = al & ~cr;
+            const bool lo_act = ((cand >> lane) & 1ull) && (d_lo & cand) != 0ull;
+            const bool hi_act = ((cand >> (lane + 32)) & 1ull) && (d_hi & cand) != 0ull;
+            unsigned long long act = (unsigned long long)__ballot_sync(0xffffffffu, lo_act) |
+                                     ((unsigned long long)__ballot_sync(0xffffffffu, hi_act) << 32);
+            while (act) {                                   // ascending row order = the reference's score order inside the block
+                const int b = __ffsll((long long)act) - 1;
+                act &= act - 1;
+                const unsigned long long db = __shfl_sync(0xffffffffu, b < 32 ? d_lo : d_hi, b & 31);
+                if (!((cr >> b) & 1ull)) cr |= db;
+            }
+            if (lane == 0) {
+                const unsigned long long keep = al & ~cr;
+                removed[blk] = cr; flagged_w = keep & rf[blk];
+            }
+        }
+        __syncthreads();
+        const unsigned long long fl = flagged_w;
+        const int later = nb - (blk + 1);
+        if (fl && later > 0) {                              // block-uniform
+            const unsigned long long* src = pre + (size_t)(blk & 1) * 64 * nb_max;
+            for (int e = threadIdx.x; e < 64 * later; e += blockDim.x) {
+                const int b = e / later;
+                if ((fl >> b) & 1ull) {
+                    const unsigned long long m = src[e];
+                    if (m) atomicOr(&removed[blk + 1 + (e - b * later)], m);
                 }
             }
         }

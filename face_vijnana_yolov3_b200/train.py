@@ -14,8 +14,10 @@ gradient all-reduce.  Gradients live in flat fp32 buckets (parameters' ``.grad``
 all-reduced asynchronously as soon as autograd has produced its last gradient, so the exchange overlaps the rest of the
 backward pass; the optimizer waits for the handles.  Bucket size is chosen for launch latency, not link count (NVSwitch).
 
-Round-1 status of row f-1: the conv / BatchNorm forward and backward run through torch autograd (cuDNN - library code);
-what is hand-written here is the exchange (bucketing, overlap), the Keras-exact Adam update (``fvy_adam_step``, one fused
+Status of row f-1: every BatchNormalization (training mode: batch statistics) + LeakyReLU pair runs through this repo's own
+CUDA kernels forward and backward (``fvy_bn_leaky_train_forward / _backward``, csrc/train_kernels.cuh, bound to autograd by
+``_BnLeakyFn``); the convolutions' forward / dgrad / wgrad still run through torch autograd (cuDNN - library code, the stated
+baseline).  Also hand-written: the exchange (bucketing, overlap), the Keras-exact Adam update (``fvy_adam_step``, one fused
 CUDA pass over the flat buckets) and the weight-stream interop that lets trained weights flow straight into the tcgen05
 inference engine.  The ground-truth tensor builder restates ``TrainingSequence.__getitem__`` (:150-200).
 """
@@ -128,6 +130,48 @@ def synthetic_targets(batch: int, seed: int = 0, cell_size: int = 13, positives:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# BatchNormalization (training mode) + LeakyReLU on this repo's kernels
+# ----------------------------------------------------------------------------------------------------------------------
+class _BnLeakyFn(torch.autograd.Function):
+    """y = LeakyReLU_slope(BatchNorm_train(x)) through ``fvy_bn_leaky_train_forward / _backward`` (NHWC fp32, CUDA only).
+    The running statistics of ``bn`` (a torch BatchNorm2d used as the parameter / buffer holder) are updated in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, slope):
+        from . import _lib as L
+        lib = L.load()
+        x = x.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        invstd = torch.empty_like(mean)
+        ws = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        P = lambda t: C.c_void_p(t.data_ptr())
+        L.check(lib.fvy_bn_leaky_train_forward(P(x), C.c_longlong(n * h * w), c, P(gamma), P(beta), C.c_float(bn.eps), C.c_float(bn.momentum),
+                                               C.c_float(slope), P(bn.running_mean), P(bn.running_var), P(y), P(mean), P(invstd), P(ws), C.c_void_p(st)))
+        ctx.save_for_backward(x, gamma, beta, mean, invstd)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _lib as L
+        lib = L.load()
+        x, gamma, beta, mean, invstd = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dgamma = torch.empty_like(gamma); dbeta = torch.empty_like(beta)
+        ws = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        P = lambda t: C.c_void_p(t.data_ptr())
+        L.check(lib.fvy_bn_leaky_train_backward(P(x), P(dy), C.c_longlong(n * h * w), c, P(gamma), P(beta), P(mean), P(invstd), C.c_float(ctx.slope),
+                                                P(dx), P(dgamma), P(dbeta), P(ws), C.c_void_p(st)))
+        return dx, dgamma, dbeta, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # model
 # ----------------------------------------------------------------------------------------------------------------------
 class FdNet(nn.Module):
@@ -140,6 +184,7 @@ class FdNet(nn.Module):
     def __init__(self, bb_info_c_size: int = 6):
         super().__init__()
         self.specs = arch.fd6_table(bb_info_c_size)
+        self.fvy_bn = False        # True: BatchNorm (training) + LeakyReLU through this repo's kernels (fp32 CUDA tensors only)
         self.convs = nn.ModuleDict()
         self.bns = nn.ModuleDict()
         for c in self.specs:
@@ -153,10 +198,14 @@ class FdNet(nn.Module):
         y = x
         for c in self.specs:
             y = self.convs[str(c.idx)](outs[c.src])
-            if c.bn:
-                y = self.bns[str(c.idx)](y)
-            if c.leaky:
-                y = F.leaky_relu(y, 0.1)
+            if c.bn and self.fvy_bn and self.training and y.is_cuda and y.dtype == torch.float32:
+                bn = self.bns[str(c.idx)]
+                y = _BnLeakyFn.apply(y, bn.weight, bn.bias, bn, 0.1 if c.leaky else 1.0)
+            else:
+                if c.bn:
+                    y = self.bns[str(c.idx)](y)
+                if c.leaky:
+                    y = F.leaky_relu(y, 0.1)
             if c.res is not None:
                 y = y + outs[c.res]
             outs[c.idx] = y
@@ -254,7 +303,7 @@ class DataParallelTrainer:
     """
 
     def __init__(self, hps: dict, device: str = "cpu", bb_info_c_size: int = 6, bucket_mb: float = 32.0, autocast_bf16: bool = False,
-                 stream: Optional[np.ndarray] = None, model: Optional[nn.Module] = None):
+                 stream: Optional[np.ndarray] = None, model: Optional[nn.Module] = None, fvy_bn: Optional[bool] = None):
         self.device = torch.device(device)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
@@ -266,6 +315,9 @@ class DataParallelTrainer:
             self.model.to(memory_format=torch.channels_last)
         self.model.train()
         self.autocast_bf16 = autocast_bf16 and self.device.type == "cuda"
+        # BatchNorm + LeakyReLU on this repo's kernels whenever they can run (fp32 on a GPU); torch's modules otherwise
+        if hasattr(self.model, "fvy_bn"):
+            self.model.fvy_bn = (self.device.type == "cuda" and not self.autocast_bf16) if fvy_bn is None else bool(fvy_bn)
         # flat buckets in REVERSE parameter order (= the order autograd finishes gradients in)
         params = [p for p in self.model.parameters() if p.requires_grad]
         limit = int(bucket_mb * (1 << 20) / 4)
@@ -292,6 +344,7 @@ class DataParallelTrainer:
         self.n_params = sum(f.numel() for f in self.flat_p)
         self.opt = FlatAdam(self.flat_p, self.flat_g, hps['lr'], hps['beta_1'], hps['beta_2'], hps.get('decay', 0.0))
         self._pending = [0] * len(self.buckets)
+        self._next_bucket = 0
         self._handles: List = []
         self._comm_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         if self.world > 1:
@@ -304,14 +357,20 @@ class DataParallelTrainer:
     def _on_grad(self, p: torch.Tensor) -> None:
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            self._launch(bi)
+        self._launch_ready()
+
+    def _launch_ready(self, force: bool = False) -> None:
+        """Buckets go out strictly in index order (bucket i only after buckets < i), whatever order autograd completes them in:
+        every rank - including one that runs no backward because its slice is empty - issues the same sequence of collectives."""
+        while self._next_bucket < len(self.buckets) and (force or self._pending[self._next_bucket] == 0):
+            self._launch(self._next_bucket)
+            self._next_bucket += 1
 
     def exchange_all(self) -> None:
         """The step's exchange on its own (every bucket, same order and stream): bench.py times it for the bus bandwidth."""
         self._handles = []
-        for bi in range(len(self.buckets)):
-            self._launch(bi)
+        self._next_bucket = 0
+        self._launch_ready(force=True)
         for h in self._handles:
             h.wait()
         if self._comm_stream is not None:
@@ -355,11 +414,13 @@ class DataParallelTrainer:
         for g in self.flat_g:
             g.zero_()
         self._pending = [len(b) for b in self.buckets]
-        self._handles, self.last_allreduce_bytes = [], 0
+        self._handles, self.last_allreduce_bytes, self._next_bucket = [], 0, 0
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
             y = self.model(x)
         loss = F.mse_loss(y.float(), t)
         (loss * weight if weight != 1.0 else loss).backward()
+        if self.world > 1:
+            self._launch_ready(force=True)       # nothing is left in practice; keeps the collective sequence complete
         for h in self._handles:
             h.wait()
         if self._comm_stream is not None:

@@ -206,6 +206,21 @@ int fvy_detect_async(fvy_handle* h, const void* images, int dtype, int batch, co
  * per-GPU gradients into multi_gpu_model's whole-batch mean (face_detection.py:369). */
 int fvy_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta_1, float beta_2,
                   float epsilon, float grad_scale, void* cuda_stream);
+/* Training step, row f-1 (first slice): BatchNormalization in TRAINING mode fused with the LeakyReLU that follows it, forward and
+ * backward, over NHWC float32 activations x[rows][C] (rows = batch * H * W, C a multiple of 4), all pointers DEVICE memory, enqueued
+ * on `cuda_stream`.  Replaces what Keras runs for every bnorm_i + leaky_i pair of the reference's model when it trains
+ * (src/space/yolov3_detect.py:212-213 via src/space/face_detection.py:361-381, :602-630): batch statistics per GPU (as in
+ * multi_gpu_model's towers), eps = 1e-3, Keras momentum 0.99 <=> `momentum` = 0.01 here (new = old + momentum (batch - old), the
+ * running variance takes the unbiased batch variance).  slope = 0.1 (LeakyReLU(alpha=0.1)); slope = 1 gives a plain BatchNorm.
+ *   forward : y = leaky(gamma (x - mean) / sqrt(var + eps) + beta); save_mean / save_invstd [C] are kept for the backward.
+ *   backward: dx, dgamma [C], dbeta [C] from dy (gradient w.r.t. y) and the saved statistics.
+ * workspace: 2 * C doubles of scratch. */
+int fvy_bn_leaky_train_forward(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps, float momentum,
+                               float slope, float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd,
+                               double* workspace, void* cuda_stream);
+int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows, int C, const float* gamma, const float* beta,
+                                const float* save_mean, const float* save_invstd, float slope, float* dx, float* dgamma, float* dbeta,
+                                double* workspace, void* cuda_stream);
 /* Pre-processing of FaceDetector.evaluate / FaceDetector.test (src/space/face_detection.py:657-690 and :798-835):
  *   image = imread(file) / 255;  image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC);
  *   image = cv.copyMakeBorder(image, pad_t, pad_b, pad_l, pad_r, cv.BORDER_CONSTANT, value=[0, 0, 0])

@@ -311,3 +311,58 @@ def test_cal_mAP_fd_larger_case_matches_oracle(tmp_path):
         ev.cal_mAP_fd(gt, sol, 0.5)
     with pytest.raises(UnboundLocalError):
         M.cal_mAP_fd(gt, sol, 0.5)
+
+
+# ------------------------------------------------------------------------------------------ row f-1: training-mode BatchNorm + LeakyReLU
+@pytest.mark.parametrize("shape,slope", [((5, 32, 52, 52), 0.1), ((2, 256, 13, 13), 0.1), ((3, 64, 26, 26), 1.0)])
+def test_bn_leaky_train_kernels_match_torch(shape, slope):
+    """fvy_bn_leaky_train_forward / _backward (batch statistics, eps 1e-3, Keras momentum 0.99) vs torch's BatchNorm2d + LeakyReLU
+    in float32: outputs, running statistics and all three gradients.  Tolerance: relative L2 <= 1e-5 (fp32 op-order noise)."""
+    import torch
+    from face_vijnana_yolov3_b200 import train as T
+    torch.manual_seed(3)
+    n, c, h, w = shape
+    x = (torch.randn(shape, device="cuda") * 1.7 + 0.4).contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.BatchNorm2d(c, eps=1e-3, momentum=1.0 - T.KERAS_BN_MOMENTUM).cuda().train()
+    mine = torch.nn.BatchNorm2d(c, eps=1e-3, momentum=1.0 - T.KERAS_BN_MOMENTUM).cuda().train()
+    with torch.no_grad():
+        for m in (ref, mine):
+            m.weight.copy_(torch.linspace(0.5, 1.5, c)); m.bias.copy_(torch.linspace(-0.3, 0.3, c))
+            m.running_mean.copy_(torch.linspace(-1, 1, c)); m.running_var.copy_(torch.linspace(0.5, 2, c))
+    xr = x.clone().requires_grad_(True); xm = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.leaky_relu(ref(xr), slope) if slope != 1.0 else ref(xr)
+    ym = T._BnLeakyFn.apply(xm, mine.weight, mine.bias, mine, slope)
+    g = torch.randn_like(yr)
+    yr.backward(g); ym.backward(g)
+    torch.cuda.synchronize()
+    rl = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    assert rl(ym, yr) <= 1e-5
+    assert rl(mine.running_mean, ref.running_mean) <= 1e-6 and rl(mine.running_var, ref.running_var) <= 1e-6
+    assert rl(xm.grad, xr.grad) <= 1e-4, rl(xm.grad, xr.grad)          # dx is a difference of nearly cancelling terms
+    assert rl(mine.weight.grad, ref.weight.grad) <= 1e-5 and rl(mine.bias.grad, ref.bias.grad) <= 1e-5
+
+
+def test_training_step_with_fvy_bn_matches_autograd_baseline():
+    """One whole FaceDetector training step (fp32, TF32 off) with every BatchNorm + LeakyReLU pair on this repo's kernels vs the
+    same step on torch's modules: loss, every gradient tensor (relative L2 <= 1e-2, the bar VERDICT r1 item 7 sets) and the
+    updated weights."""
+    import torch
+    from face_vijnana_yolov3_b200 import train as T
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    stream = synth.darknet_stream(arch.fd6_table(6), 0, synth.INIT_KERAS_DEFAULT)
+    hps = dict(lr=1e-4, beta_1=0.99, beta_2=0.99, decay=0.0)
+    x = torch.from_numpy(synth.images(2, 416, 416, 0)); t = torch.from_numpy(T.synthetic_targets(2, 1))
+    res = {}
+    for name, flag in (("fvy", True), ("torch", False)):
+        tr = T.DataParallelTrainer(hps, device="cuda:0", stream=stream, fvy_bn=flag)
+        assert tr.model.fvy_bn is flag
+        loss = tr.step(x, t)
+        res[name] = (loss, [g.clone() for g in tr.flat_g], tr.weight_stream())
+        del tr
+    assert abs(res["fvy"][0] - res["torch"][0]) <= 1e-5 * max(1.0, abs(res["torch"][0]))
+    worst = 0.0
+    for a, b in zip(res["fvy"][1], res["torch"][1]):
+        worst = max(worst, float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)))
+    assert worst <= 1e-2, worst
+    assert rel_l2(res["fvy"][2], res["torch"][2]) <= 1e-5

@@ -140,6 +140,61 @@ def test_gloo_two_rank_training_step_matches_whole_batch_gradients(tmp_path):
     assert "WORST" in out.stdout
 
 
+def test_gloo_unequal_and_empty_slices_weight_gradients_like_the_whole_batch(tmp_path):
+    """A short last batch gives ranks unequal (3 images -> 2 + 1) or empty (1 image -> 1 + 0) slices.  multi_gpu_model takes the
+    loss mean over the WHOLE batch (face_detection.py:366, :369): rank r's mean-loss gradient must enter with weight b_r / B
+    (ADVICE r1), and a rank without images contributes zeros but still joins every all-reduce."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys, numpy as np, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r})
+        from face_vijnana_yolov3_b200 import arch, synth, train as T
+        torch.set_num_threads(2)
+        dist.init_process_group('gloo')
+        r, n = dist.get_rank(), dist.get_world_size()
+        hps = dict(lr=1e-3, beta_1=0.9, beta_2=0.999, decay=0.0)
+        stream = synth.darknet_stream(arch.fd6_table(6), 0, synth.INIT_KERAS_DEFAULT)
+        for B in (3, 1):
+            images = synth.images(B, 64, 64, 7)
+            targets = np.random.default_rng(1).random((B, 2, 2, 6)).astype(np.float32)
+            tr = T.DataParallelTrainer(hps, device='cpu', stream=stream, bucket_mb=8.0)
+            xs, ts = T.slice_for_rank(images, targets, r, n)
+            tr.step(torch.from_numpy(np.ascontiguousarray(xs)), torch.from_numpy(np.ascontiguousarray(ts)), global_batch=B)
+            flat = torch.cat([p.reshape(-1) for p in tr.flat_p])
+            both = [torch.empty_like(flat) for _ in range(n)]
+            dist.all_gather(both, flat)
+            assert torch.equal(both[0], both[1])
+            if r == 0:
+                acc = None
+                for k in range(n):
+                    lo, hi = T.shard_bounds(B, n)[k]
+                    if hi == lo:
+                        continue
+                    net = T.FdNet(6); net.load_stream(stream); net.train()
+                    y = net(torch.from_numpy(images[lo:hi]).permute(0, 3, 1, 2))
+                    (torch.nn.functional.mse_loss(y, torch.from_numpy(targets[lo:hi]).permute(0, 3, 1, 2)) * ((hi - lo) / B)).backward()
+                    g = {{name: p.grad.clone() for name, p in net.named_parameters()}}
+                    acc = g if acc is None else {{k2: acc[k2] + g[k2] for k2 in g}}
+                net = T.FdNet(6); net.load_stream(stream)
+                lr_t = T.keras_adam_lr_t(1e-3, 0.9, 0.999, 0.0, 0)
+                trained = dict(tr.model.named_parameters())
+                worst = 0.0
+                for name, p in net.named_parameters():
+                    g = acc[name]
+                    want = p.detach() - lr_t * (0.1 * g) / ((0.001 * g * g).sqrt() + 1e-7)
+                    worst = max(worst, float((trained[name].detach() - want).abs().max()))
+                print('WORST', B, worst)
+                assert worst < 1e-5, (B, worst)
+            dist.barrier()
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29654", str(script)], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("WORST") == 2
+
+
 @pytest.mark.gpu
 def test_fused_adam_kernel_matches_torch_ops():
     p0 = torch.randn(100003, device="cuda")
