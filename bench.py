@@ -335,6 +335,15 @@ def run_detect(args, D):
                      "clocks": sampler.summary(first=s_first)}
     sampler.stop()
 
+    # ---- the two halves timed ALONE (synchronous calls: no overlap between the post-processing of one step and the forward of
+    # the next), for comparison with the in-region figures above
+    fa, pa = [], []
+    for _ in range(min(args.steps, 10)):
+        eng.detect(x_dev, pp=pp, image_hw=hw_dev, max_out=max_out, dets=dets_dev, counts=cnt_dev, sync=True)
+        a_, b_ = eng.last_timing()
+        fa.append(a_); pa.append(b_)
+    fwd_alone, post_alone = float(np.median(fa)), float(np.median(pa))
+
     # ---- rooflines.  Conv stack (tensor bound): algorithmic FLOPs / the forward's CUDA-event time inside the timed steps.
     n_conv = len(eng.layer_infos())
     l0 = eng.launch_count
@@ -349,7 +358,11 @@ def run_detect(args, D):
                 "frac_of_sustained_peak": achieved / peaks["tf_sustained"],
                 "algorithmic_flops_per_step": flops_step, "avg_launch_ms": fwd_ms / max(1, n_fwd_launches), "forward_ms": fwd_ms,
                 "forward_ms_source": f"CUDA events around the forward of each of the {n_timed} timed steps (fvy_timer_breakdown)",
-                "postprocess_ms": post_ms, "share_of_step": fwd_ms / max(ms_step, 1e-9), "traffic": None}
+                "postprocess_ms": post_ms, "share_of_step": fwd_ms / max(ms_step, 1e-9),
+                "forward_ms_alone": fwd_alone, "postprocess_ms_alone": post_alone,
+                "note": "in the timed (asynchronous) steps the post-processing of step i runs on a low-priority stream beside the forward of step i+1: "
+                        "forward_ms includes that interference and postprocess_ms is stretched by it; *_alone are the same kernels in synchronous calls",
+                "traffic": None}
     if sustained:
         a_s = flops_step / (sustained["forward_ms"] * 1e-3) / 1e12
         sustained["roofline"] = {"achieved": a_s, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": a_s / peaks["tf_sustained"],
@@ -375,7 +388,8 @@ def run_detect(args, D):
     post_ach = post_bytes / (post_ms * 1e-3) / 1e9
     roofline_post = {"bound": "hbm", "kernel": "decode_yolo_kernel + sort_scores_kernel + nms_mask_kernel + nms_sweep_kernel + assemble_yolo_kernel",
                      "achieved": post_ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": post_ach / peaks["hbm"], "peak_source": peaks["source"],
-                     "postprocess_ms": post_ms, "algorithmic_bytes_per_step": post_bytes, "candidates_per_image_mean": float(n_c.mean()),
+                     "postprocess_ms": post_ms, "postprocess_ms_alone": post_alone, "achieved_alone": post_bytes / (post_alone * 1e-3) / 1e9,
+                     "algorithmic_bytes_per_step": post_bytes, "candidates_per_image_mean": float(n_c.mean()),
                      "kept_per_image_mean": float(cnt_now.mean()),
                      "note": "launch/latency-bound at ~2k candidates per image, not bandwidth-bound (DESIGN.md 3.3); BASELINE configs[4] "
                              "(--config stress) is the size the HBM roofline is meaningful at"}

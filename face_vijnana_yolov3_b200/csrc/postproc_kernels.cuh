@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_yolo_kernel(const Decod
         }
         ws[lane] = in2 - v;
         if (lane == 31) ws[32] = in2;
-        // publish this chunk's count, then add up the earlier chunks' (spinning until each has published)
-        if (lane == 0) st_release_gpu(isync + 1 + chunk, (in2 << 1) | 1);
+        // publish this chunk's count (lane 31 holds the block total), then add up the earlier chunks' (spinning until each has published)
+        if (lane == 31) st_release_gpu(isync + 1 + chunk, (in2 << 1) | 1);
         int before = 0;
         for (int c = lane; c < chunk; c += 32) {
             int v2;

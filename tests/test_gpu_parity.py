@@ -292,7 +292,7 @@ def test_dropin_functions_and_facedetector():
     anchors = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]
     boxes = []
     for i in range(3):
-        boxes += yd.decode_netout(outs[i][0], anchors[i], i, 0.5, 416, 416)
+        boxes += yd.decode_netout(outs[i][0].copy(), anchors[i], i, 0.5, 416, 416)     # like the reference, it writes the sigmoid into its argument
     d = P.decode_image([o[0] for o in outs])
     assert len(boxes) == len(d["cell"]) and isinstance(boxes[0].xmin, np.float64)
     assert np.array_equal(np.array([[b.xmin, b.ymin, b.xmax, b.ymax] for b in boxes]), d["box"])

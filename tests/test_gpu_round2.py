@@ -365,4 +365,5 @@ def test_training_step_with_fvy_bn_matches_autograd_baseline():
     for a, b in zip(res["fvy"][1], res["torch"][1]):
         worst = max(worst, float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)))
     assert worst <= 1e-2, worst
-    assert rel_l2(res["fvy"][2], res["torch"][2]) <= 1e-5
+    # the first Keras-Adam step moves every weight by ~lr * sign(g): a gradient whose sign differs in the noise moves it by 2 lr
+    assert rel_l2(res["fvy"][2], res["torch"][2]) <= 1e-3

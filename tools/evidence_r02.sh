@@ -1,0 +1,43 @@
+#!/bin/bash
+# Round-2 single-GPU evidence of the shipped build (run under gpurun; raw results land in gpurun_out/r2e_*, summaries are then
+# copied to profiles/ by tools/evidence_r02_collect.sh here).  Every ncu pass runs only after its command has exited 0 without ncu.
+T=${1:-r2e}
+python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err || tail -5 gpurun_out/${T}_bench.err
+python bench.py --config 608x320 --no-cpu-baseline > gpurun_out/${T}_bench_608x320.json 2>> gpurun_out/${T}_bench.err
+python bench.py --config stress > gpurun_out/${T}_bench_stress.json 2>> gpurun_out/${T}_bench.err
+python bench.py --config train > gpurun_out/${T}_bench_train.json 2>> gpurun_out/${T}_bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
+python tools/gpu_check.py --tile-n 256 > gpurun_out/${T}_check.log 2>&1
+# launch list of the headline command (cold-cache, serialised: shares, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-s 0 > gpurun_out/${T}_ncu1.log 2>&1
+cat > /tmp/fwd2.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+from face_vijnana_yolov3_b200 import arch, synth
+from face_vijnana_yolov3_b200.engine import Engine, post_params
+import torch, numpy as np
+eng = Engine(416, 416, nb_class=1, max_batch=40)
+eng.load_weights(synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT))
+xd = torch.from_numpy(synth.images(40, 416, 416, 1)).cuda()
+hw = np.array([[416, 416]] * 40, np.int32)
+for _ in range(2):
+    eng.forward(xd, want_outputs=False)
+if len(sys.argv) > 1:
+    eng.detect(xd, pp=post_params(0.5, 0.45), image_hw=hw, max_out=4225)
+PY
+# DRAM traffic of every conv launch of one forward -> profiles/conv_traffic.json (stamped with the build hash)
+FVY_GRAPH=0 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k regex:"conv_igemm|conv_chain|stem_" -c 200 --csv --log-file gpurun_out/${T}_traffic.csv python /tmp/fwd2.py > gpurun_out/${T}_ncu2.log 2>&1
+python tools/summarize_ncu.py traffic gpurun_out/${T}_traffic.csv gpurun_out/${T}_conv_traffic_per_launch.csv gpurun_out/${T}_conv_traffic.json
+# full capture of the post-processing kernels of one detect call (the kernels changed this round)
+ncu --set full --clock-control none --import-source on -k regex:"decode_yolo|sort_scores|nms_mask|nms_sweep|assemble" -c 5 -o gpurun_out/${T}_post -f \
+    python /tmp/fwd2.py detect > gpurun_out/${T}_ncu3.log 2>&1
+ncu -i gpurun_out/${T}_post.ncu-rep --page raw --csv > gpurun_out/${T}_post_raw.csv 2>/dev/null; rm -f gpurun_out/${T}_post.ncu-rep
+# compute-sanitizer: one batch-40 forward + detect with chains, tile-dependency flags and the CUDA graph on (default configuration)
+for tool in memcheck synccheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/fwd2.py detect > gpurun_out/${T}_sanitizer_$tool.log 2>&1
+  echo "compute-sanitizer $tool rc=$?" | tee -a gpurun_out/${T}_sanitizer_$tool.log; tail -3 gpurun_out/${T}_sanitizer_$tool.log
+done
+for f in bench bench_608x320 bench_stress bench_train bench_ref; do cut -c1-330 gpurun_out/${T}_$f.json; echo; done; tail -2 gpurun_out/${T}_check.log; tail -5 gpurun_out/${T}_bench.err
