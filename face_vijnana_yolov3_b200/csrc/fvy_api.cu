@@ -456,6 +456,16 @@ int fvy_postprocess(fvy_handle* h, const float* out0, const float* out1, const f
     return postprocess_common(h, out0, out1, out2, batch, pp, image_hw, max_out, dets, det_counts, true);
 }
 
+// Adds the elapsed times of ring slot `slot` to the running sums (its events completed long ago, or the streams were just synchronised).
+static void harvest_time_slot(fvy_handle* h, int slot) {
+    if (!h->ring_used[slot]) return;
+    h->ring_used[slot] = false;
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, h->ev_tf[slot][0], h->ev_tf[slot][1]) != cudaSuccess ||
+        cudaEventElapsedTime(&b, h->ev_tp[slot][0], h->ev_tp[slot][1]) != cudaSuccess) { cudaGetLastError(); return; }
+    h->acc_fwd_ms += a; h->acc_post_ms += b; ++h->acc_calls;
+}
+
 static int detect_common(fvy_handle* h, const void* images, int dtype, int batch, const fvy_post_params* pp, const int* image_hw,
                          int max_out, fvy_det* dets, int32_t* det_counts, bool sync) {
     if (!h || !images) return fail(FVY_E_INVALID, "NULL argument");
@@ -473,12 +483,14 @@ static int detect_common(fvy_handle* h, const void* images, int dtype, int batch
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_post_done[1], 0));              // nothing of an earlier asynchronous call is still in flight
     }
     const int slot = (int)(h->call_count++ % fvy_handle::kTimeRing);
+    harvest_time_slot(h, slot);
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     CUDA_TRY(cudaEventRecord(h->ev_tf[slot][0], h->stream));
     if (int e = forward_enqueue(h, images, dtype, batch)) return e;
     CUDA_TRY(cudaEventRecord(h->ev_tf[slot][1], h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
     h->time_slot = slot;
+    h->ring_used[slot] = true;
     int e = FVY_OK;
     if (overlap) {
         CUDA_TRY(cudaEventRecord(h->ev_fwd_done[h->logit_set], h->stream));
@@ -706,7 +718,8 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms) {
 int fvy_timer_start(fvy_handle* h) {
     if (!h) return fail(FVY_E_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    h->timer_mark = h->call_count;
+    for (bool& u : h->ring_used) u = false;
+    h->acc_fwd_ms = h->acc_post_ms = 0.0; h->acc_calls = 0;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
     return FVY_OK;
 }
@@ -715,19 +728,11 @@ int fvy_timer_breakdown(fvy_handle* h, float* forward_ms_mean, float* post_ms_me
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->post_stream));
-    const long long first = std::max(h->timer_mark, h->call_count - fvy_handle::kTimeRing);
-    double f = 0.0, p = 0.0;
-    int n = 0;
-    for (long long c = first; c < h->call_count; ++c) {
-        const int slot = (int)(c % fvy_handle::kTimeRing);
-        float a = 0.f, b = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&a, h->ev_tf[slot][0], h->ev_tf[slot][1]));
-        CUDA_TRY(cudaEventElapsedTime(&b, h->ev_tp[slot][0], h->ev_tp[slot][1]));
-        f += a; p += b; ++n;
-    }
-    if (forward_ms_mean) *forward_ms_mean = n ? (float)(f / n) : 0.f;
-    if (post_ms_mean) *post_ms_mean = n ? (float)(p / n) : 0.f;
-    if (calls) *calls = n;
+    for (int s = 0; s < fvy_handle::kTimeRing; ++s) harvest_time_slot(h, s);
+    const double n = (double)std::max<long long>(1, h->acc_calls);
+    if (forward_ms_mean) *forward_ms_mean = (float)(h->acc_fwd_ms / n);
+    if (post_ms_mean) *post_ms_mean = (float)(h->acc_post_ms / n);
+    if (calls) *calls = (int)h->acc_calls;
     return FVY_OK;
 }
 int fvy_timer_stop(fvy_handle* h, float* ms) {

@@ -208,10 +208,14 @@ struct fvy_handle {
     // pinned host memory behind its post-processing (one block per logit set) and examined at the next synchronisation point
     // (fvy_sync, any synchronous entry point, or the next asynchronous call that reuses the set).
     // Device time of the forward / post-processing part of every detect call of a timed region (fvy_timer_start ..
-    // fvy_timer_stop): event pairs in a ring, read back by fvy_timer_breakdown after the region has been synchronised.
-    static constexpr int kTimeRing = 512;
+    // fvy_timer_breakdown): event pairs in a small ring; a slot's elapsed times are added to the running sums when the slot comes
+    // round again (kTimeRing calls later its events have long completed) or when the breakdown is read.  (A first version kept
+    // 512 pairs per handle: a test process that had created ~32 k events segfaulted inside cuEventDestroy.)
+    static constexpr int kTimeRing = 32;
     cudaEvent_t ev_tf[kTimeRing][2] = {}, ev_tp[kTimeRing][2] = {};
-    long long call_count = 0, timer_mark = 0;
+    bool ring_used[kTimeRing] = {};
+    double acc_fwd_ms = 0.0, acc_post_ms = 0.0; long long acc_calls = 0;
+    long long call_count = 0;
     int time_slot = -1;                      // ring slot of the detect call being enqueued, or -1
     int* h_async[2] = {nullptr, nullptr};    // pinned: [0] status word, [1 .. max_batch] candidate counts
     int async_batch[2] = {0, 0};             // images of the set's pending call; 0 = nothing to examine

@@ -190,7 +190,7 @@ int fvy_run_layer(fvy_handle* h, int layer, int batch, int iters, float* ms);
 int fvy_timer_start(fvy_handle* h);
 int fvy_timer_stop(fvy_handle* h, float* ms);
 /* Mean device time (CUDA events inside the timed region, on the streams the kernels run on) of the forward part and of the
- * post-processing part of the fvy_detect / fvy_detect_async calls made since fvy_timer_start (the last 512 at most): what
+ * post-processing part of the fvy_detect / fvy_detect_async calls made since fvy_timer_start (any number of calls: a ring of 32 event pairs is drained into running sums): what
  * bench.py's roofline entries are computed from.  Synchronises the handle's streams. */
 int fvy_timer_breakdown(fvy_handle* h, float* forward_ms_mean, float* post_ms_mean, int* calls);
 /* Blocks until all work queued on the handle's streams is done.  Returns the deferred error of an asynchronous call, if any
