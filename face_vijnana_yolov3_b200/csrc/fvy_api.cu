@@ -70,9 +70,9 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
             ok = ok && cudaStreamCreateWithPriority(&h->post_stream, cudaStreamNonBlocking, lo) == cudaSuccess;
             h->ps = h->stream;
             const char* v = getenv("FVY_OVERLAP_POST");
-            h->overlap_post = !(v && *v && atoi(v) == 0);
+            h->overlap_post = !(v && *v && atoi(v) == 0) && !(cfg->flags & FVY_CFG_NO_OVERLAP_POST);
             const char* g = getenv("FVY_GRAPH");
-            h->use_graph = !(g && *g && atoi(g) == 0);
+            h->use_graph = !(g && *g && atoi(g) == 0) && !(cfg->flags & FVY_CFG_NO_GRAPH);
         }
         for (cudaEvent_t* ev : {&h->ev_fwd_done[0], &h->ev_fwd_done[1], &h->ev_post_done[0], &h->ev_post_done[1]})
             ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
@@ -599,9 +599,6 @@ int fvy_letterbox_u8(fvy_handle* h, const unsigned char* src, int src_h, int src
         if (bytes > h->lb_src_bytes) {                    // grows to the largest image seen (stream-ordered: earlier kernels have been enqueued)
             CUDA_TRY(cudaStreamSynchronize(h->stream));
             if (h->d_lb_src) cudaFree(h->d_lb_src);
-    for (int* p : h->h_async) if (p) cudaFreeHost(p);
-    for (auto& pr : h->ev_tf) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
-    for (auto& pr : h->ev_tp) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
             h->d_lb_src = nullptr; h->lb_src_bytes = 0;
             CUDA_TRY(cudaMalloc((void**)&h->d_lb_src, bytes));
             h->lb_src_bytes = bytes;

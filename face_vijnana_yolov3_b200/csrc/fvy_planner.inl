@@ -2,6 +2,8 @@
 // Included by fvy_api.cu inside no namespace (opens fvy itself).
 namespace fvy {
 
+constexpr int kChainSchedDefault = 0;      // FVY_CHAIN_SCHED when neither the environment nor fvy_config.flags says otherwise
+
 template <int BN, int BK, bool CTA2>
 static int launch_conv_t(fvy_handle* h, Layer& L, int grid) {
     auto kern = conv_igemm_kernel<BN, BK, CTA2>;   // max dynamic smem was raised in query_occ_t at plan time
@@ -334,7 +336,7 @@ static int build_plan(fvy_handle* h) {
     // ---- cross-layer tile dependencies: consumer = stride-1 conv reading the plain padded output of a producer whose stored
     // forms all leave by TMA (same geometry: the consumer's compute-domain rows ARE the producer's output rows)
     {
-        h->use_flags = env_int("FVY_FLAGS", 1) != 0;
+        h->use_flags = env_int("FVY_FLAGS", 1) != 0 && !(c.flags & FVY_CFG_NO_TILE_FLAGS);
         std::map<int, int> layer_of;
         for (size_t i = 0; i < h->layers.size(); ++i) layer_of[h->layers[i].s.idx] = (int)i;
         size_t total = 0;
@@ -363,8 +365,8 @@ static int build_plan(fvy_handle* h) {
     // ---- chains: runs of consecutive layers of the 256-wide CTA-pair instance, each reading its predecessor's TMA-stored
     // output, go out as ONE persistent launch (conv_chain_kernel)
     {
-        h->use_chain = h->use_flags && env_int("FVY_CHAIN", 1) != 0;
-        h->chain_sched = env_int("FVY_CHAIN_SCHED", 0) != 0;
+        h->use_chain = h->use_flags && env_int("FVY_CHAIN", 1) != 0 && !(c.flags & FVY_CFG_NO_CHAIN);
+        h->chain_sched = (c.flags & FVY_CFG_CHAIN_SCHED) ? true : ((c.flags & FVY_CFG_NO_CHAIN_SCHED) ? false : env_int("FVY_CHAIN_SCHED", kChainSchedDefault) != 0);
         auto eligible = [&](const Layer& L) {
             if (!L.cta2 || L.BN != 256 || L.BK != 64 || L.s.stride != 1 || L.s.src < 0 || !L.s.bn) return false;
             if (L.p.b_resident || L.p.b_cover != 1) return false;

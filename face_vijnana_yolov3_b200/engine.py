@@ -65,10 +65,10 @@ class Engine:
     """One handle = one device + one stream.  Not re-entrant (SURVEY 8b threading)."""
 
     def __init__(self, net_h=416, net_w=416, head=L.HEAD_YOLO3, nb_class=1, max_batch=1, device=0, max_cands=0,
-                 bb_info_c_size=6, tile_n_max=0):
+                 bb_info_c_size=6, tile_n_max=0, flags=0):
         self.lib = L.load()
         cfg = L.FvyConfig(device=device, net_h=net_h, net_w=net_w, head=head, nb_class=nb_class, bb_info_c_size=bb_info_c_size,
-                          max_batch=max_batch, max_cands=max_cands, tile_n_max=tile_n_max, flags=0)
+                          max_batch=max_batch, max_cands=max_cands, tile_n_max=tile_n_max, flags=int(flags))
         self.cfg = cfg
         self._h = C.c_void_p()
         L.check(self.lib.fvy_create(C.byref(cfg), C.byref(self._h)))

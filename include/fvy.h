@@ -57,8 +57,16 @@ typedef struct {
     int max_batch;       /* images per forward call */
     int max_cands;       /* candidate capacity per image for decode/NMS; 0 = every cell x anchor */
     int tile_n_max;      /* 0 = default; upper bound on the GEMM N tile (tuning knob) */
-    int flags;           /* reserved, 0 */
+    int flags;           /* 0 = the measured-best schedule, or a combination of FVY_CFG_* (the execution-schedule switches a caller
+                            may pin per handle; results are bit-identical either way, tests/test_gpu_parity.py) */
 } fvy_config;
+/* fvy_config.flags: each bit overrides the corresponding FVY_* environment variable for this handle. */
+#define FVY_CFG_NO_GRAPH 0x01u         /* launch the conv stack kernel by kernel instead of replaying a CUDA graph (FVY_GRAPH=0) */
+#define FVY_CFG_NO_CHAIN 0x02u         /* no layer chains (conv_chain_kernel), one launch per layer (FVY_CHAIN=0) */
+#define FVY_CFG_NO_TILE_FLAGS 0x04u    /* kernel boundaries instead of cross-layer tile dependencies; implies NO_CHAIN (FVY_FLAGS=0) */
+#define FVY_CFG_CHAIN_SCHED 0x08u      /* per-pair work lists from the host list schedule inside the chains (FVY_CHAIN_SCHED=1) */
+#define FVY_CFG_NO_CHAIN_SCHED 0x10u   /* static rotation inside the chains (FVY_CHAIN_SCHED=0) */
+#define FVY_CFG_NO_OVERLAP_POST 0x20u  /* asynchronous calls post-process on the main stream (FVY_OVERLAP_POST=0) */
 
 /* One detection, 32 bytes.  Mirrors the fields of the reference's BoundBox that survive the hot
  * path (src/space/yolov3_detect.py:126-145): xmin,ymin,xmax,ymax,objness, get_label(), get_score(). */
