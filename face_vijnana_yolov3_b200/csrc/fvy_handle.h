@@ -209,8 +209,8 @@ struct fvy_handle {
     // (fvy_sync, any synchronous entry point, or the next asynchronous call that reuses the set).
     // Device time of the forward / post-processing part of every detect call of a timed region (fvy_timer_start ..
     // fvy_timer_breakdown): event pairs in a small ring; a slot's elapsed times are added to the running sums when the slot comes
-    // round again (kTimeRing calls later its events have long completed) or when the breakdown is read.  (A first version kept
-    // 512 pairs per handle: a test process that had created ~32 k events segfaulted inside cuEventDestroy.)
+    // round again (kTimeRing calls later its events have long completed) or when the breakdown is read: a handle
+    // holds 128 timing events however long the timed region is.
     static constexpr int kTimeRing = 32;
     cudaEvent_t ev_tf[kTimeRing][2] = {}, ev_tp[kTimeRing][2] = {};
     bool ring_used[kTimeRing] = {};
