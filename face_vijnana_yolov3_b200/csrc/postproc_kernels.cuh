@@ -611,8 +611,9 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
                 const float th_lo = (float)(a.th * 0.99), th_hi = (float)(a.th * 1.01);
                 if (all_small) {
                     // Two phases over the 64 columns.  Phase 1, branch-free: one bit per column whose box can overlap this row's at all
-                    // (four compares on float copies - a superset of "intersection > 0"); at the usual candidate densities a few per
-                    // cent of the pairs.  Phase 2 runs the float pre-filter (same decisions as iou_prefilter_f) on those bits only;
+                    // (four compares on float copies - a superset of "intersection > 0") AND whose area is close enough to this row's
+                    // for the IoU to reach the threshold (IoU <= min / max of the areas; th_lo leaves 1 % of slack over the float
+                    // rounding): at the usual candidate densities a few per cent of the pairs.  Phase 2 runs the float pre-filter (same decisions as iou_prefilter_f) on those bits only;
                     // when a warp's rows overlap many columns (crowd scenes) it takes the branch-free form over all 64 instead, as
                     // a loop over set bits would diverge.  Bits inside the 1 % band then take the exact int64 / fp64 test one by one.
                     const float4 mef = make_float4((float)me.x, (float)me.y, (float)me.z, (float)me.w);
@@ -624,7 +625,11 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
 #pragma unroll 16
                     for (int j = 0; j < 64; ++j) {
                         const float4 b = cboxf[j];
-                        ov |= (unsigned long long)(mef.z > b.x && b.z > mef.x && mef.w > b.y && b.w > mef.y) << j;
+                        const float ab = careaf[j];
+                        // IoU <= min(area) / max(area): boxes of different anchors (areas 480 .. 30 888 px^2) cannot reach the threshold
+                        // however much they overlap - by far the most frequent overlap at the reference's anchor mask
+                        const bool ratio = fminf(my_area_f, ab) >= th_lo * fmaxf(my_area_f, ab);
+                        ov |= (unsigned long long)(ratio && mef.z > b.x && b.z > mef.x && mef.w > b.y && b.w > mef.y) << j;
                     }
                     ov &= valid;
                     unsigned long long yes = 0, band = 0;
@@ -889,14 +894,14 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const SweepArgs a) {
 
 // The same sweep for segments of up to kSweepMaxBlocks x 64 boxes with every global round trip taken off the per-block chain.
 // nms_sweep_kernel pays, per block step, a dependent global read for the next block's "score != 0" bits (order -> classes) and
-// another for the later words of the kept rows (~1.9 us per step, 64 us for 2 100 boxes).  Here the diagonal words and the alive
-// bits of ALL blocks are read up front into shared memory (one parallel pass), and the later words of a block's flagged rows are
-// fetched one whole step before they are needed (registers -> a double buffer in shared memory), so a step is two barriers and
-// shared-memory work.  Same decisions in the same order: bit-identical result.
-constexpr int kSweepMaxBlocks = 96;          // 6 144 boxes: 147 KB of shared memory at the limit
-constexpr int kSweepThreads = 512;
-constexpr int kSweepPf = (64 * (kSweepMaxBlocks - 1) + kSweepThreads - 1) / kSweepThreads;    // words a thread may hold in flight
-__host__ __device__ inline size_t sweep_small_smem(int nb) { return (size_t)nb * 8 * (2 + 64 + 2 * 64); }
+// another for the later words of the kept rows (~1.9 us per step, 64 us for 2 100 boxes).  Here the diagonal words, the row flags
+// and the alive bits of ALL blocks are read up front into shared memory (one parallel pass), and the later words of a block's
+// flagged rows are fetched two whole steps before they are needed (two register sets -> a double buffer in shared memory), so a
+// step is two barriers and shared-memory work.  Same decisions in the same order: bit-identical result.
+constexpr int kSweepMaxBlocks = 96;          // 6 144 boxes: 148 KB of shared memory at the limit
+constexpr int kSweepThreads = 512;           // 64 rows x 8 threads: thread t serves row t >> 3, later words (t & 7) + 8 k
+constexpr int kSweepPf = (kSweepMaxBlocks - 1 + 7) / 8;      // words a thread may hold in flight per register set
+__host__ __device__ inline size_t sweep_small_smem(int nb) { return (size_t)nb * 8 * (3 + 64 + 2 * 64); }
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_small_kernel(const SweepArgs a, int nb_max) {
     extern __shared__ unsigned long long sm[];
     __shared__ unsigned long long flagged_w;
@@ -906,14 +911,15 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_small_kernel(const Sw
     const int nb = (n + 63) >> 6;
     unsigned long long* removed = sm;                       // [nb_max]
     unsigned long long* alive = sm + nb_max;                // [nb_max]
-    unsigned long long* diag = sm + 2 * nb_max;             // [nb_max][64]
+    unsigned long long* rfs = sm + 2 * nb_max;              // [nb_max]  row flags (rows with a word in a later block)
+    unsigned long long* diag = sm + 3 * nb_max;             // [nb_max][64]
     unsigned long long* pre = diag + (size_t)nb_max * 64;   // [2][64][nb_max]: later words of the flagged rows of a block
     const size_t seg = (size_t)img * a.seg_stride;
     const int* ord = a.order + (size_t)img * a.capP;
     const unsigned long long* mk = a.mask + (size_t)img * a.capP * a.words;
     const unsigned long long* rf = a.rowflag + (size_t)img * a.words;
     const int lane = threadIdx.x & 31;
-    for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
+    for (int w = threadIdx.x; w < nb; w += blockDim.x) { removed[w] = 0; rfs[w] = rf[w]; }
     for (int i0 = (threadIdx.x >> 5) * 32; i0 < nb * 64; i0 += blockDim.x) {       // whole warps: i0 .. i0 + 31 share half a block
         const int i = i0 + lane;
         unsigned long long d = 0;
@@ -926,38 +932,37 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_small_kernel(const Sw
         const unsigned bal = __ballot_sync(0xffffffffu, al);
         if (lane == 0) reinterpret_cast<unsigned*>(alive)[i >> 5] = bal;
     }
-    // later words of block c's flagged rows: entry e = b * later + (w - c - 1), e < 64 * later, later = nb - c - 1
-    unsigned long long pf[kSweepPf];
-    auto fetch_rows = [&](int c) {
+    __syncthreads();                                         // rfs is read by the prefetches below
+    // later words of block c's flagged rows: thread (row b = t >> 3, lane8 = t & 7) holds words w = c + 1 + lane8 + 8 k
+    const int prow = threadIdx.x >> 3, pl8 = threadIdx.x & 7;
+    unsigned long long pf0[kSweepPf], pf1[kSweepPf];         // blocks of even / odd index: fetched TWO steps before they are stashed
+    auto fetch_rows = [&](int c, unsigned long long (&pf)[kSweepPf]) {
         const int later = nb - c - 1;
-        const unsigned long long fl = c < nb ? rf[c] : 0ull;
+        const bool on = c < nb && ((rfs[c < nb ? c : 0] >> prow) & 1ull);
+        const unsigned long long* src = mk + (size_t)(c * 64 + prow) * a.words + c + 1;
 #pragma unroll
         for (int k = 0; k < kSweepPf; ++k) {
-            const int e = threadIdx.x + k * kSweepThreads;
-            unsigned long long v = 0;
-            if (later > 0 && e < 64 * later) {
-                const int b = e / later, w = c + 1 + (e - b * later);
-                if ((fl >> b) & 1ull) v = mk[(size_t)(c * 64 + b) * a.words + w];
-            }
-            pf[k] = v;
+            const int w = pl8 + 8 * k;
+            pf[k] = (on && w < later) ? src[w] : 0ull;
         }
     };
-    auto stash_rows = [&](int c) {
+    auto stash_rows = [&](int c, const unsigned long long (&pf)[kSweepPf]) {
         const int later = nb - c - 1;
-        unsigned long long* dst = pre + (size_t)(c & 1) * 64 * nb_max;
+        unsigned long long* dst = pre + (size_t)(c & 1) * 64 * nb_max + (size_t)prow * nb_max;
 #pragma unroll
         for (int k = 0; k < kSweepPf; ++k) {
-            const int e = threadIdx.x + k * kSweepThreads;
-            if (later > 0 && e < 64 * later) dst[e] = pf[k];
+            const int w = pl8 + 8 * k;
+            if (w < later) dst[w] = pf[k];
         }
     };
-    fetch_rows(0);
-    stash_rows(0);
-    fetch_rows(1);
-    for (int blk = 0; blk < nb; ++blk) {
+    fetch_rows(0, pf0);
+    stash_rows(0, pf0);
+    fetch_rows(1, pf1);
+    fetch_rows(2, pf0);
+    auto step = [&](int blk, unsigned long long (&pf)[kSweepPf]) {      // pf: the register set of block blk + 1 (and blk + 3)
         __syncthreads();        // diag / alive / pre[blk & 1] are in place; every OR into removed[blk] has been made
-        stash_rows(blk + 1);    // fetched one step ago; pre[(blk + 1) & 1] was last read in step blk - 1, before the barrier above
-        fetch_rows(blk + 2);
+        stash_rows(blk + 1, pf);    // fetched two steps ago; pre[(blk + 1) & 1] was last read in step blk - 1, before the barrier above
+        fetch_rows(blk + 3, pf);
         if (threadIdx.x < 32) {
             const unsigned long long d_lo = diag[blk * 64 + lane], d_hi = diag[blk * 64 + lane + 32];
             const unsigned long long al = alive[blk];
@@ -975,22 +980,23 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_small_kernel(const Sw
             }
             if (lane == 0) {
                 const unsigned long long keep = al & ~cr;
-                removed[blk] = cr; flagged_w = keep & rf[blk];
+                removed[blk] = cr; flagged_w = keep & rfs[blk];
             }
         }
         __syncthreads();
         const unsigned long long fl = flagged_w;
         const int later = nb - (blk + 1);
-        if (fl && later > 0) {                              // block-uniform
-            const unsigned long long* src = pre + (size_t)(blk & 1) * 64 * nb_max;
-            for (int e = threadIdx.x; e < 64 * later; e += blockDim.x) {
-                const int b = e / later;
-                if ((fl >> b) & 1ull) {
-                    const unsigned long long m = src[e];
-                    if (m) atomicOr(&removed[blk + 1 + (e - b * later)], m);
-                }
+        if ((fl >> prow) & 1ull) {
+            const unsigned long long* src = pre + (size_t)(blk & 1) * 64 * nb_max + (size_t)prow * nb_max;
+            for (int w = pl8; w < later; w += 8) {
+                const unsigned long long m = src[w];
+                if (m) atomicOr(&removed[blk + 1 + w], m);
             }
         }
+    };
+    for (int blk = 0; blk < nb; blk += 2) {
+        step(blk, pf1);
+        if (blk + 1 < nb) step(blk + 1, pf0);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
