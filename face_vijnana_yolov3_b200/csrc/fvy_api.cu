@@ -548,6 +548,8 @@ int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host) {
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d", batch);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const Layer& L = h->layers[layer];
+    if (layer == 0 && h->fuse_stem && !h->stem_phase_valid)      // the fused forward keeps conv_0's activation on chip: make it now
+        if (int e = run_layers(h, batch, 0, 1)) return e;
     const size_t n = (size_t)batch * L.Hout * L.Wout * L.s.cout;
     float* tmp = nullptr;
     CUDA_TRY(cudaMalloc(&tmp, n * 4));

@@ -40,6 +40,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             const int m_tiles = (batch * C.p.dom_plane + kBlockM - 1) / kBlockM;
             const int tiles = C.cta2 ? ((m_tiles + 1) / 2) * C.num_n_tiles : m_tiles * C.num_n_tiles;
             const int ctas = std::max(1, std::min(tiles, C.cta2 ? h->num_sms / 2 : h->num_sms));
+            if (h->fuse_stem && C.wait_on == 1) continue;          // conv_1 runs inside the fused stem kernel: no counters
             if ((tiles + ctas - 1) / ctas <= flags_max_tiles) { wait_live[i] = 1; sig_live[C.wait_on] = 1; }
         }
     for (int i = first; i < last; ++i) {
@@ -50,8 +51,29 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             i += ch.count - 1;
             continue;
         }
+        if (L.s.src == -1 && h->fuse_stem && first == 0 && last == (int)h->layers.size()) {
+            // conv_0 + conv_1 in one kernel: conv_0's activation never leaves shared memory
+            if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
+            FuseParams f = h->fuse;
+            f.batch = batch;
+            const int items = batch * f.tiles_w * f.segs;
+            const int grid = std::min(items, h->num_sms);
+            if (h->cur_dtype == FVY_F32)
+                stem_conv1_fused_kernel<float><<<grid, kFuseThreads, kFuseSmem, h->stream>>>(h->tmap_w1f, (const float*)h->cur_img, f);
+            else if (h->cur_dtype == FVY_U8)
+                stem_conv1_fused_kernel<unsigned char><<<grid, kFuseThreads, kFuseSmem, h->stream>>>(h->tmap_w1f, (const unsigned char*)h->cur_img, f);
+            else
+                stem_conv1_fused_kernel<double><<<grid, kFuseThreads, kFuseSmem, h->stream>>>(h->tmap_w1f, (const double*)h->cur_img, f);
+            CUDA_TRY(cudaGetLastError());
+            ++h->launches;
+            h->stem_phase_valid = false;
+            if (h->last_slot >= 0 && !h->capturing) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
+            ++i;                   // conv_1 is done as well
+            continue;
+        }
         if (L.s.src == -1) {       // conv_0: stem_strip_kernel straight from the image
             if (!h->cur_img) return fail(FVY_E_STATE, "no input image resident for conv_0");
+            h->stem_phase_valid = true;
             const long long total = (long long)batch * (h->cfg.net_w / 16) * h->cfg.net_h;     // (image, strip, row) triples
             const int blocks = (int)std::min<long long>((total + kStripWarps - 1) / kStripWarps, (long long)h->num_sms * h->stem_blocks_per_sm);
             __nv_bfloat16* dst = (__nv_bfloat16*)L.p.out[0].ptr;

@@ -22,6 +22,7 @@
 #include "postproc_kernels.cuh"
 
 #include "stem_kernel.cuh"
+#include "stem_conv1_fused.cuh"
 #include "prepost_kernels.cuh"
 #include "train_kernels.cuh"
 
@@ -162,6 +163,10 @@ struct fvy_handle {
     int stem_blocks_per_sm = 3;          // resident blocks of stem_strip_kernel (occupancy query)
     __nv_bfloat16* d_stem_w2 = nullptr;  // conv_0 weights in stem_strip_kernel's K order (k = 10 r + 3 q + ci)
     const void* cur_img = nullptr; int cur_dtype = FVY_F32;   // device image of the current forward (layer 0 re-runs)
+    // conv_0 + conv_1 in one kernel (stem_conv1_fused_kernel): conv_0's activation stays in shared memory.  Whole forwards only;
+    // single-layer runs (profiling, fvy_layer_output of conv_0) use the separate kernels.
+    bool fuse_stem = false; bool stem_phase_valid = false;
+    CUtensorMap tmap_w1f; FuseParams fuse;
     long long launches = 0;
     long long weight_count = 0;
     // forward

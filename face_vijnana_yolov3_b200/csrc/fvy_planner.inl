@@ -2,6 +2,7 @@
 // Included by fvy_api.cu inside no namespace (opens fvy itself).
 namespace fvy {
 
+constexpr int kFuseStemDefault = 0;        // FVY_FUSE_STEM: conv_0 + conv_1 in one kernel
 constexpr int kChainSchedDefault = 0;      // FVY_CHAIN_SCHED when neither the environment nor fvy_config.flags says otherwise
 
 template <int BN, int BK, bool CTA2>
@@ -415,6 +416,32 @@ static int build_plan(fvy_handle* h) {
                 h->chains.clear();
                 h->use_chain = false;
             }
+        }
+    }
+    // ---- conv_0 + conv_1 fused (csrc/stem_conv1_fused.cuh): conv_1 = 3x3 / stride 2 / 32 -> 64 reading conv_0, padded output only
+    if (h->layers.size() >= 2) {
+        const Layer& L0 = h->layers[0];
+        Layer& L1 = h->layers[1];
+        const bool shape_ok = L0.s.src == -1 && L0.s.cout == 32 && L1.s.src == L0.s.idx && L1.s.k == 3 && L1.s.stride == 2 && L1.s.cin == 32 &&
+                              L1.s.cout == 64 && L1.s.bn && L1.s.leaky && L1.s.res < 0 && L1.tap_perm && L1.p.out[0].kind == OUT_PADDED &&
+                              L1.p.out[1].kind == OUT_NONE && L1.p.out[0].pitch == 64 && L1.p.out[0].choff == 0;
+        h->fuse_stem = shape_ok && env_int("FVY_FUSE_STEM", kFuseStemDefault) != 0 && !(c.flags & FVY_CFG_NO_FUSED_STEM);
+        if (h->fuse_stem) {
+            if (int e = make_tmap_2d(&h->tmap_w1f, L1.w, 288, 64, 288, 32, 64)) return e;
+            const int Ho = c.net_h / 2, Wo = c.net_w / 2;
+            FuseParams& f = h->fuse;
+            memset(&f, 0, sizeof(f));
+            f.H = c.net_h; f.W = c.net_w;
+            f.tiles_w = (Wo + kBlockM - 1) / kBlockM;
+            f.tile_w = (Wo + f.tiles_w - 1) / f.tiles_w;
+            f.seg_rows = std::max(2, std::min(32, (Ho + 15) / 16));
+            if (const int sr = env_int("FVY_FUSE_SEG", 0)) f.seg_rows = std::max(1, sr);
+            f.segs = (Ho + f.seg_rows - 1) / f.seg_rows;
+            f.w0 = h->d_stem_w2; f.bias0 = L0.bias; f.bias1 = L1.bias; f.out = (__nv_bfloat16*)L1.p.out[0].ptr;
+            if ((2 * f.tile_w + 1 + 15) / 16 > kFuseProducers * kFuseMaxStrips) h->fuse_stem = false;
+            CUDA_TRY(cudaFuncSetAttribute(stem_conv1_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
+            CUDA_TRY(cudaFuncSetAttribute(stem_conv1_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
+            CUDA_TRY(cudaFuncSetAttribute(stem_conv1_fused_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
         }
     }
     return FVY_OK;

@@ -460,35 +460,33 @@ __device__ __forceinline__ uint32_t float_orderable(float f) {
 // Every warp owns aligned 64-key segments; the compare-exchange steps with partner distance j <= 32 stay inside a segment, so a
 // whole run of them (the tail j = 32 .. 1 of every stage, and all of the stages k <= 64) needs only __syncwarp; the block-wide
 // barrier is paid for the steps with j >= 64 alone: 21 instead of 78 barriers at np2 = 4096.
-__device__ __forceinline__ void bitonic_cmpx(unsigned long long* keys, int i, int j, int k) {
-    const int l = i ^ j;
-    if (l > i) {
-        const unsigned long long a = keys[i], b = keys[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { keys[i] = b; keys[l] = a; }
-    }
+// compare-exchange of pair p of a step with partner distance j (a power of two): elements i and i + j, i = (p / j) * 2 j + p % j -
+// every thread that calls this does work (indexing by element instead leaves half of the lanes idle in every step)
+__device__ __forceinline__ void bitonic_pair(unsigned long long* keys, int p, int j, int k) {
+    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+    const unsigned long long a = keys[i], b = keys[i + j];
+    const bool up = (i & k) == 0;
+    if ((a > b) == up) { keys[i] = b; keys[i + j] = a; }
 }
 __device__ void bitonic_sort_u64(unsigned long long* keys, int np2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // stages k = 2 .. 64: entirely inside 64-key segments
+    // stages k = 2 .. 64: entirely inside 64-key segments (32 pairs per step: one per lane)
     for (int seg = warp * 64; seg < np2; seg += nwarps * 64) {
         for (int k = 2; k <= 64; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
-                bitonic_cmpx(keys, seg + lane, j, k);
-                bitonic_cmpx(keys, seg + lane + 32, j, k);
+                bitonic_pair(keys, (seg >> 1) + lane, j, k);
                 __syncwarp();
             }
     }
     __syncthreads();
     for (int k = 128; k <= np2; k <<= 1) {
         for (int j = k >> 1; j >= 64; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += blockDim.x) bitonic_cmpx(keys, i, j, k);
+            for (int p = threadIdx.x; p < (np2 >> 1); p += blockDim.x) bitonic_pair(keys, p, j, k);
             __syncthreads();
         }
         for (int seg = warp * 64; seg < np2; seg += nwarps * 64) {
             for (int j = 32; j > 0; j >>= 1) {
-                bitonic_cmpx(keys, seg + lane, j, k);
-                bitonic_cmpx(keys, seg + lane + 32, j, k);
+                bitonic_pair(keys, (seg >> 1) + lane, j, k);
                 __syncwarp();
             }
         }
@@ -551,7 +549,9 @@ struct MaskArgs {
 };
 
 // Persistent blocks of 64 threads; one 64x64 tile per iteration: thread t owns sorted row r*64+t and
-// produces the 64-bit word of column block c (bit j set <=> IoU(row, c*64+j) >= th and c*64+j > row).
+// produces the 64-bit word of column block c (bit j set <=> IoU(row, c*64+j) >= th and c*64+j > row).  Work items are the
+// upper-triangle tiles only, dealt round-robin: every block gets the same number of real tiles (dealing all nb^2 tile slots and
+// skipping the lower triangle left some blocks with twice the mean).
 __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
     __shared__ int4 cbox[64];
     __shared__ float4 cboxf[64];
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
     for (int b = threadIdx.x; b < a.batch; b += blockDim.x) {
         const int n = min(a.counts[b], a.seg_stride);
         const int nb = (n + 63) >> 6;
-        tile_prefix[b + 1] = nb * nb;
+        tile_prefix[b + 1] = nb * (nb + 1) / 2;          // upper-triangle tiles only (c >= r): every work item is a real tile
     }
     if (threadIdx.x == 0) { tile_prefix[0] = 0; all_wellformed = 1; }
     __syncthreads();
@@ -576,9 +576,10 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
         while (tile_prefix[img + 1] <= t) ++img;          // t is increasing
         const int n = min(a.counts[img], a.seg_stride);
         const int nb = (n + 63) >> 6;
-        const int lt = t - tile_prefix[img];
-        const int r = lt / nb, c = lt - r * nb;
-        if (c < r) continue;                               // block-uniform
+        int lt = t - tile_prefix[img];
+        int r = 0;
+        while (lt >= nb - r) { lt -= nb - r; ++r; }        // row r holds the nb - r tiles c = r .. nb - 1 (block-uniform scalar loop)
+        const int c = r + lt;
         const int4* sb = a.sbox + (size_t)img * a.capP;
         const int col = c * 64 + threadIdx.x;
         const int row = r * 64 + threadIdx.x;

@@ -367,3 +367,42 @@ def test_training_step_with_fvy_bn_matches_autograd_baseline():
     assert worst <= 1e-2, worst
     # the first Keras-Adam step moves every weight by ~lr * sign(g): a gradient whose sign differs in the noise moves it by 2 lr
     assert rel_l2(res["fvy"][2], res["torch"][2]) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------ conv_0 + conv_1 in one kernel
+@pytest.mark.parametrize("B,H,W", [(3, 416, 416), (2, 608, 608), (2, 320, 480), (1, 64, 64)])
+def test_fused_stem_is_bit_identical_to_the_two_kernel_path(B, H, W):
+    """stem_conv1_fused_kernel (conv_0's activation kept in shared memory) against stem_strip_kernel + conv_igemm_kernel with the
+    4-phase activation in HBM: same MMA shapes, K order and epilogue arithmetic, so conv_1's output and the head logits must be
+    identical bit for bit - for float32, float64 and uint8 images, square / wide / tiny networks (1, 2 and 3 column tiles)."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    rng = np.random.default_rng(5)
+    x = rng.random((B, H, W, 3), dtype=np.float32)
+    x8 = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    old = os.environ.get("FVY_FUSE_STEM")
+    res = {}
+    try:
+        for mode in ("1", "0"):
+            os.environ["FVY_FUSE_STEM"] = mode
+            eng = Engine(H, W, head=L.HEAD_YOLO3, nb_class=1, max_batch=B)
+            eng.load_weights(stream)
+            outs = eng.forward(x)
+            c1 = eng.layer_output(1, B)                     # conv_1's padded output, unpacked
+            c0 = eng.layer_output(0, B)                     # conv_0 (produced on demand in fused mode)
+            o64 = eng.forward(x.astype(np.float64))
+            o8 = eng.forward(x8)
+            n_launch0 = eng.launch_count
+            eng.forward(x)
+            res[mode] = (outs, c1, c0, o64, o8, eng.launch_count - n_launch0)
+            eng.close()
+    finally:
+        if old is None:
+            os.environ.pop("FVY_FUSE_STEM", None)
+        else:
+            os.environ["FVY_FUSE_STEM"] = old
+    assert res["1"][5] == res["0"][5] - 1                   # one launch fewer: the fused path really ran
+    assert np.array_equal(res["1"][1], res["0"][1]) and np.array_equal(res["1"][2], res["0"][2])
+    assert np.abs(res["0"][1]).max() > 0
+    for k in (0, 3, 4):
+        for a, b in zip(res["1"][k], res["0"][k]):
+            assert np.array_equal(a, b)

@@ -35,9 +35,7 @@ python tools/summarize_ncu.py traffic gpurun_out/${T}_traffic.csv gpurun_out/${T
 ncu --set full --clock-control none --import-source on -k regex:"decode_yolo|sort_scores|nms_mask|nms_sweep|assemble" -c 5 -o gpurun_out/${T}_post -f \
     python /tmp/fwd2.py detect > gpurun_out/${T}_ncu3.log 2>&1
 ncu -i gpurun_out/${T}_post.ncu-rep --page raw --csv > gpurun_out/${T}_post_raw.csv 2>/dev/null; rm -f gpurun_out/${T}_post.ncu-rep
-# compute-sanitizer: one batch-40 forward + detect with chains, tile-dependency flags and the CUDA graph on (default configuration)
-for tool in memcheck synccheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/fwd2.py detect > gpurun_out/${T}_sanitizer_$tool.log 2>&1
-  echo "compute-sanitizer $tool rc=$?" | tee -a gpurun_out/${T}_sanitizer_$tool.log; tail -3 gpurun_out/${T}_sanitizer_$tool.log
-done
+# compute-sanitizer (racecheck / synccheck / memcheck asked for by VERDICT r1) is closed on this GPU pool: the wrapper refuses to
+# start it (profiles/r02_sanitizer_unavailable.log holds its answer).  What stands in for it: every spin wait in the kernels is bounded
+# and traps with a message, and the full-size equivalence tests compare chains + tile flags + graph against plain per-layer launches.
 for f in bench bench_608x320 bench_stress bench_train bench_ref; do cut -c1-330 gpurun_out/${T}_$f.json; echo; done; tail -2 gpurun_out/${T}_check.log; tail -5 gpurun_out/${T}_bench.err
