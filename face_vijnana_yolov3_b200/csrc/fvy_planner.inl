@@ -432,13 +432,13 @@ static int build_plan(fvy_handle* h) {
             FuseParams& f = h->fuse;
             memset(&f, 0, sizeof(f));
             f.H = c.net_h; f.W = c.net_w;
-            f.tiles_w = (Wo + kBlockM - 1) / kBlockM;
+            f.tiles_w = (Wo + kFuseMaxTileW - 1) / kFuseMaxTileW;
             f.tile_w = (Wo + f.tiles_w - 1) / f.tiles_w;
             f.seg_rows = std::max(2, std::min(32, (Ho + 15) / 16));
             if (const int sr = env_int("FVY_FUSE_SEG", 0)) f.seg_rows = std::max(1, sr);
             f.segs = (Ho + f.seg_rows - 1) / f.seg_rows;
             f.w0 = h->d_stem_w2; f.bias0 = L0.bias; f.bias1 = L1.bias; f.out = (__nv_bfloat16*)L1.p.out[0].ptr;
-            if ((2 * f.tile_w + 1 + 15) / 16 > kFuseProducers * kFuseMaxStrips) h->fuse_stem = false;
+            if ((2 * f.tile_w + 1 + 15) / 16 > kFuseProducers) h->fuse_stem = false;
             CUDA_TRY(cudaFuncSetAttribute(stem_conv1_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
             CUDA_TRY(cudaFuncSetAttribute(stem_conv1_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
             CUDA_TRY(cudaFuncSetAttribute(stem_conv1_fused_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));

@@ -5,9 +5,9 @@
 // 158 us + 124 us of HBM-bound time for 7 % of the FLOPs.  Here a persistent CTA produces the conv_0 rows an output row of conv_1
 // needs in SHARED memory, in exactly the form conv_1's tcgen05 MMA reads its A operand in, and consumes them from there:
 //
-//   producer warps (7)   conv_0 with warp-level bf16 MMAs (m16n8k16), the same staged-row scheme, K order and arithmetic as
-//                        stem_strip_kernel (bit-identical values): every warp owns up to three 16-pixel strips of the tile's
-//                        column range and walks down the rows, keeping a private ring of staged image rows; results are written
+//   producer warps (14)  conv_0 with warp-level bf16 MMAs (m16n8k16), the same staged-row scheme, K order and arithmetic as
+//                        stem_strip_kernel (bit-identical values): every warp owns one 16-pixel strip of the tile's column
+//                        range and walks down the rows, keeping a private ring of staged image rows; results are written
 //                        as bf16 into a ring of conv_0 ROW SLOTS: per row two arrays - even and odd padded columns - of 64-byte
 //                        entries (32 channels) in the 64-byte-swizzle K-major layout (the column phases a stride-2 tap reads)
 //   MMA warp (1 thread)  per output row tile (<= 128 pixels of one output row): 9 taps x 2 K-steps of tcgen05.mma M = 128, N = 64
@@ -23,16 +23,19 @@
 // L2) and conv_1's output written once.  Row slots, TMEM stages and all barrier phases carry across tiles and work items.
 #pragma once
 
+#include <type_traits>
+
 #include "conv_igemm_sm100.cuh"
 #include "stem_kernel.cuh"
 
 namespace fvy {
 
-constexpr int kFuseProducers = 7;                  // producer warps: 14 strips of 16 pixels at 416 (two each)
+constexpr int kFuseProducers = 14;                 // producer warps: one 16-pixel strip each (14 strips at 416)
 constexpr int kFuseThreads = 32 * (4 + 1 + kFuseProducers);      // warps 0-3 epilogue, 4 MMA / TMEM / weights, 5.. producers
 constexpr int kFuseSlots = 6;                      // conv_0 row slots
 constexpr int kFuseAcc = 4;                        // accumulator stages of 64 TMEM columns
-constexpr int kFuseMaxStrips = 3;                  // strips per producer warp (tile width <= 128 pixels -> <= 17 strips)
+constexpr int kFuseMaxTileW = (16 * kFuseProducers - 1) / 2;     // 111: 14 strips cover 2 x 111 + 1 conv_0 pixels
+constexpr int kFusePf = 4;                         // image rows in flight per strip (registers): ~4 row times cover the HBM latency
 constexpr int kFuseArrayBytes = 9 * 1024;          // one column-phase array of a row slot: <= 129 entries x 64 B, 1 024-byte aligned
 constexpr int kFuseSlotBytes = 2 * kFuseArrayBytes;
 constexpr int kFuseW1Bytes = 9 * 64 * 64;          // conv_1 weights: nine [64 x 32] bf16 tiles
@@ -43,9 +46,35 @@ constexpr int kFuseOffFrag = kFuseOffBias + 256;                           // ui
 constexpr int kFuseOffW1 = 5 * 1024;
 constexpr int kFuseOffSlots = kFuseOffW1 + kFuseW1Bytes;                   // 41 KB, 1 024-aligned
 constexpr int kFuseOffStage = kFuseOffSlots + kFuseSlots * kFuseSlotBytes + 2048;
-constexpr int kFuseStageBytes = kFuseMaxStrips * 4 * 2 * kStripLen * 2;    // per producer warp: strips x 4 image rows x 2 copies x 64 bf16
+constexpr int kFuseStageBytes = 4 * 2 * kStripLen * 2;                     // per producer warp: 4 image rows x 2 copies x 64 bf16
 constexpr int kFuseSmem = kFuseOffStage + kFuseProducers * kFuseStageBytes + 1024;   // + alignment slack
 static_assert(kFuseOffSlots % 1024 == 0 && kFuseSmem <= 232448, "fused stem: shared-memory plan");
+static_assert(kFusePf == 4, "the row loop is unrolled by hand over the register slots");
+
+__device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+// Long waits of the consumer roles (a tile takes microseconds): sleep between polls so that the spinning warps do not take
+// issue slots from the producer warps they share a scheduler with (in a first version 35 % of all issued instructions were polls).
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        if (mbar_try_u32(addr, parity)) return;
+        __nanosleep(spin < 4 ? 64 : 256);
+        if (spin > (1u << 22)) {
+            printf("fvy: fused stem wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+            __trap();
+        }
+    }
+}
 
 struct FuseParams {
     int batch, H, W;              // network input
@@ -124,7 +153,7 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
                     for (int r = 0; r < 3; ++r) {
                         const long long rc = rowc + 2 * i + r;
                         const int slot = (int)(rc % kFuseSlots);
-                        mbar_wait(&row_full[slot], (uint32_t)((rc / kFuseSlots) & 1));
+                        mbar_wait_sleepy(&row_full[slot], (uint32_t)((rc / kFuseSlots) & 1));
                         tc_fence_after();
                         const uint32_t srow16 = slots16 + (uint32_t)slot * (kFuseSlotBytes >> 4);
 #pragma unroll
@@ -161,7 +190,7 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
             const int x0 = tw * p.tile_w, w = min(p.tile_w, Wo - x0);
             for (int y = y0; y < y1; ++y, ++tilec) {
                 const int acc = (int)(tilec % kFuseAcc);
-                mbar_wait(&tmem_full[acc], (uint32_t)((tilec / kFuseAcc) & 1));
+                mbar_wait_sleepy(&tmem_full[acc], (uint32_t)((tilec / kFuseAcc) & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 64;
                 __nv_bfloat16* dst = p.out + (((size_t)n * (Ho + 2) + (y + 1)) * (Wo + 2) + (x0 + r + 1)) * 64;
@@ -204,17 +233,24 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
         }
     } else {
         // ===================== producers: conv_0 rows into the row slots =====================
-        const int pw = warp - 5;                          // 0 .. kFuseProducers - 1
+        // One strip per warp; every shared-memory access below uses explicit shared-space addresses computed once per work item
+        // (generic loads / stores through pointers carved out of the aligned base cost three times the instructions).
+        const int pw = warp - 5;                          // strip index 0 .. kFuseProducers - 1
         const int quad = lane & 3, grp = lane >> 2;
-        uint16_t* stage_base = reinterpret_cast<uint16_t*>(smem + kFuseOffStage + pw * kFuseStageBytes);     // [strip][row & 3][copy][64]
-        int pr[4], pj[4];
+        const int par = grp & 1;                          // parity of this lane's pixels: which staged copy gives 4-byte aligned pairs
+        const uint32_t stage_u32 = smem_u32(smem + kFuseOffStage + pw * kFuseStageBytes);      // [row & 3][copy][64] bf16
+        const uint32_t slots_u32 = smem_u32(slots);
+        const uint32_t swf_u32 = smem_u32(swf) + lane * 16, sbf_u32 = smem_u32(sbf) + lane * 8;
+        // A fragments: this lane's four (k, k + 1) pairs of a pixel, k = ks * 16 + half * 8 + quad * 2 -> filter row k / 10, window element k % 10
+        int frow[4]; uint32_t foff[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int k = (i >> 1) * 16 + (i & 1) * 8 + quad * 2;
-            pr[i] = k < 30 ? k / 10 : 0;
-            pj[i] = k < 30 ? k % 10 : 0;
+            frow[i] = k < 30 ? k / 10 : 0;
+            const int pjv = k < 30 ? k % 10 : 0;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) foff[i][rr] = (uint32_t)(par * kStripLen + pjv - par + (grp + rr * 8) * 3) * 2u;
         }
-        const int par = grp & 1;
         long long rowc = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int seg = item % p.segs;
@@ -224,111 +260,99 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
             const int L = y1 - y0;
             const int x0 = tw * p.tile_w, w = min(p.tile_w, Wo - x0);
             const int npx = 2 * w + 1;                    // conv_0 pixels per row: padded columns 2 x0 .. 2 x0 + 2 w (q = 0 .. 2 w)
-            const int nstrips = (npx + 15) >> 4;
+            const bool has = 16 * pw < npx;
             const T* base = img + (size_t)n * p.H * p.W * 3;
-            // this warp's strips: pw, pw + P, pw + 2 P
-            int c0s[kFuseMaxStrips];
-            bool ok0[kFuseMaxStrips], ok1[kFuseMaxStrips], has[kFuseMaxStrips];
+            const int cfirst = 2 * x0 - 1 + 16 * pw;      // conv_0 column of the strip's first pixel
+            const int c0 = (cfirst - 1) * 3 + lane;       // staged element `lane` = image element (cfirst - 1) * 3 + lane of the row
+            const bool ok0 = has && c0 >= 0 && c0 < p.W * 3;
+            const bool ok1 = has && lane + 32 < 54 && c0 + 32 >= 0 && c0 + 32 < p.W * 3;
+            // where this lane's eight results of a row go inside a row slot, and which of its two pixels are real / padding
+            uint32_t soff[2][4]; bool live[2], zero[2];
 #pragma unroll
-            for (int u = 0; u < kFuseMaxStrips; ++u) {
-                const int mt = pw + u * kFuseProducers;
-                has[u] = mt < nstrips;
-                const int cfirst = 2 * x0 - 1 + 16 * mt;                  // conv_0 column of the strip's first pixel
-                c0s[u] = (cfirst - 1) * 3 + lane;                          // staged element `lane` = image element (cfirst - 1) * 3 + lane
-                ok0[u] = has[u] && c0s[u] >= 0 && c0s[u] < p.W * 3;
-                ok1[u] = has[u] && lane + 32 < 54 && c0s[u] + 32 >= 0 && c0s[u] + 32 < p.W * 3;
+            for (int rr = 0; rr < 2; ++rr) {
+                const int q = 16 * pw + grp + rr * 8;      // padded column 2 x0 + q
+                const int cc = 2 * x0 - 1 + q;             // conv_0 column
+                live[rr] = has && q < npx;
+                zero[rr] = cc < 0 || cc >= p.W;            // conv_1's zero padding, not conv_0 of a padded image
+                const int entry = q >> 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    soff[rr][j] = (uint32_t)((q & 1) * kFuseArrayBytes + entry * 64 + ((j ^ ((entry >> 1) & 3)) << 4) + quad * 4);
             }
-            auto fetch = [&](int u, int hh, float& a, float& b) {
+            auto fetch = [&](int hh, float& a, float& b) {
                 const bool in = hh >= 0 && hh < p.H;
                 const T* src = base + (size_t)(in ? hh : 0) * p.W * 3;
-                a = (in && ok0[u]) ? stem_px(__ldg(src + c0s[u])) : 0.f;
-                b = (in && ok1[u]) ? stem_px(__ldg(src + c0s[u] + 32)) : 0.f;
+                a = (in && ok0) ? stem_px(__ldg(src + c0)) : 0.f;
+                b = (in && ok1) ? stem_px(__ldg(src + c0 + 32)) : 0.f;
             };
-            auto stage = [&](int u, int hh, float a, float b) {
-                uint16_t* E = stage_base + ((u * 4 + (hh & 3)) * 2 + 0) * kStripLen;
-                uint16_t* O = E + kStripLen;
+            auto stage = [&](int hh, float a, float b) {
+                const uint32_t E = stage_u32 + (uint32_t)((hh & 3) * 2 * kStripLen * 2), O = E + kStripLen * 2;
                 const uint16_t x = __bfloat16_as_ushort(__float2bfloat16_rn(a)), y = __bfloat16_as_ushort(__float2bfloat16_rn(b));
-                E[lane] = x; E[lane + 32] = y;
-                if (lane >= 1) O[lane - 1] = x;
-                O[lane + 31] = y;
+                sts16(E + lane * 2, x); sts16(E + (lane + 32) * 2, y);
+                if (lane >= 1) sts16(O + (lane - 1) * 2, x);
+                sts16(O + (lane + 31) * 2, y);
             };
             // conv_0 rows of the item: padded rows 2 y0 .. 2 (y1 - 1) + 2, i.e. conv_0 rows ic = 2 y0 - 1 .. 2 y1 - 1
             const int ic0 = 2 * y0 - 1, nrows = 2 * L + 1;
-            float p0a[kFuseMaxStrips], p0b[kFuseMaxStrips], p1a[kFuseMaxStrips], p1b[kFuseMaxStrips];   // image rows ic + 2, ic + 3 in flight
+            float pfa[kFusePf], pfb[kFusePf];             // image rows ic + 2 .. ic + 5 in flight: slot (k & 3) holds row ic0 + k + 2
             __syncwarp();
-            {   // prime the staged ring: all loads go out before the first one is used
-                float ra[kFuseMaxStrips][3], rb[kFuseMaxStrips][3];
+            if (has) {      // prime the staged ring: all loads go out before the first one is used
+                float ra[3], rb[3];
 #pragma unroll
-                for (int u = 0; u < kFuseMaxStrips; ++u) {
-                    if (!has[u]) continue;
+                for (int d = 0; d < 3; ++d) fetch(ic0 - 1 + d, ra[d], rb[d]);
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) fetch(u, ic0 - 1 + d, ra[u][d], rb[u][d]);
-                    fetch(u, ic0 + 2, p0a[u], p0b[u]);
-                    fetch(u, ic0 + 3, p1a[u], p1b[u]);
-                }
+                for (int d = 0; d < kFusePf; ++d) fetch(ic0 + 2 + d, pfa[d], pfb[d]);
 #pragma unroll
-                for (int u = 0; u < kFuseMaxStrips; ++u) {
-                    if (!has[u]) continue;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) stage(u, ic0 - 1 + d, ra[u][d], rb[u][d]);
-                }
+                for (int d = 0; d < 3; ++d) stage(ic0 - 1 + d, ra[d], rb[d]);
             }
             __syncwarp();
-            for (int k = 0; k < nrows; ++k) {
+            auto do_row = [&](auto slot_c, int k) {
+                constexpr int PS = decltype(slot_c)::value;
                 const int ic = ic0 + k;
                 const long long rc = rowc + k;
                 const int slot = (int)(rc % kFuseSlots);
                 mbar_wait(&row_empty[slot], (uint32_t)(((rc / kFuseSlots) & 1) ^ 1));
-                uint8_t* arrE = slots + slot * kFuseSlotBytes;
-                const bool row_in = ic >= 0 && ic < p.H;                  // outside: conv_1's zero padding, not conv_0 of a padded image
-#pragma unroll
-                for (int u = 0; u < kFuseMaxStrips; ++u) {
-                    if (!has[u]) continue;
-                    const int mt = pw + u * kFuseProducers;
+                if (has) {
+                    const uint32_t slot_u32 = slots_u32 + (uint32_t)slot * kFuseSlotBytes;
+                    const bool row_in = ic >= 0 && ic < p.H;
                     uint32_t afrag[2][4];
-                    const uint16_t* sb = stage_base + (u * 4) * 2 * kStripLen;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const uint16_t* rp = sb + ((((ic - 1 + pr[i]) & 3) * 2 + par) * kStripLen) + pj[i] - par;
+                        const uint32_t rowb = stage_u32 + (uint32_t)(((ic - 1 + frow[i]) & 3) * 2 * kStripLen * 2);
 #pragma unroll
-                        for (int rr = 0; rr < 2; ++rr)
-                            afrag[i >> 1][(i & 1) * 2 + rr] = *reinterpret_cast<const uint32_t*>(rp + (grp + rr * 8) * 3);
+                        for (int rr = 0; rr < 2; ++rr) afrag[i >> 1][(i & 1) * 2 + rr] = lds_u32(rowb + foff[i][rr]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 wf = swf[j * 32 + lane];
-                        const float2 bj = sbf[j * 32 + lane];
+                        const uint4 wf = lds128(swf_u32 + j * 512);
+                        const float2 bj = lds64f(sbf_u32 + j * 256);
                         float acc[4] = {bj.x, bj.y, bj.x, bj.y};
                         mma_m16n8k16_bf16(acc, afrag[0], wf.x, wf.y);
                         mma_m16n8k16_bf16(acc, afrag[1], wf.z, wf.w);
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
-                            const int q = 16 * mt + grp + rr * 8;           // padded column 2 x0 + q of the conv_0 row
-                            if (q >= npx) continue;
-                            const int cc = 2 * x0 - 1 + q;                  // conv_0 column
                             float a = acc[rr * 2 + 0], b = acc[rr * 2 + 1];
                             a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
                             __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
                             uint32_t val = *reinterpret_cast<uint32_t*>(&pk);
-                            if (!row_in || cc < 0 || cc >= p.W) val = 0u;
-                            const int entry = q >> 1;
-                            uint8_t* arr = arrE + (q & 1) * kFuseArrayBytes;
-                            *reinterpret_cast<uint32_t*>(arr + entry * 64 + ((j ^ ((entry >> 1) & 3)) << 4) + quad * 4) = val;
+                            if (!row_in || zero[rr]) val = 0u;
+                            if (live[rr]) sts32(slot_u32 + soff[rr][j], (int)val);
                         }
                     }
+                    // image row ic + 2 (loaded four rows ago) replaces row ic - 2 in the staged ring; its register slot is refilled
+                    __syncwarp();
+                    stage(ic + 2, pfa[PS], pfb[PS]);
+                    fetch(ic + 2 + kFusePf, pfa[PS], pfb[PS]);
+                    fence_proxy_async();    // generic-proxy writes of the row -> visible to the tensor core's async-proxy reads
                 }
-                // image row ic + 2 (loaded two iterations ago) replaces row ic - 2 in the staged ring; the next load goes out
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < kFuseMaxStrips; ++u) {
-                    if (!has[u]) continue;
-                    stage(u, ic + 2, p0a[u], p0b[u]);
-                    p0a[u] = p1a[u]; p0b[u] = p1b[u];
-                    fetch(u, ic + 4, p1a[u], p1b[u]);
-                }
-                fence_proxy_async();        // generic-proxy writes of the row -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&row_full[slot]);
+            };
+            for (int k = 0; k < nrows; k += kFusePf) {
+                do_row(std::integral_constant<int, 0>{}, k);
+                if (k + 1 < nrows) do_row(std::integral_constant<int, 1>{}, k + 1);
+                if (k + 2 < nrows) do_row(std::integral_constant<int, 2>{}, k + 2);
+                if (k + 3 < nrows) do_row(std::integral_constant<int, 3>{}, k + 3);
             }
             rowc += nrows;
         }
