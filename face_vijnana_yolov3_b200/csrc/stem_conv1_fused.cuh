@@ -268,6 +268,7 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
             const bool ok1 = has && lane + 32 < 54 && c0 + 32 >= 0 && c0 + 32 < p.W * 3;
             // where this lane's eight results of a row go inside a row slot, and which of its two pixels are real / padding
             uint32_t soff[2][4]; bool live[2], zero[2];
+            const bool edge = 16 * pw + 15 >= npx - 1 || cfirst < 0;      // the strip holds the row's first or last pixel (may be padding)
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int q = 16 * pw + grp + rr * 8;      // padded column 2 x0 + q
@@ -314,6 +315,7 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
                 mbar_wait(&row_empty[slot], (uint32_t)(((rc / kFuseSlots) & 1) ^ 1));
                 if (has) {
                     const uint32_t slot_u32 = slots_u32 + (uint32_t)slot * kFuseSlotBytes;
+                    const bool plain = ic >= 0 && ic < p.H && !edge;     // warp-uniform: no padding pixel among this strip's results
                     const bool row_in = ic >= 0 && ic < p.H;
                     uint32_t afrag[2][4];
 #pragma unroll
@@ -331,22 +333,25 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
                         mma_m16n8k16_bf16(acc, afrag[1], wf.z, wf.w);
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
-                            float a = acc[rr * 2 + 0], b = acc[rr * 2 + 1];
-                            a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b);
-                            __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
-                            uint32_t val = *reinterpret_cast<uint32_t*>(&pk);
-                            if (!row_in || zero[rr]) val = 0u;
+                            float m0, m1;
+                            mul2(m0, m1, acc[rr * 2 + 0], acc[rr * 2 + 1], 0.1f);        // LeakyReLU(0.1) = max(v, 0.1 v), as stem_strip_kernel
+                            uint32_t val = pack_bf16x2(fmaxf(acc[rr * 2 + 0], m0), fmaxf(acc[rr * 2 + 1], m1));
+                            if (!plain && (!row_in || zero[rr])) val = 0u;
                             if (live[rr]) sts32(slot_u32 + soff[rr][j], (int)val);
                         }
                     }
-                    // image row ic + 2 (loaded four rows ago) replaces row ic - 2 in the staged ring; its register slot is refilled
-                    __syncwarp();
-                    stage(ic + 2, pfa[PS], pfb[PS]);
-                    fetch(ic + 2 + kFusePf, pfa[PS], pfb[PS]);
                     fence_proxy_async();    // generic-proxy writes of the row -> visible to the tensor core's async-proxy reads
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&row_full[slot]);
+                // Only now the next image row is requested: the fence above waits for the thread's outstanding memory operations, so
+                // a load issued in front of it would expose its whole latency in every row.  Image row ic + 2 (loaded four rows ago)
+                // replaces row ic - 2 in the staged ring; its register slot is refilled.
+                if (has) {
+                    stage(ic + 2, pfa[PS], pfb[PS]);
+                    fetch(ic + 2 + kFusePf, pfa[PS], pfb[PS]);
+                }
+                __syncwarp();
             };
             for (int k = 0; k < nrows; k += kFusePf) {
                 do_row(std::integral_constant<int, 0>{}, k);
