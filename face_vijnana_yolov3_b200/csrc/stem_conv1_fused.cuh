@@ -268,7 +268,6 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
             const bool ok1 = has && lane + 32 < 54 && c0 + 32 >= 0 && c0 + 32 < p.W * 3;
             // where this lane's eight results of a row go inside a row slot, and which of its two pixels are real / padding
             uint32_t soff[2][4]; bool live[2], zero[2];
-            const bool edge = 16 * pw + 15 >= npx - 1 || cfirst < 0;      // the strip holds the row's first or last pixel (may be padding)
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int q = 16 * pw + grp + rr * 8;      // padded column 2 x0 + q
@@ -315,7 +314,6 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
                 mbar_wait(&row_empty[slot], (uint32_t)(((rc / kFuseSlots) & 1) ^ 1));
                 if (has) {
                     const uint32_t slot_u32 = slots_u32 + (uint32_t)slot * kFuseSlotBytes;
-                    const bool plain = ic >= 0 && ic < p.H && !edge;     // warp-uniform: no padding pixel among this strip's results
                     const bool row_in = ic >= 0 && ic < p.H;
                     uint32_t afrag[2][4];
 #pragma unroll
@@ -336,7 +334,7 @@ stem_conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const T* __
                             float m0, m1;
                             mul2(m0, m1, acc[rr * 2 + 0], acc[rr * 2 + 1], 0.1f);        // LeakyReLU(0.1) = max(v, 0.1 v), as stem_strip_kernel
                             uint32_t val = pack_bf16x2(fmaxf(acc[rr * 2 + 0], m0), fmaxf(acc[rr * 2 + 1], m1));
-                            if (!plain && (!row_in || zero[rr])) val = 0u;
+                            if (!row_in || zero[rr]) val = 0u;
                             if (live[rr]) sts32(slot_u32 + soff[rr][j], (int)val);
                         }
                     }
