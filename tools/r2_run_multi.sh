@@ -8,10 +8,9 @@ for n in 2 4 8; do
   P=$((P+1)); timeout 900 $TR --nproc-per-node $n --master-port $P bench.py --gpus $n --config 608x320 --no-cpu-baseline > gpurun_out/r2m_608x320_${n}gpu.json 2> gpurun_out/r2m_608x320_${n}gpu.err
   cut -c1-200 gpurun_out/r2m_608x320_${n}gpu.json; echo
 done
-python bench.py --config 608x320 --no-cpu-baseline > gpurun_out/r2m_608x320_1gpu.json 2> gpurun_out/r2m_608x320_1gpu.err; cut -c1-200 gpurun_out/r2m_608x320_1gpu.json; echo
 P=$((P+1)); NCCL_DEBUG=INFO timeout 900 $TR --nproc-per-node 8 --master-port $P bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2m_headline_8gpu.json 2> gpurun_out/r2m_headline_8gpu.err
 cut -c1-200 gpurun_out/r2m_headline_8gpu.json; echo; grep -c "NCCL INFO" gpurun_out/r2m_headline_8gpu.err; grep -m3 "nranks\|NVLS" gpurun_out/r2m_headline_8gpu.err
-for v in "64:" "256:" "64:NCCL_ALGO=NVLS" "32:"; do
+for v in "64:" "256:"; do
   mb=${v%%:*}; envv=${v#*:}
   P=$((P+1)); env $envv timeout 900 $TR --nproc-per-node 8 --master-port $P bench.py --gpus 8 --config train --bucket-mb $mb > gpurun_out/r2m_train_8gpu_mb${mb}_${envv:-default}.json 2> gpurun_out/r2m_train_8gpu_mb${mb}_${envv:-default}.err
   python - <<PY
@@ -23,4 +22,3 @@ except Exception as e:
     print("train variant ${mb} ${envv} failed:", e)
 PY
 done
-python bench.py --config train > gpurun_out/r2m_train_1gpu.json 2> gpurun_out/r2m_train_1gpu.err; cut -c1-250 gpurun_out/r2m_train_1gpu.json
