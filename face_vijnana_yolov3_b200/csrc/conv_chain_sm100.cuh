@@ -31,6 +31,9 @@ struct alignas(128) ChainLayer {        // tensor maps read by TMA straight from
     const int* res_flags;      // completion counters of the layer that produced the residual rows (nullptr: before the chain)
     int res_expected, res_blocks;
     int rot;                   // rotation of the tile -> CTA-pair assignment
+    int chunks;                // 32-channel chunks of a tile that hold real output channels: 8, or Cout / 32 when Cout < 256 (a 128-wide
+                               // 1x1 layer rides the 256-wide pair tile: its upper weight rows are TMA zero fill, chunks 4..7 are not drained)
+    int bias_n;                // bias entries to stage (Cout padded to 32)
 };
 static_assert(sizeof(ChainLayer) % 128 == 0 && offsetof(ChainLayer, tmap_b) == 128, "tensor maps of a chain entry must stay aligned");
 
@@ -253,7 +256,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
         int buf = 0; uint32_t buf_ph = 0;
         int acc = 0; uint32_t acc_ph = 0;
         ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
-        int cur = -1, nnt = 1;
+        int cur = -1, nnt = 1, nchunks = kChunks;
         bool has_res = false, leaky = false;
         const ConvParams* pp = &chain[0].p;
         while (w.next()) {
@@ -261,9 +264,11 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
                 cur = w.li;
                 pp = &chain[cur].p;
                 nnt = pp->num_n_tiles; has_res = pp->res != nullptr; leaky = pp->leaky != 0;
+                nchunks = chain[cur].chunks;
+                const int bias_n = chain[cur].bias_n;
                 // this layer's bias: the group's own copy (its previous contents were last read in the group's previous tile)
                 named_bar_sync(bar_id, kEpiThreads);
-                for (int i = et; i < nnt * BN; i += kEpiThreads) sbias[i] = __ldg(pp->bias + i);
+                for (int i = et; i < bias_n; i += kEpiThreads) sbias[i] = __ldg(pp->bias + i);
                 named_bar_sync(bar_id, kEpiThreads);
             }
             const ConvParams& p = *pp;
@@ -286,7 +291,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-                for (int c = g; c < kChunks; c += 2) {
+                for (int c = g; c < nchunks; c += 2) {
                     const int c0 = c * 32;
                     const uint32_t sbuf = ring_u32 + (uint32_t)buf * kChunkBytes;
                     const uint32_t myslot = sbuf + (uint32_t)r * 64u;
@@ -381,7 +386,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
                     mbar_arrive(&ready[pbuf]);
                 }
                 if (++pbuf == nb) pbuf = 0;
-                if ((pchunk += 2) >= kChunks) {
+                if ((pchunk += 2) >= L.chunks) {
                     pchunk = g;
                     p_has = pw.next();
                 }
@@ -392,7 +397,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
             service_pending();
             int buf = 0, prev = -1; uint32_t sph = 0;
             ChainWalk w(chain, n_layers, n_pairs, pair, sched, sched_stride);
-            int cur = -1, nnt = 1, ch0 = 0, ch1 = 0;
+            int cur = -1, nnt = 1, ch0 = 0, ch1 = 0, nchunks = kChunks;
             bool o0 = false, o1 = false;
             int* sig = nullptr;
             const ChainLayer* L = chain;
@@ -404,13 +409,14 @@ conv_chain_kernel(const ChainLayer* __restrict__ chain, const int n_layers, cons
                     o0 = p.out[0].tma != 0; o1 = p.out[1].tma != 0;
                     ch0 = p.out[0].choff; ch1 = p.out[1].choff;
                     sig = p.sig_flags;
+                    nchunks = L->chunks;
                 }
                 {
                     const int tile = w.tile;
                     const int m0 = (tile / nnt) * kTileM + m_rank_off;
                     const int n0 = (tile % nnt) * BN;
 #pragma unroll 1
-                    for (int c = g; c < kChunks; c += 2) {
+                    for (int c = g; c < nchunks; c += 2) {
                         for (uint32_t spin = 0; !mbar_test(&staged[buf], sph); ++spin) {      // keep the owed buffers moving while waiting
                             if (pending > 0) service_pending(); else if (spin > 16) __nanosleep(64);
                             if (spin > (1u << 24)) { printf("fvy: chain store warp timed out (block %d)\n", blockIdx.x); __trap(); }

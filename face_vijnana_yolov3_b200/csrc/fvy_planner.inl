@@ -3,6 +3,7 @@
 namespace fvy {
 
 constexpr int kFuseStemDefault = 0;        // FVY_FUSE_STEM: conv_0 + conv_1 in one kernel
+constexpr int kChain128Default = 0;        // FVY_CHAIN_128: 128-wide 1x1 layers on the 256-wide pair tile (chain membership at 52^2)
 constexpr int kChainSchedDefault = 0;      // FVY_CHAIN_SCHED when neither the environment nor fvy_config.flags says otherwise
 
 template <int BN, int BK, bool CTA2>
@@ -156,6 +157,13 @@ static int build_plan(fvy_handle* h) {
         for (int bn : {256, 128, 64, 32})
             if (bn <= cap_n && L.cout_pad % bn == 0) { L.BN = bn; break; }
         L.num_n_tiles = L.cout_pad / L.BN;
+        // 128-wide 1x1 layers of the residual blocks at 52^2 (conv_13 ... conv_34, conv_101, conv_103): run them on the 256-wide CTA-pair
+        // tile (upper 128 weight rows = TMA zero fill, upper output chunks clipped by the TMA store) so that they are eligible for
+        // conv_chain_kernel together with the 3x3 layers around them - the kernel boundary costs these 9 us layers more than the
+        // doubled (still small) MMA work does.
+        const bool wide1x1 = env_int("FVY_CHAIN_128", kChain128Default) != 0 && !(c.flags & FVY_CFG_NO_CHAIN) && !stem && s.k == 1 && s.stride == 1 &&
+                             s.bn && s.cout == 128 && s.cin % 64 == 0 && s.src >= 0 && s.idx != 96 && bn_cap >= 256;
+        if (wide1x1) { L.BN = 256; L.num_n_tiles = 1; }
         const int gt = L.taps == 9 ? 3 : 1;                       // column taps per filter row
         // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of the B tile): every 256-wide layer, and the
         // 128-wide 3x3 layers whose whole weight tile then fits in shared memory (conv_5/7/10)
@@ -197,7 +205,7 @@ static int build_plan(fvy_handle* h) {
             fixed = 1024 + kSmemRing + (size_t)groups * nb * kChunkBytes;
             budget = 232448 - fixed;
         }
-        if (L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot <= budget) {
+        if (L.num_n_tiles == 1 && env_int("FVY_RESIDENT", 1) != 0 && b_total + 3 * a_slot <= budget && !wide1x1) {
             if (L.taps * k_chunks / b_cover > kMaxB && a_cover == gt) b_cover = gt;
             if (L.taps * k_chunks / b_cover <= kMaxB) {
                 b_res = 1;
@@ -231,7 +239,7 @@ static int build_plan(fvy_handle* h) {
         // operands
         const size_t kdim = (size_t)L.taps * L.cin_pad;
         if (int e = dev_alloc(h, (void**)&L.w, (size_t)L.cout_pad * kdim * 2, true)) return e;
-        if (int e = dev_alloc(h, (void**)&L.bias, (size_t)L.cout_pad * 4, true)) return e;
+        if (int e = dev_alloc(h, (void**)&L.bias, (size_t)std::max(L.cout_pad, L.num_n_tiles * L.BN) * 4, true)) return e;   // zero beyond Cout
         if (b_cover == 3) { if (int e = make_tmap_b3(&L.tmap_b, L.w, L.cin_pad, L.cout_pad, L.taps, L.BK, L.cta2 ? L.BN / 2 : L.BN, 3)) return e; }
         else if (int e = make_tmap_2d(&L.tmap_b, L.w, kdim, L.cout_pad, kdim, L.BK, L.cta2 ? L.BN / 2 : L.BN)) return e;
         ConvParams& p = L.p;
@@ -546,6 +554,8 @@ static int prepare_chains(fvy_handle* h, int batch) {
                     }
                 }
             c.rot = (k * 25) % pairs;
+            c.chunks = (L.num_n_tiles > 1 || L.cout_pad >= kChainBN) ? kChainBN / 32 : std::max(1, L.cout_pad / 32);
+            c.bias_n = L.num_n_tiles * kChainBN;          // the bias array is zero-padded to a whole tile
         }
         CUDA_TRY(cudaMemcpyAsync(ch.dev, ch.host.data(), sizeof(ChainLayer) * ch.count, cudaMemcpyHostToDevice, h->stream));
         if (h->chain_sched)

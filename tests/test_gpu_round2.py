@@ -406,3 +406,37 @@ def test_fused_stem_is_bit_identical_to_the_two_kernel_path(B, H, W):
     for k in (0, 3, 4):
         for a, b in zip(res["1"][k], res["0"][k]):
             assert np.array_equal(a, b)
+
+
+def test_wide_1x1_chain_membership_is_bit_identical():
+    """FVY_CHAIN_128=1: the 128-wide 1x1 layers at 52^2 run on the 256-wide CTA-pair tile (zero-filled upper weight rows, clipped
+    upper output chunks) and join conv_chain_kernel with the 3x3 layers around them.  A row's dot products do not change: the
+    head logits must equal those of the default plan bit for bit, at the full batch (where chains engage) and for one image."""
+    stream = synth.darknet_stream(arch.yolo3_table(1), 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(40, 416, 416, 11)
+    res = {}
+    old = os.environ.get("FVY_CHAIN_128")
+    try:
+        for mode in ("1", "0"):
+            os.environ["FVY_CHAIN_128"] = mode
+            eng = Engine(416, 416, head=L.HEAD_YOLO3, nb_class=1, max_batch=40)
+            eng.load_weights(stream)
+            full = eng.forward(x)
+            again = eng.forward(x)                  # graph replay
+            l0 = eng.launch_count
+            eng.forward(x)
+            n_launch = eng.launch_count - l0
+            one = eng.forward(x[7:8])
+            res[mode] = (full, again, one, n_launch)
+            eng.close()
+    finally:
+        if old is None:
+            os.environ.pop("FVY_CHAIN_128", None)
+        else:
+            os.environ["FVY_CHAIN_128"] = old
+    assert res["1"][3] < res["0"][3] - 20           # 28 more layers ride in chains
+    for k in (0, 1, 2):
+        for a, b in zip(res["1"][k], res["0"][k]):
+            assert np.array_equal(a, b)
+    for a, b in zip(res["1"][0], res["1"][2]):
+        assert np.array_equal(a[7], b[0])
