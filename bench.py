@@ -638,7 +638,7 @@ def main():
     ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-s", type=float, default=1.0, help="length of the additional sustained timed region (0 = skip)")
-    ap.add_argument("--bucket-mb", type=float, default=64.0)
+    ap.add_argument("--bucket-mb", type=float, default=256.0, help="gradient bucket size: one 162.6 MB bucket reaches 608 GB/s bus bandwidth at N = 8 (three 64 MB buckets: 394)")
     ap.add_argument("--tile-n", type=int, default=0)
     args = ap.parse_args()
     dflt_steps = {"headline": 20, "608x320": 5, "stress": 20, "train": 10}[args.config]

