@@ -3,13 +3,8 @@
 # copied to profiles/ by tools/evidence_r02_collect.sh here).  Every ncu pass runs only after its command has exited 0 without ncu.
 T=${1:-r2e}
 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err || tail -5 gpurun_out/${T}_bench.err
-python bench.py --config 608x320 --no-cpu-baseline > gpurun_out/${T}_bench_608x320.json 2>> gpurun_out/${T}_bench.err
-python bench.py --config stress > gpurun_out/${T}_bench_stress.json 2>> gpurun_out/${T}_bench.err
-python bench.py --config train > gpurun_out/${T}_bench_train.json 2>> gpurun_out/${T}_bench.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
-python tools/gpu_check.py --tile-n 256 > gpurun_out/${T}_check.log 2>&1
-# launch list of the headline command (cold-cache, serialised: shares, not absolutes)
+# launch list of the headline command (cold-cache, serialised: shares, not absolutes); the command runs plain first
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-s 0 > gpurun_out/${T}_plain1.json 2> gpurun_out/${T}_plain1.err || { echo "plain bench failed"; tail -3 gpurun_out/${T}_plain1.err; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-s 0 > gpurun_out/${T}_ncu1.log 2>&1
 cat > /tmp/fwd2.py <<'PY'
@@ -28,10 +23,26 @@ if len(sys.argv) > 1:
     eng.detect(xd, pp=post_params(0.5, 0.45), image_hw=hw, max_out=4225)
 PY
 # DRAM traffic of every conv launch of one forward -> profiles/conv_traffic.json (stamped with the build hash)
+FVY_GRAPH=0 python /tmp/fwd2.py detect || echo "plain forward failed"
 FVY_GRAPH=0 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -k regex:"conv_igemm|conv_chain|stem_" -c 200 --csv --log-file gpurun_out/${T}_traffic.csv python /tmp/fwd2.py > gpurun_out/${T}_ncu2.log 2>&1
 python tools/summarize_ncu.py traffic gpurun_out/${T}_traffic.csv gpurun_out/${T}_conv_traffic_per_launch.csv gpurun_out/${T}_conv_traffic.json
+cp gpurun_out/${T}_conv_traffic.json profiles/conv_traffic.json     # bench.py reads it: the traffic figure of THIS build
+python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err || tail -5 gpurun_out/${T}_bench.err
+python bench.py --config 608x320 --no-cpu-baseline > gpurun_out/${T}_bench_608x320.json 2>> gpurun_out/${T}_bench.err
+python bench.py --config stress > gpurun_out/${T}_bench_stress.json 2>> gpurun_out/${T}_bench.err
+python bench.py --config train > gpurun_out/${T}_bench_train.json 2>> gpurun_out/${T}_bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
+python tools/gpu_check.py --tile-n 256 > gpurun_out/${T}_check.log 2>&1
+# full capture of eight representative conv layers (two launches each) and of the three chain launches of one forward
+FVY_CHAIN=0 python tools/run_layer.py --layers 28,11,27,3,45,10,1,6 --iters 1 > gpurun_out/${T}_layers_plain.log 2>&1 || echo "plain run_layer failed"
+FVY_CHAIN=0 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 74 -c 16 -o gpurun_out/${T}_full -f \
+    python tools/run_layer.py --layers 28,11,27,3,45,10,1,6 --iters 1 > gpurun_out/${T}_ncu4.log 2>&1
+ncu -i gpurun_out/${T}_full.ncu-rep --page raw --csv > gpurun_out/${T}_full_raw.csv 2>/dev/null; rm -f gpurun_out/${T}_full.ncu-rep
+FVY_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:conv_chain -s 3 -c 3 -o gpurun_out/${T}_chain -f python /tmp/fwd2.py > gpurun_out/${T}_ncu5.log 2>&1
+ncu -i gpurun_out/${T}_chain.ncu-rep --page raw --csv > gpurun_out/${T}_chain_raw.csv 2>/dev/null; rm -f gpurun_out/${T}_chain.ncu-rep
 # full capture of the post-processing kernels of one detect call (the kernels changed this round)
+python -m pytest tests/test_gpu_round2.py -q -k wide_1x1 > gpurun_out/${T}_wide1x1.log 2>&1; tail -2 gpurun_out/${T}_wide1x1.log
 ncu --set full --clock-control none --import-source on -k regex:"decode_yolo|sort_scores|nms_mask|nms_sweep|assemble" -c 5 -o gpurun_out/${T}_post -f \
     python /tmp/fwd2.py detect > gpurun_out/${T}_ncu3.log 2>&1
 ncu -i gpurun_out/${T}_post.ncu-rep --page raw --csv > gpurun_out/${T}_post_raw.csv 2>/dev/null; rm -f gpurun_out/${T}_post.ncu-rep
