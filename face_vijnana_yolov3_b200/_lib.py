@@ -20,6 +20,7 @@ ARITH_F64, ARITH_F32 = 0, 1
 ANCHOR_MASK_REFERENCE = 0x0AA   # src/space/yolov3_detect.py:354-362
 ANCHOR_MASK_ALL = 0x1FF
 CFG_NO_GRAPH, CFG_NO_CHAIN, CFG_NO_TILE_FLAGS, CFG_CHAIN_SCHED, CFG_NO_CHAIN_SCHED, CFG_NO_OVERLAP_POST, CFG_NO_FUSED_STEM = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40   # fvy_config.flags
+CFG_NO_COMPACT = 0x80
 
 
 class FvyConfig(C.Structure):

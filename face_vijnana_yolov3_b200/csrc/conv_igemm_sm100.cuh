@@ -68,6 +68,7 @@ struct OutDesc {
     int choff;    // first destination channel
     int nmax;     // batch capacity of the buffer (phase stride)
     int c_real;   // valid channels (heads: 18 / 255 / 6); others: >= BLOCK_N * num_n_tiles
+    int dst_w, dst_plane;   // stored geometry of the destination level: row pitch (pixels) and rows per image (per phase plane)
     int tma;      // 1: stored with TMA (tmap_out[o]); rows of the compute domain coincide with rows of this buffer
                   // 2: OUT_PHASE stored with TMA through the 5-D phase view, one store per image row the tile touches
 };
@@ -913,12 +914,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const OutDesc& od = p.out[o];
                 int ridx = -1;
                 if (valid) {
-                    if (od.kind == OUT_PADDED) ridx = (img * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
+                    if (od.kind == OUT_PADDED) ridx = img * od.dst_plane + (h + 1) * od.dst_w + (w + 1);
                     else if (od.kind == OUT_PHASE) {
-                        const int hp = h + 1, wp = w + 1;
-                        const int pw = (p.W >> 1) + 2, plane = ((p.H >> 1) + 2) * pw;    // planes of the consumer's padded output geometry
-                        ridx = ((((hp & 1) << 1) | (wp & 1)) * od.nmax + img) * plane + (hp >> 1) * pw + (wp >> 1);
-                    } else ridx = (img * (2 * p.H + 2) + (2 * h + 1)) * (2 * p.W + 2) + (2 * w + 1);   // OUT_UP2_PADDED
+                        const int hp = h + 1, wp = w + 1;                                // planes of the consumer level's stored geometry
+                        ridx = ((((hp & 1) << 1) | (wp & 1)) * od.nmax + img) * od.dst_plane + (hp >> 1) * od.dst_w + (wp >> 1);
+                    } else ridx = img * od.dst_plane + (2 * h + 1) * od.dst_w + (2 * w + 1);   // OUT_UP2_PADDED
                 }
                 sts32(myrow + (uint32_t)(o * kBlockM + r) * 4u, ridx);
             }
@@ -1020,7 +1020,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         if (ridx < 0) continue;
                         const uint4 t = lds128(sbuf + (uint32_t)row * 64u + (uint32_t)(((et & 3) ^ ((row >> 1) & 3)) << 4));
                         if (od.kind == OUT_UP2_PADDED) {
-                            const int W2 = 2 * p.W + 2;
+                            const int W2 = od.dst_w;
                             *reinterpret_cast<uint4*>(base + (long long)ridx * od.pitch) = t;
                             *reinterpret_cast<uint4*>(base + (long long)(ridx + 1) * od.pitch) = t;
                             *reinterpret_cast<uint4*>(base + (long long)(ridx + W2) * od.pitch) = t;

@@ -132,7 +132,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
                 const int pgroups = p_chained ? 2 : ((P.p.epi_groups == 2 && P.BN >= 64 && P.p.epi_split != 0) ? 2 : 1);
                 L.p.wait_flags = P.flags;
                 L.p.wait_expected = P.num_n_tiles * pgroups;
-                L.p.wait_margin = L.s.k == 3 ? L.Win + 3 : 0;
+                L.p.wait_margin = L.s.k == 3 ? L.p.dom_w + 1 : 0;
                 L.p.wait_blocks = (batch * P.p.dom_plane + 127) / 128;      // row blocks the producer really writes in this call
             }
             if (L.p.sig_flags) L.p.split_from = L.cta2 ? ((L.p.num_m_tiles + 1) / 2) * L.p.num_n_tiles : L.p.num_m_tiles * L.p.num_n_tiles;

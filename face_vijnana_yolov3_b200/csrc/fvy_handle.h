@@ -103,10 +103,10 @@ static int make_tmap_b3(CUtensorMap* m, const void* base, uint64_t cin, uint64_t
 // ends at the tile's end (not the row's) has nothing to clip it, so the store warp covers such a run with two (overlapping)
 // boxes of the largest power of two that fits - hence one map per box size 1, 2, 4 ... 64 pairs, kept in global memory
 // (tools/phase_tma_test.cu pins these properties).  Replaces 128 threads writing 16-byte pieces (conv_igemm_kernel, tma == 2).
-static int make_tmap_phase(CUtensorMap* m, const void* base, int nmax, int H, int W, int pitch_elems, int box_pairs) {
+static int make_tmap_phase(CUtensorMap* m, const void* base, int nmax, int H, int W, int dst_w, int dst_plane, int pitch_elems, int box_pairs) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(FVY_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    const uint64_t pw = (uint64_t)(W / 2 + 2), plane = (uint64_t)(H / 2 + 2) * pw, eb = (uint64_t)pitch_elems * 2;
+    const uint64_t pw = (uint64_t)dst_w, plane = (uint64_t)dst_plane, eb = (uint64_t)pitch_elems * 2;   // the consumer level's stored geometry
     cuuint64_t dims[5] = {(cuuint64_t)pitch_elems, 2, (cuuint64_t)((W + 2) / 2), (cuuint64_t)((H + 2) / 2), (cuuint64_t)(3 * nmax)};
     cuuint64_t strides[4] = {(cuuint64_t)nmax * plane * eb, eb, pw * eb, plane * eb};
     cuuint32_t box[5] = {32, 2, (cuuint32_t)box_pairs, 1, 1};

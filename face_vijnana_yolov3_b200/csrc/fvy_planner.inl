@@ -3,6 +3,7 @@
 namespace fvy {
 
 constexpr int kFuseStemDefault = 0;        // FVY_FUSE_STEM: conv_0 + conv_1 in one kernel
+constexpr int kCompactDefault = 1;         // FVY_COMPACT: shared-halo geometry of the narrow deep levels (see build_plan)
 constexpr int kChain128Default = 0;        // FVY_CHAIN_128: 128-wide 1x1 layers on the 256-wide pair tile (chain membership at 52^2)
 constexpr int kChainSchedDefault = 0;      // FVY_CHAIN_SCHED when neither the environment nor fvy_config.flags says otherwise
 
@@ -88,14 +89,28 @@ static int build_plan(fvy_handle* h) {
     for (const ConvSpec& s : specs) by_idx[s.idx] = &s;
     std::map<int, TensorBufs> bufs;
     auto HW = [&](int level, int* H, int* W) { *H = c.net_h >> level; *W = c.net_w >> level; };
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    // Stored geometry of a level.  Legacy: every image carries its own one-pixel halo, (H+2) x (W+2).  Compact (the narrow deep levels,
+    // 26^2 and 13^2 at 416): neighbouring rows and neighbouring images SHARE their halo - row pitch W+1 (the zero pixel that ends row y
+    // is the one that starts row y+1), image pitch (H+1)(W+1) (the zero row on top of image n+1 closes image n; past the last image the
+    // tensor map's out-of-bounds zero fill does) - so every tap is still a constant row shift of the flattened buffer while the compute
+    // domain, which is this geometry, shrinks from 225 to 196 rows per image at 13^2 (-13 % MMA work) and from 784 to 729 at 26^2 (-7 %).
+    // Levels whose outputs leave through the 5-D phase view (rows of >= 32 pixels) need an even row pitch: they keep W+2 and only share
+    // the halo ROW between images (FVY_COMPACT=2; 52^2: 2916 -> 2862 rows per image).  Level 1 (written by the stem kernels) stays legacy.
+    const int phase_min_w = env_int("FVY_TMA_PHASE_MIN_W", 32);
+    const int compact_mode = (c.flags & FVY_CFG_NO_COMPACT) ? 0 : env_int("FVY_COMPACT", kCompactDefault);
+    auto is_compact = [&](int level) { return compact_mode >= 1 && level >= 2 && (c.net_w >> level) < phase_min_w; };   // shared columns too
+    auto share_rows = [&](int level) { return is_compact(level) || (compact_mode >= 2 && level >= 2); };
+    auto geom_w = [&](int level) { return (c.net_w >> level) + (is_compact(level) ? 1 : 2); };
+    auto geom_plane = [&](int level) { return (long long)((c.net_h >> level) + (share_rows(level) ? 1 : 2)) * geom_w(level); };
     // concat buffers (yolo3 only): A = [up(conv_84) 256 | skip_61 512] at level 4, B = [up(conv_96) 128 | skip_36 256] at level 3
     __nv_bfloat16 *catA = nullptr, *catB = nullptr;
     if (c.head == FVY_HEAD_YOLO3) {
         int H, W;
         HW(4, &H, &W);
-        if (int e = dev_alloc(h, (void**)&catA, (size_t)nmax * (H + 2) * (W + 2) * 768 * 2, true)) return e;
+        if (int e = dev_alloc(h, (void**)&catA, (size_t)nmax * geom_plane(4) * 768 * 2, true)) return e;
         HW(3, &H, &W);
-        if (int e = dev_alloc(h, (void**)&catB, (size_t)nmax * (H + 2) * (W + 2) * 384 * 2, true)) return e;
+        if (int e = dev_alloc(h, (void**)&catB, (size_t)nmax * geom_plane(3) * 384 * 2, true)) return e;
     }
     // stem: grid of stem_strip_kernel (two pieces per resident warp: 161 vs 166 us) and conv_0's weights in its K order
     {
@@ -110,9 +125,9 @@ static int build_plan(fvy_handle* h) {
         HW(s.level, &H, &W);
         TensorBufs tb;
         if (need_padded.count(s.idx))
-            if (int e = dev_alloc(h, (void**)&tb.padded, (size_t)nmax * (H + 2) * (W + 2) * s.cout * 2, true)) return e;
-        if (need_phase.count(s.idx))
-            if (int e = dev_alloc(h, (void**)&tb.phase, (size_t)4 * nmax * (H / 2 + 2) * (W / 2 + 2) * s.cout * 2, true)) return e;
+            if (int e = dev_alloc(h, (void**)&tb.padded, (size_t)nmax * geom_plane(s.level) * s.cout * 2, true)) return e;
+        if (need_phase.count(s.idx))      // four planes of the consumer's (next level's) geometry
+            if (int e = dev_alloc(h, (void**)&tb.phase, (size_t)4 * nmax * geom_plane(s.level + 1) * s.cout * 2, true)) return e;
         bufs[s.idx] = tb;
     }
     // heads
@@ -127,7 +142,6 @@ static int build_plan(fvy_handle* h) {
             if (int e = dev_alloc(h, (void**)&h->d_logits_alt[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
             ++nh;
         }
-    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     const int bn_cap = c.tile_n_max > 0 ? c.tile_n_max : env_int("FVY_BN", 256);
     const int bn_res_cap = std::min(bn_cap, env_int("FVY_BN_RES", 256));
     const int nb_res = env_int("FVY_NB_RES", 4), nb_plain = env_int("FVY_NB", 3);
@@ -260,29 +274,29 @@ static int build_plan(fvy_handle* h) {
             a_base = L.w; a_rows = (uint64_t)L.cout_pad; a_pitch = 32;   // placeholder map: conv_0 runs in stem_strip_kernel
             p.dom_plane = L.Hin * L.Win; p.dom_w = L.Win; p.dom_off = 0; p.tap_off[0] = 0;
         } else if (s.stride == 2) {
-            const int Ho = L.Hout, Wo = L.Wout;
-            // The compute domain is the padded geometry of the OUTPUT ((Ho+2) x (Wo+2), like a stride-1 layer), and the four
-            // phase planes of the input are stored with that same geometry: output pixel (h, w) = domain row m reads phase
-            // (r&1, s&1) at position (h + (r>>1), w + (s>>1)) = row m + ((r>>1) - 1) * (Wo+2) + ((s>>1) - 1) of that plane:
-            // every tap is a constant row shift AND the rows of the domain are the rows of the padded output (TMA stores).
-            const long long plane = (long long)(Ho + 2) * (Wo + 2);
+            // The compute domain is the stored geometry of the OUTPUT level (like a stride-1 layer), and the four phase planes of
+            // the input are stored with that same geometry: output pixel (h, w) = domain row m reads phase (r&1, s&1) at position
+            // (h + (r>>1), w + (s>>1)) = row m + ((r>>1) - 1) * pitch + ((s>>1) - 1) of that plane: every tap is a constant row
+            // shift AND the rows of the domain are the rows of the stored output (TMA stores).
+            const long long plane = geom_plane(s.level);
+            const int gw = geom_w(s.level);
             a_base = bufs[s.src].phase; a_rows = (uint64_t)(4 * nmax * plane); a_pitch = s.cin;
-            p.dom_plane = (int)plane; p.dom_w = Wo + 2; p.dom_off = 1;
+            p.dom_plane = (int)plane; p.dom_w = gw; p.dom_off = 1;
             for (int r = 0; r < 3; ++r)
                 for (int q = 0; q < 3; ++q)
                     p.tap_off[r * 3 + (L.tap_perm ? (q == 0 ? 0 : (q == 2 ? 1 : 2)) : q)] =
-                        (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + ((r >> 1) - 1) * (Wo + 2) + ((q >> 1) - 1));
+                        (int)((((r & 1) << 1) | (q & 1)) * nmax * plane + ((r >> 1) - 1) * gw + ((q >> 1) - 1));
         } else {
-            const int H = L.Hin, W = L.Win;
             if (s.src == -2) { a_base = catA; a_pitch = 768; }
             else if (s.src == -3) { a_base = catB; a_pitch = 384; }
             else { a_base = bufs[s.src].padded; a_pitch = s.cin; }
-            a_rows = (uint64_t)nmax * (H + 2) * (W + 2);
-            p.dom_plane = (H + 2) * (W + 2); p.dom_w = W + 2; p.dom_off = 1;
+            const int gw = geom_w(s.level);
+            a_rows = (uint64_t)nmax * geom_plane(s.level);
+            p.dom_plane = (int)geom_plane(s.level); p.dom_w = gw; p.dom_off = 1;
             if (s.k == 1) p.tap_off[0] = 0;
             else
                 for (int r = 0; r < 3; ++r)
-                    for (int q = 0; q < 3; ++q) p.tap_off[r * 3 + q] = (r - 1) * (W + 2) + (q - 1);
+                    for (int q = 0; q < 3; ++q) p.tap_off[r * 3 + q] = (r - 1) * gw + (q - 1);
         }
         if (a_base == nullptr) return fail(FVY_E_INVALID, "conv_%d: input buffer missing", s.idx);
         p.magic_plane = ~0ull / (unsigned long long)p.dom_plane + 1ull;
@@ -293,7 +307,7 @@ static int build_plan(fvy_handle* h) {
         // rows of the compute domain coincide with rows of the padded (H, W) output buffer (stride-1 convs on a padded input,
         // stride-2 convs on phase planes of the output's geometry)
         const bool coincident = !stem;
-        const uint64_t out_rows = (uint64_t)nmax * (L.Hout + 2) * (L.Wout + 2);
+        const uint64_t out_rows = (uint64_t)nmax * geom_plane(s.level);
         if (s.res >= 0) {
             p.res = bufs[s.res].padded; p.res_pitch = by_idx[s.res]->cout; p.res_choff = 0;
             if (!p.res) return fail(FVY_E_INVALID, "conv_%d: residual buffer missing", s.idx);
@@ -306,15 +320,17 @@ static int build_plan(fvy_handle* h) {
         const bool use_tma_store = env_int("FVY_TMA_STORE", 1) != 0;
         auto add_out = [&](void* ptr, int kind, int pitch, int choff, int c_real) {
             OutDesc od; od.ptr = ptr; od.aux = nullptr; od.kind = kind; od.pitch = pitch; od.choff = choff; od.nmax = nmax; od.c_real = c_real;
+            const int dst_level = kind == OUT_PHASE ? s.level + 1 : (kind == OUT_UP2_PADDED ? s.level - 1 : s.level);
+            od.dst_w = geom_w(dst_level); od.dst_plane = (int)geom_plane(dst_level);
             od.tma = (kind == OUT_PADDED && coincident && use_tma_store) ? 1 : 0;
             if (no < 2 && od.tma && make_tmap_2d(&L.tmap_out[no], ptr, (uint64_t)pitch, out_rows, (uint64_t)pitch, 32, kBlockM)) tmap_fail = true;
             // 4-phase form of a stride-1 layer's output: TMA stores through the 5-D phase view (needs an even padded width, which
             // every level with a stride-2 consumer has)
             if (no < 2 && kind == OUT_PHASE && coincident && use_tma_store && env_int("FVY_TMA_PHASE", 1) != 0 && s.stride == 1 && (L.Wout & 1) == 0 &&
-                (L.Hout & 1) == 0 && L.Wout >= env_int("FVY_TMA_PHASE_MIN_W", 32)) {   // narrower rows: too many stores per tile (conv_60 @26: 57 vs 56 us)
+                (L.Hout & 1) == 0 && L.Wout >= phase_min_w && !is_compact(s.level)) {   // narrower rows: too many stores per tile (conv_60 @26: 57 vs 56 us)
                 CUtensorMap maps[7];
                 bool ok = true;
-                for (int k = 0; k < 7 && ok; ++k) ok = make_tmap_phase(&maps[k], ptr, nmax, L.Hout, L.Wout, pitch, 1 << k) == FVY_OK;
+                for (int k = 0; k < 7 && ok; ++k) ok = make_tmap_phase(&maps[k], ptr, nmax, L.Hout, L.Wout, od.dst_w, od.dst_plane, pitch, 1 << k) == FVY_OK;
                 void* dmaps = nullptr;
                 if (!ok || dev_alloc(h, &dmaps, sizeof(maps), false) || cudaMemcpy(dmaps, maps, sizeof(maps), cudaMemcpyHostToDevice) != cudaSuccess) tmap_fail = true;
                 else { od.tma = 2; od.aux = dmaps; L.tmap_out[no] = maps[6]; }
@@ -542,7 +558,7 @@ static int prepare_chains(fvy_handle* h, int batch) {
                 const Layer& P = h->layers[L.wait_on];
                 c.p.wait_flags = P.flags;
                 c.p.wait_expected = P.num_n_tiles * 2;              // both epilogue groups store part of every tile
-                c.p.wait_margin = L.s.k == 3 ? L.Win + 3 : 0;
+                c.p.wait_margin = L.s.k == 3 ? L.p.dom_w + 1 : 0;
                 c.p.wait_blocks = (batch * P.p.dom_plane + 127) / 128;
             }
             c.res_flags = nullptr;

@@ -22,12 +22,11 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
             v = reinterpret_cast<const float*>(od.ptr)[((n * H + h) * W + w) * od.c_real + c];
         } else {
             long long row;
-            if (od.kind == OUT_PADDED) row = (n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+            if (od.kind == OUT_PADDED) row = n * od.dst_plane + (long long)(h + 1) * od.dst_w + (w + 1);
             else if (od.kind == OUT_PHASE) {
-                const int hp = h + 1, wp = w + 1, ph = ((hp & 1) << 1) | (wp & 1), pw = (W >> 1) + 2;
-                const long long plane = (long long)((H >> 1) + 2) * pw;
-                row = ((long long)ph * od.nmax + n) * plane + (long long)(hp >> 1) * pw + (wp >> 1);
-            } else row = (n * (2 * H + 2) + (2 * h + 1)) * (2 * W + 2) + (2 * w + 1);
+                const int hp = h + 1, wp = w + 1, ph = ((hp & 1) << 1) | (wp & 1);
+                row = ((long long)ph * od.nmax + n) * od.dst_plane + (long long)(hp >> 1) * od.dst_w + (wp >> 1);
+            } else row = n * od.dst_plane + (long long)(2 * h + 1) * od.dst_w + (2 * w + 1);
             v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(od.ptr)[row * od.pitch + od.choff + c]);
         }
         dst[i] = v;

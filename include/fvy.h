@@ -68,6 +68,7 @@ typedef struct {
 #define FVY_CFG_NO_CHAIN_SCHED 0x10u   /* static rotation inside the chains (FVY_CHAIN_SCHED=0) */
 #define FVY_CFG_NO_OVERLAP_POST 0x20u  /* asynchronous calls post-process on the main stream (FVY_OVERLAP_POST=0) */
 #define FVY_CFG_NO_FUSED_STEM 0x40u    /* conv_0 and conv_1 as two kernels with the 4-phase activation in HBM (FVY_FUSE_STEM=0) */
+#define FVY_CFG_NO_COMPACT 0x80u       /* every level stored with a private halo per image, (H+2) x (W+2) (FVY_COMPACT=0) */
 
 /* One detection, 32 bytes.  Mirrors the fields of the reference's BoundBox that survive the hot
  * path (src/space/yolov3_detect.py:126-145): xmin,ymin,xmax,ymax,objness, get_label(), get_score(). */

@@ -440,3 +440,35 @@ def test_wide_1x1_chain_membership_is_bit_identical():
             assert np.array_equal(a, b)
     for a, b in zip(res["1"][0], res["1"][2]):
         assert np.array_equal(a[7], b[0])
+
+
+@pytest.mark.parametrize("head,net_h,net_w,batch", [("yolo3", 416, 416, 40), ("yolo3", 320, 480, 3), ("yolo3", 608, 608, 2),
+                                                      ("yolo3", 64, 64, 5), ("fd6", 416, 416, 4)])
+def test_shared_halo_geometry_is_bit_identical_to_private_halos(head, net_h, net_w, batch):
+    """The narrow deep levels (26^2 and 13^2 at 416) are stored with halos shared between rows and between images (DESIGN 3.1);
+    FVY_CFG_NO_COMPACT keeps the (H+2) x (W+2) geometry everywhere.  The geometry only changes which zero pixel a border tap reads:
+    every stored activation (checked on the layers of the compact levels and their neighbours) and the head logits are equal bit
+    for bit, for the whole batch (chains + tile flags engaged) and for a batch smaller than the handle's capacity."""
+    yolo = head == "yolo3"
+    table = arch.yolo3_table(1) if yolo else arch.fd6_table(6)
+    stream = synth.darknet_stream(table, 0, synth.INIT_KERAS_DEFAULT)
+    x = synth.images(batch, net_h, net_w, 5)
+    res = {}
+    for name, flags in (("compact", 0), ("legacy", L.CFG_NO_COMPACT)):
+        eng = Engine(net_h, net_w, head=L.HEAD_YOLO3 if yolo else L.HEAD_FD6, nb_class=1, max_batch=batch, flags=flags)
+        eng.load_weights(stream)
+        full = eng.forward(x)
+        again = eng.forward(x)                              # graph replay
+        n_layers = len(eng.layer_infos())
+        acts = [eng.layer_output(li, batch) for li in range(max(0, n_layers - 50), n_layers, 3)]
+        part = eng.forward(x[: max(1, batch // 2)])          # stale rows of the images beyond the batch must not leak in
+        res[name] = (full, again, part, acts)
+        eng.close()
+    for k in (0, 1, 2):
+        for a, b in zip(res["compact"][k], res["legacy"][k]):
+            assert np.array_equal(a, b)
+    for a, b in zip(res["compact"][3], res["legacy"][3]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res["compact"][0], res["compact"][2]):
+        assert np.array_equal(a[: b.shape[0]], b)
+    assert np.abs(res["compact"][0][0]).max() > 0
