@@ -311,7 +311,7 @@ int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batc
         SortArgs s;
         s.ibox = nullptr; s.classes = h->d_cls; s.counts = h->d_counts; s.seg_stride = seg_stride; s.nb_class = nb_class; s.cls = c;
         s.capP = h->capP; s.descending = 1; s.order = h->d_order; s.sbox = nullptr; s.gkeys = h->d_gkeys;
-        s.smem_keys = h->smem_keys; s.np2max = h->np2max;
+        s.smem_keys = h->smem_keys; s.np2max = h->np2max; s.srow = nullptr; s.sflag = nullptr; s.rowflag = nullptr;
         sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->stream>>>(s);
         CUDA_TRY(cudaGetLastError());
         MaskFpArgs m;

@@ -206,6 +206,7 @@ struct fvy_handle {
     int* d_status = nullptr; size_t status_bytes = 16; int* d_image_hw = nullptr;
     int* d_order = nullptr; int4* d_sbox = nullptr; unsigned long long* d_mask = nullptr; unsigned long long* d_gkeys = nullptr;
     unsigned long long* d_rowflag = nullptr;
+    uint4* d_srow = nullptr; unsigned char* d_sflag = nullptr;   // half-precision records / per-32 flags of the sorted boxes (nms_mask_kernel)
     int* d_kept = nullptr; int* d_kept_counts = nullptr;
     FvyDet* d_dets = nullptr; int* d_det_counts = nullptr; int dets_cap = 0;
     float last_fwd_ms = 0.f, last_post_ms = 0.f;

@@ -3,7 +3,7 @@
 namespace fvy {
 
 constexpr int kFuseStemDefault = 0;        // FVY_FUSE_STEM: conv_0 + conv_1 in one kernel
-constexpr int kCompactDefault = 1;         // FVY_COMPACT: shared-halo geometry of the narrow deep levels (see build_plan)
+constexpr int kCompactDefault = 2;         // FVY_COMPACT: shared-halo geometry of the narrow deep levels (see build_plan)
 constexpr int kChain128Default = 0;        // FVY_CHAIN_128: 128-wide 1x1 layers on the 256-wide pair tile (chain membership at 52^2)
 constexpr int kChainSchedDefault = 0;      // FVY_CHAIN_SCHED when neither the environment nor fvy_config.flags says otherwise
 

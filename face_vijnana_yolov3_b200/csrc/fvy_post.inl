@@ -42,6 +42,8 @@ static int build_post(fvy_handle* h) {
     if (int e = dev_alloc(h, (void**)&h->d_image_hw, (size_t)B * 8, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_order, (size_t)B * h->capP * 4, true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_sbox, (size_t)B * h->capP * 16, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_srow, (size_t)B * h->capP * 16, true)) return e;
+    if (int e = dev_alloc(h, (void**)&h->d_sflag, (size_t)B * (h->capP / 32), true)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_mask, (size_t)B * h->capP * h->words * 8, false)) return e;
     if (int e = dev_alloc(h, (void**)&h->d_rowflag, (size_t)B * h->words * 8, true)) return e;
     if (h->np2max > h->smem_keys)
@@ -136,12 +138,12 @@ static int nms_enqueue(fvy_handle* h, const int* d_ibox, float* d_cls, const int
         s.ibox = d_ibox; s.classes = d_cls; s.counts = d_counts; s.seg_stride = seg_stride; s.nb_class = nb_class; s.cls = c;
         s.capP = h->capP; s.descending = 1; s.order = h->d_order; s.sbox = h->d_sbox; s.gkeys = h->d_gkeys;
         s.smem_keys = h->smem_keys; s.np2max = h->np2max;
+        s.srow = h->d_srow; s.sflag = h->d_sflag; s.rowflag = h->d_rowflag;      // the sort kernel also zeroes the row flags
         sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->ps>>>(s);
         CUDA_TRY(cudaGetLastError());
         MaskArgs m;
         m.sbox = h->d_sbox; m.counts = d_counts; m.seg_stride = seg_stride; m.batch = batch; m.capP = h->capP; m.words = h->words;
-        m.th = th; m.mask = h->d_mask; m.rowflag = h->d_rowflag;
-        CUDA_TRY(cudaMemsetAsync(h->d_rowflag, 0, (size_t)batch * h->words * 8, h->ps));
+        m.th = th; m.mask = h->d_mask; m.rowflag = h->d_rowflag; m.srow = h->d_srow; m.sflag = h->d_sflag;
         nms_mask_kernel<<<h->num_sms * 16, 64, 0, h->ps>>>(m);
         CUDA_TRY(cudaGetLastError());
         SweepArgs w;
@@ -173,7 +175,7 @@ static int post_enqueue(fvy_handle* h, const float* dev[3], int batch, const fvy
         SortArgs s;
         s.ibox = h->d_ibox; s.classes = h->d_cls; s.counts = h->d_counts; s.seg_stride = h->cap; s.nb_class = 1; s.cls = 0;
         s.capP = h->capP; s.descending = 0; s.order = h->d_order; s.sbox = nullptr; s.gkeys = h->d_gkeys;
-        s.smem_keys = h->smem_keys; s.np2max = h->np2max;
+        s.smem_keys = h->smem_keys; s.np2max = h->np2max; s.srow = nullptr; s.sflag = nullptr; s.rowflag = nullptr;
         sort_scores_kernel<<<batch, 1024, (size_t)h->smem_keys * 8, h->ps>>>(s);
         CUDA_TRY(cudaGetLastError());
         assemble_fd6_kernel<<<batch, 512, 0, h->ps>>>(a, h->d_order, h->capP);

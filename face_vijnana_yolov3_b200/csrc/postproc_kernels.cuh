@@ -15,6 +15,7 @@
 #pragma once
 #include <climits>
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -504,16 +505,24 @@ struct SortArgs {
     int descending;         // 1: score desc (do_nms), 0: score asc (detect's final argsort)
     int* order;             // [B][capP] sorted candidate indices
     int4* sbox;             // [B][capP] boxes in sorted order (may be nullptr)
+    uint4* srow;            // [B][capP] half-precision record of each sorted box for nms_mask_kernel's pre-filter (with sbox; may be nullptr)
+    unsigned char* sflag;   // [B][capP/32] per 32 sorted boxes: bit 0 = all well-formed, bit 1 = all have a half record
+    unsigned long long* rowflag;   // [B][capP/64] zeroed here for the mask kernel (may be nullptr)
     unsigned long long* gkeys;   // [B][np2max] global scratch when the keys do not fit in shared memory
     int smem_keys;          // number of keys that fit in dynamic shared memory
     int np2max;
 };
+
+constexpr int kHalfCoord = 60000;            // |coordinate| bound for a half-precision record (finite after directed rounding)
+constexpr long long kHalfArea = 16000000;    // area bound: area / 256 stays below the largest half
 
 // One block per image: order = argsort(-score) with ties by index ascending (yolov3_detect.py:433, 447).
 __global__ void __launch_bounds__(1024) sort_scores_kernel(const SortArgs a) {
     extern __shared__ unsigned long long skeys[];
     const int img = blockIdx.x;
     const int n = min(a.counts[img], a.seg_stride);
+    if (a.rowflag)      // consumed by the kernels behind this one
+        for (int i = threadIdx.x; i < (a.capP >> 6); i += blockDim.x) a.rowflag[(size_t)img * (a.capP >> 6) + i] = 0ull;
     if (n <= 0) return;
     int np2 = 64;
     while (np2 < n) np2 <<= 1;
@@ -530,145 +539,186 @@ __global__ void __launch_bounds__(1024) sort_scores_kernel(const SortArgs a) {
     }
     __syncthreads();
     bitonic_sort_u64(keys, np2);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int idx = (int)(keys[i] & 0xffffffffu);
-        a.order[(size_t)img * a.capP + i] = idx;
-        if (a.sbox) a.sbox[(size_t)img * a.capP + i] = reinterpret_cast<const int4*>(a.ibox)[seg + idx];
+    const bool recs = a.sbox != nullptr && a.srow != nullptr;
+    const int n64 = (n + 63) & ~63;            // whole 64-blocks: both flag bytes of the last block are written
+    for (int i = threadIdx.x; i < n64; i += blockDim.x) {
+        bool wf = true, hk = true;
+        if (i < n) {
+            const int idx = (int)(keys[i] & 0xffffffffu);
+            a.order[(size_t)img * a.capP + i] = idx;
+            if (a.sbox) {
+                const int4 b = reinterpret_cast<const int4*>(a.ibox)[seg + idx];
+                a.sbox[(size_t)img * a.capP + i] = b;
+                if (recs) {
+                    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+                    wf = b.z >= b.x && b.w >= b.y;
+                    const long long area = ((long long)b.z - b.x) * ((long long)b.w - b.y);
+                    hk = (unsigned)(b.x + kHalfCoord) <= 2u * kHalfCoord && (unsigned)(b.y + kHalfCoord) <= 2u * kHalfCoord &&
+                         (unsigned)(b.z + kHalfCoord) <= 2u * kHalfCoord && (unsigned)(b.w + kHalfCoord) <= 2u * kHalfCoord &&
+                         area >= 0 && area < kHalfArea;
+                    if (hk) {
+                        // the box grown to half precision (minima rounded down, maxima up: an overlap of the exact boxes is an
+                        // overlap of these) and its area / 256 rounded to nearest (relative error 2^-11, see nms_mask_kernel)
+                        const unsigned x = __half_as_ushort(__float2half_rd((float)b.x)), y = __half_as_ushort(__float2half_rd((float)b.y));
+                        const unsigned z = __half_as_ushort(__float2half_ru((float)b.z)), w = __half_as_ushort(__float2half_ru((float)b.w));
+                        const unsigned ar = __half_as_ushort(__float2half_rn((float)area * (1.0f / 256.0f)));
+                        rec = make_uint4(x | (y << 16), z | (w << 16), ar, __float_as_uint((float)area));    // .w: the float area of phase 2
+                    }
+                    a.srow[(size_t)img * a.capP + i] = rec;
+                }
+            }
+        }
+        if (recs) {     // i < n64 is warp-uniform (n64 is a multiple of 64)
+            const unsigned bw = __ballot_sync(0xffffffffu, wf), bk = __ballot_sync(0xffffffffu, hk);
+            if ((threadIdx.x & 31) == 0) a.sflag[(size_t)img * (a.capP >> 5) + (i >> 5)] = (unsigned char)((bw == 0xffffffffu ? 1 : 0) | (bk == 0xffffffffu ? 2 : 0));
+        }
     }
 }
 
 // ---------------------------------------------------------------- bitmask IoU
+__device__ __forceinline__ __half2 u32_as_half2(unsigned v) { return *reinterpret_cast<const __half2*>(&v); }
 struct MaskArgs {
     const int4* sbox;       // [B][capP]
     const int* counts;      // [B]
     int seg_stride;
     int batch, capP, words; // words = capP / 64
     double th;
+    const uint4* srow;      // [B][capP] half records of the sorted boxes (sort_scores_kernel)
+    const unsigned char* sflag;   // [B][capP/32]
     unsigned long long* mask;   // [B][capP][words]; only words >= row/64 are written
     unsigned long long* rowflag; // [B][words], zeroed by the caller; see SweepArgs
 };
 
 // Persistent blocks of 64 threads; one 64x64 tile per iteration: thread t owns sorted row r*64+t and
 // produces the 64-bit word of column block c (bit j set <=> IoU(row, c*64+j) >= th and c*64+j > row).  Work items are the
-// upper-triangle tiles only, dealt round-robin: every block gets the same number of real tiles (dealing all nb^2 tile slots and
-// skipping the lower triangle left some blocks with twice the mean).
-__global__ void __launch_bounds__(64) nms_mask_kernel(const MaskArgs a) {
-    __shared__ int4 cbox[64];
-    __shared__ float4 cboxf[64];
-    __shared__ long long carea[64];
-    __shared__ float careaf[64];
-    __shared__ int tile_prefix[1025];   // batch <= 1024
-    __shared__ int all_wellformed, all_small;
+// upper-triangle tiles only, dealt round-robin: every block gets the same number of real tiles.
+//
+// Fast path (every box of the row block and of the column block well-formed and with a half record - sort_scores_kernel's flags -
+// and th > 0), two phases:
+//  1. a packed-half pre-filter over all 64 columns, two columns per instruction (HSET2 masks): a bit survives when the boxes,
+//     grown to half precision, overlap AND the areas are close enough for the IoU to reach the threshold at all
+//     (IoU <= min / max of the areas; boxes of different anchors - areas 480 .. 30 888 px^2 - cannot however much they overlap).
+//     It is a SUPERSET of the pairs with IoU >= th: growing a box keeps every strict overlap, and with a = rn(A / 256), b likewise
+//     (relative error e = 2^-11 each) and t = half(0.99 th), A >= th B implies a >= A (1 - e) / 256 >= th B (1 - e) / 256 >=
+//     0.99 th B (1 + e)^3 / 256 >= rn(t b): the 1 % of slack dwarfs the three roundings.  12 instructions per two columns.
+//     The staged columns are ordered so that shifting the running word left once per step leaves bit j = column j.
+//  2. the surviving bits (a few per cent at the usual candidate densities) take the float pre-filter (iou_prefilter_f) on float
+//     copies of the column boxes staged in shared memory, and the 1 % band around the threshold the exact int64 / fp64 test on the
+//     integer boxes: the decisions of the reference's bbox_iou, bit for bit.
+// Every other tile (malformed boxes, coordinates beyond +-60 000, th <= 0) takes the plain per-pair loops.
+__global__ void __launch_bounds__(64, 16) nms_mask_kernel(const MaskArgs a) {
+    __shared__ uint4 s_cols[64];          // per step: {x2, y2, z2, w2} and {b2, t*b2, -, -}: two columns per half2
+    __shared__ float4 s_cf[64];           // float copies of the column boxes and of their areas for phase 2
+    __shared__ float s_caf[64];
+    __shared__ int tile_prefix[1025];     // batch <= 1024
     for (int b = threadIdx.x; b < a.batch; b += blockDim.x) {
         const int n = min(a.counts[b], a.seg_stride);
         const int nb = (n + 63) >> 6;
         tile_prefix[b + 1] = nb * (nb + 1) / 2;          // upper-triangle tiles only (c >= r): every work item is a real tile
     }
-    if (threadIdx.x == 0) { tile_prefix[0] = 0; all_wellformed = 1; }
+    if (threadIdx.x == 0) tile_prefix[0] = 0;
     __syncthreads();
     if (threadIdx.x == 0)
         for (int b = 0; b < a.batch; ++b) tile_prefix[b + 1] += tile_prefix[b];
     __syncthreads();
     const int total = tile_prefix[a.batch];
     const bool zero_ge = 0.0 >= a.th;
+    const float th_lo = (float)(a.th * 0.99), th_hi = (float)(a.th * 1.01);     // 1 % either side of the threshold
+    const __half2 th2 = __float2half2_rn(th_lo);
     int img = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
         while (tile_prefix[img + 1] <= t) ++img;          // t is increasing
         const int n = min(a.counts[img], a.seg_stride);
         const int nb = (n + 63) >> 6;
-        int lt = t - tile_prefix[img];
-        int r = 0;
-        while (lt >= nb - r) { lt -= nb - r; ++r; }        // row r holds the nb - r tiles c = r .. nb - 1 (block-uniform scalar loop)
-        const int c = r + lt;
+        const int lt = t - tile_prefix[img];
+        // row r holds the nb - r tiles c = r .. nb - 1; rows 0 .. r-1 hold S(r) = r nb - r (r - 1) / 2 tiles: largest r with S(r) <= lt
+        const float d = (float)(2 * nb + 1);
+        int r = (int)((d - sqrtf(fmaxf(d * d - 8.0f * (float)lt, 0.f))) * 0.5f);
+        r = max(0, min(r, nb - 1));
+        while (r + 1 < nb && (r + 1) * nb - ((r + 1) * r >> 1) <= lt) ++r;
+        while (r > 0 && r * nb - (r * (r - 1) >> 1) > lt) --r;
+        const int c = r + lt - (r * nb - (r * (r - 1) >> 1));
         const int4* sb = a.sbox + (size_t)img * a.capP;
+        const uint4* sr = a.srow + (size_t)img * a.capP;
+        const unsigned char* fl = a.sflag + (size_t)img * (a.capP >> 5);
+        const unsigned flags = (unsigned)fl[2 * r] & fl[2 * r + 1] & fl[2 * c] & fl[2 * c + 1];
+        const bool wellformed = (flags & 1u) != 0;
+        const bool fast = flags == 3u && !zero_ge;
         const int col = c * 64 + threadIdx.x;
         const int row = r * 64 + threadIdx.x;
-        __syncthreads();
-        const int4 cb = col < n ? sb[col] : make_int4(0, 0, 0, 0);
-        const int4 me = row < n ? sb[row] : make_int4(0, 0, 0, 0);
-        cbox[threadIdx.x] = cb;
-        carea[threadIdx.x] = ((long long)cb.z - cb.x) * ((long long)cb.w - cb.y);
-        careaf[threadIdx.x] = (float)carea[threadIdx.x];
-        cboxf[threadIdx.x] = make_float4((float)cb.x, (float)cb.y, (float)cb.z, (float)cb.w);
-        all_wellformed = 1; all_small = 1;
-        __syncthreads();
-        if (cb.z < cb.x || cb.w < cb.y || me.z < me.x || me.w < me.y) all_wellformed = 0;
-        {
-            constexpr int kLim = 1 << 23;       // float copies and their differences stay exact
-            const int m = max(max(max(abs(cb.x), abs(cb.y)), max(abs(cb.z), abs(cb.w))), max(max(abs(me.x), abs(me.y)), max(abs(me.z), abs(me.w))));
-            if (m >= kLim || cb.x == INT_MIN || cb.y == INT_MIN || cb.z == INT_MIN || cb.w == INT_MIN || me.x == INT_MIN || me.y == INT_MIN ||
-                me.z == INT_MIN || me.w == INT_MIN)
-                all_small = 0;
+        __syncthreads();                                   // the previous tile's readers are done with s_cols
+        if (fast) {
+            const uint4 rec = col < n ? sr[col] : make_uint4(0u, 0u, 0u, 0u);
+            const int4 cb = col < n ? sb[col] : make_int4(0, 0, 0, 0);
+            s_cf[threadIdx.x] = make_float4((float)cb.x, (float)cb.y, (float)cb.z, (float)cb.w);
+            s_caf[threadIdx.x] = __uint_as_float(rec.w);
+            // step `it` of word w handles columns 32 w + 15 - it (low halves) and 32 w + 31 - it (high halves)
+            const int j = threadIdx.x;
+            unsigned short* e = reinterpret_cast<unsigned short*>(s_cols) + (size_t)((j >> 5) * 16 + 15 - (j & 15)) * 16 + ((j >> 4) & 1);
+            const __half bh = __ushort_as_half((unsigned short)(rec.z & 0xffffu));
+            e[0] = (unsigned short)(rec.x & 0xffffu); e[2] = (unsigned short)(rec.x >> 16);
+            e[4] = (unsigned short)(rec.y & 0xffffu); e[6] = (unsigned short)(rec.y >> 16);
+            e[8] = (unsigned short)(rec.z & 0xffffu); e[10] = __half_as_ushort(__hmul(__low2half(th2), bh));
         }
         __syncthreads();
         if (row < n) {
             unsigned long long word = 0;
             const int jmax = min(64, n - c * 64);
             const int j0 = (c == r ? threadIdx.x + 1 : 0);
-            if (all_wellformed && !zero_ge) {
-                const long long my_area = ((long long)me.z - me.x) * ((long long)me.w - me.y);
-                const float my_area_f = (float)my_area;
-                // thresholds of the float pre-filter: 1 % either side (th in (0, 1]: the margin dwarfs the float rounding)
-                const float th_lo = (float)(a.th * 0.99), th_hi = (float)(a.th * 1.01);
-                if (all_small) {
-                    // Two phases over the 64 columns.  Phase 1, branch-free: one bit per column whose box can overlap this row's at all
-                    // (four compares on float copies - a superset of "intersection > 0") AND whose area is close enough to this row's
-                    // for the IoU to reach the threshold (IoU <= min / max of the areas; th_lo leaves 1 % of slack over the float
-                    // rounding): at the usual candidate densities a few per cent of the pairs.  Phase 2 runs the float pre-filter (same decisions as iou_prefilter_f) on those bits only;
-                    // when a warp's rows overlap many columns (crowd scenes) it takes the branch-free form over all 64 instead, as
-                    // a loop over set bits would diverge.  Bits inside the 1 % band then take the exact int64 / fp64 test one by one.
+            if (fast) {
+                const uint4 rec = sr[row];
+                const __half2 mex = u32_as_half2(__byte_perm(rec.x, 0u, 0x1010)), mey = u32_as_half2(__byte_perm(rec.x, 0u, 0x3232));
+                const __half2 mez = u32_as_half2(__byte_perm(rec.y, 0u, 0x1010)), mew = u32_as_half2(__byte_perm(rec.y, 0u, 0x3232));
+                const __half2 mya = u32_as_half2(__byte_perm(rec.z, 0u, 0x1010));
+                const __half2 myta = __hmul2(th2, mya);
+                unsigned acc[2];
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    unsigned v = 0;
+#pragma unroll
+                    for (int it = 0; it < 16; ++it) {
+                        const uint4 q = s_cols[(w * 16 + it) * 2];
+                        const uint2 ar = *reinterpret_cast<const uint2*>(&s_cols[(w * 16 + it) * 2 + 1]);
+                        const unsigned m1 = __hgt2_mask(mez, u32_as_half2(q.x)), m2 = __hgt2_mask(u32_as_half2(q.z), mex);
+                        const unsigned m3 = __hgt2_mask(mew, u32_as_half2(q.y)), m4 = __hgt2_mask(u32_as_half2(q.w), mey);
+                        const unsigned m5 = __hge2_mask(mya, u32_as_half2(ar.y)), m6 = __hge2_mask(u32_as_half2(ar.x), myta);
+                        v = (v << 1) + ((m1 & m2 & m3) & (m4 & m5 & m6) & 0x00010001u);
+                    }
+                    acc[w] = v;
+                }
+                const unsigned long long upto = jmax >= 64 ? ~0ull : ((1ull << jmax) - 1ull);
+                const unsigned long long from = j0 >= 64 ? 0ull : ~((1ull << j0) - 1ull);
+                const unsigned long long ov = (((unsigned long long)acc[1] << 32) | acc[0]) & upto & from;
+                if (ov) {
+                    const int4 me = sb[row];
+                    const long long my_area = ((long long)me.z - me.x) * ((long long)me.w - me.y);
+                    const float my_area_f = (float)my_area;
                     const float4 mef = make_float4((float)me.x, (float)me.y, (float)me.z, (float)me.w);
-                    const bool my_ok = my_area_f < 1e30f;
-                    const unsigned long long upto = jmax >= 64 ? ~0ull : ((1ull << jmax) - 1ull);
-                    const unsigned long long from = j0 >= 64 ? 0ull : ~((1ull << j0) - 1ull);
-                    const unsigned long long valid = upto & from;
-                    unsigned long long ov = 0;
-#pragma unroll 16
-                    for (int j = 0; j < 64; ++j) {
-                        const float4 b = cboxf[j];
-                        const float ab = careaf[j];
-                        // IoU <= min(area) / max(area): boxes of different anchors (areas 480 .. 30 888 px^2) cannot reach the threshold
-                        // however much they overlap - by far the most frequent overlap at the reference's anchor mask
-                        const bool ratio = fminf(my_area_f, ab) >= th_lo * fmaxf(my_area_f, ab);
-                        ov |= (unsigned long long)(ratio && mef.z > b.x && b.z > mef.x && mef.w > b.y && b.w > mef.y) << j;
-                    }
-                    ov &= valid;
-                    unsigned long long yes = 0, band = 0;
-                    if (__any_sync(__activemask(), __popcll(ov) > 16)) {
-#pragma unroll 16
-                        for (int j = 0; j < 64; ++j) {
-                            const float4 b = cboxf[j];
-                            const float ab = careaf[j];
-                            const float iw = fminf(mef.z, b.z) - fmaxf(mef.x, b.x);
-                            const float ih = fminf(mef.w, b.w) - fmaxf(mef.y, b.y);
-                            const float xf = iw * ih;
-                            const float uf = my_area_f + ab - xf;
-                            const bool pos = iw > 0.f && ih > 0.f;
-                            const bool ok = uf > 0.f && my_ok && ab < 1e30f;
-                            const bool above = xf > th_hi * uf, below = xf < th_lo * uf;
-                            yes |= (unsigned long long)(pos && ok && above && !below) << j;
-                            band |= (unsigned long long)(pos && !(ok && (above || below))) << j;
-                        }
-                        yes &= valid; band &= valid;
-                    } else {
-                        for (unsigned long long todo = ov; todo; todo &= todo - 1) {
-                            const int j = __ffsll((long long)todo) - 1;
-                            const int d = iou_prefilter_f(mef, my_area_f, cboxf[j], careaf[j], th_lo, th_hi);
-                            yes |= (unsigned long long)(d == 1) << j;
-                            band |= (unsigned long long)(d == 2) << j;
-                        }
-                    }
-                    word = yes;
-                    for (unsigned long long todo = band; todo; todo &= todo - 1) {
+                    for (unsigned long long todo = ov; todo; todo &= todo - 1) {
                         const int j = __ffsll((long long)todo) - 1;
-                        if (iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi)) word |= 1ull << j;
+                        const float area_b_f = s_caf[j];
+                        const int dcs = iou_prefilter_f(mef, my_area_f, s_cf[j], area_b_f, th_lo, th_hi);
+                        if (dcs == 1) word |= 1ull << j;
+                        else if (dcs == 2) {          // inside the 1 % band: the exact test on the integer boxes
+                            const int4 b = sb[c * 64 + j];
+                            if (iou_ge_fast(me, my_area, my_area_f, b, ((long long)b.z - b.x) * ((long long)b.w - b.y), area_b_f, a.th, th_lo, th_hi)) word |= 1ull << j;
+                        }
                     }
-                } else
-                for (int j = j0; j < jmax; ++j)
-                    if (iou_ge_fast(me, my_area, my_area_f, cbox[j], carea[j], careaf[j], a.th, th_lo, th_hi)) word |= 1ull << j;
+                }
             } else {
-                for (int j = j0; j < jmax; ++j)
-                    if (iou_ge(me, cbox[j], a.th, zero_ge)) word |= 1ull << j;
+                const int4 me = sb[row];
+                if (wellformed && !zero_ge) {
+                    const long long my_area = ((long long)me.z - me.x) * ((long long)me.w - me.y);
+                    const float my_area_f = (float)my_area;
+                    for (int j = j0; j < jmax; ++j) {
+                        const int4 b = sb[c * 64 + j];
+                        const long long area_b = ((long long)b.z - b.x) * ((long long)b.w - b.y);
+                        if (iou_ge_fast(me, my_area, my_area_f, b, area_b, (float)area_b, a.th, th_lo, th_hi)) word |= 1ull << j;
+                    }
+                } else {
+                    for (int j = j0; j < jmax; ++j)
+                        if (iou_ge(me, sb[c * 64 + j], a.th, zero_ge)) word |= 1ull << j;
+                }
             }
             a.mask[((size_t)img * a.capP + row) * a.words + c] = word;
             if (c > r && word) atomicOr(&a.rowflag[(size_t)img * a.words + r], 1ull << threadIdx.x);

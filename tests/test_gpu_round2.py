@@ -472,3 +472,41 @@ def test_shared_halo_geometry_is_bit_identical_to_private_halos(head, net_h, net
     for a, b in zip(res["compact"][0], res["compact"][2]):
         assert np.array_equal(a[: b.shape[0]], b)
     assert np.abs(res["compact"][0][0]).max() > 0
+
+
+@pytest.mark.parametrize("th", [0.45, 0.999, 1e-4, 1.0, 1.5])
+def test_nms_mask_paths_large_coordinates_and_thresholds(th):
+    """nms_mask_kernel's packed-half pre-filter must stay a superset of the suppressing pairs: boxes of a 4K image (coordinates above
+    2 048 are not exact in half precision - the directed rounding is what keeps overlaps), near-duplicates one pixel apart (IoU a hair
+    either side of the threshold), areas up to the half record's bound; tiles that leave the fast path: coordinates beyond +-60 000,
+    areas beyond 16 M, malformed boxes (xmax < xmin), all mixed into one segment so that fast and plain tiles meet.  Bit-exact against
+    the C oracle's do_nms for thresholds from 1e-4 to beyond 1."""
+    rng = np.random.default_rng(12)
+    n = 900
+    xy = rng.integers(0, 3600, (n, 2)); wh = rng.integers(4, 900, (n, 2))
+    ibx = np.concatenate([xy, xy + wh], 1).astype(np.int64)
+    # near-duplicates: shifted / resized by one or two pixels
+    src = rng.integers(0, 300, 200)
+    ibx[300:500] = ibx[src] + rng.integers(-2, 3, (200, 4))
+    # a run of boxes beyond the half record's range, a run of huge areas, a run of malformed boxes
+    ibx[500:540] = ibx[500:540] + 70000
+    ibx[540:560, 2:] = ibx[540:560, :2] + rng.integers(4200, 5000, (20, 2))
+    ibx[560:580, [0, 2]] = ibx[560:580, [2, 0]]
+    ibx[580:590] = ibx[0:10]                       # exact duplicates
+    ibx = ibx.astype(np.int32)
+    cls = rng.random((n, 1)).astype(np.float32)
+    cls[::17] = 0.0                                # boxes whose score is already 0 never suppress
+    eng = Engine(416, 416, head=L.HEAD_NONE, nb_class=1, max_batch=2)
+    S = eng.cap
+    ib = np.zeros((2, S, 4), np.int32); cl = np.zeros((2, S, 1), np.float32)
+    ib[0, :n] = ibx; cl[0, :n] = cls
+    perm = rng.permutation(n)
+    ib[1, :n] = ibx[perm]; cl[1, :n] = cls[perm]
+    out, kept, kc = eng.nms(ib, cl, np.array([n, n], np.int32), th)
+    ref0 = P.do_nms(ibx, cls, th); ref1 = P.do_nms(ibx[perm], cls[perm], th)
+    assert np.array_equal(out[0, :n], ref0)
+    assert np.array_equal(out[1, :n], ref1)
+    assert np.array_equal(kept[0, :kc[0]], np.nonzero(ref0[:, 0] > 0)[0])
+    if th < 1.0:
+        assert (ref0[:, 0] > 0).sum() < (cls[:, 0] > 0).sum()      # something was suppressed
+    eng.close()
