@@ -193,8 +193,8 @@ struct fvy_handle {
     std::map<GraphKey, long long> graph_launches;   // kernels captured in each graph (what one replay launches)
     bool use_graph = true, capturing = false;
     struct Chain { int first = 0, count = 0; ChainLayer* dev = nullptr; std::vector<ChainLayer> host;
-                   int* d_sched = nullptr; int sched_stride = 0; std::vector<int> sched_host; };   // FVY_CHAIN_SCHED: per-pair work lists
-    bool chain_sched = false;
+                   int* d_sched = nullptr; int sched_stride = 0; std::vector<int> sched_host; bool sched_on = false; };   // FVY_CHAIN_SCHED: per-pair work lists
+    int chain_sched = 0;                 // 0 / 1 / 2 = auto (see prepare_chains)
     std::vector<Chain> chains; bool use_chain = true; int chain_batch = -1;
     int chain_nb = 3, chain_a = 4, chain_b = 6; size_t chain_smem = 0;
     int* d_flags = nullptr; size_t flags_bytes = 0; bool use_flags = true, flags_live = false;

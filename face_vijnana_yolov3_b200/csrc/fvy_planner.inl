@@ -5,7 +5,8 @@ namespace fvy {
 constexpr int kFuseStemDefault = 0;        // FVY_FUSE_STEM: conv_0 + conv_1 in one kernel
 constexpr int kCompactDefault = 2;         // FVY_COMPACT: shared-halo geometry of the narrow deep levels (see build_plan)
 constexpr int kChain128Default = 0;        // FVY_CHAIN_128: 128-wide 1x1 layers on the 256-wide pair tile (chain membership at 52^2)
-constexpr int kChainSchedDefault = 0;      // FVY_CHAIN_SCHED when neither the environment nor fvy_config.flags says otherwise
+constexpr int kChainSchedDefault = 2;      // FVY_CHAIN_SCHED: 0 static rotation inside the chains, 1 host list schedule, 2 list schedule for chains of few tile waves
+constexpr int kSchedMaxWaves = 12;
 
 template <int BN, int BK, bool CTA2>
 static int launch_conv_t(fvy_handle* h, Layer& L, int grid) {
@@ -391,7 +392,8 @@ static int build_plan(fvy_handle* h) {
     // output, go out as ONE persistent launch (conv_chain_kernel)
     {
         h->use_chain = h->use_flags && env_int("FVY_CHAIN", 1) != 0 && !(c.flags & FVY_CFG_NO_CHAIN);
-        h->chain_sched = (c.flags & FVY_CFG_CHAIN_SCHED) ? true : ((c.flags & FVY_CFG_NO_CHAIN_SCHED) ? false : env_int("FVY_CHAIN_SCHED", kChainSchedDefault) != 0);
+        // 0 = static rotation, 1 = host list schedule, 2 = the list schedule for chains whose layers give a pair at most kSchedMaxWaves tiles
+        h->chain_sched = (c.flags & FVY_CFG_CHAIN_SCHED) ? 1 : ((c.flags & FVY_CFG_NO_CHAIN_SCHED) ? 0 : env_int("FVY_CHAIN_SCHED", kChainSchedDefault));
         auto eligible = [&](const Layer& L) {
             if (!L.cta2 || L.BN != 256 || L.BK != 64 || L.s.stride != 1 || L.s.src < 0 || !L.s.bn) return false;
             if (L.p.b_resident || L.p.b_cover != 1) return false;
@@ -574,7 +576,13 @@ static int prepare_chains(fvy_handle* h, int batch) {
             c.bias_n = L.num_n_tiles * kChainBN;          // the bias array is zero-padded to a whole tile
         }
         CUDA_TRY(cudaMemcpyAsync(ch.dev, ch.host.data(), sizeof(ChainLayer) * ch.count, cudaMemcpyHostToDevice, h->stream));
-        if (h->chain_sched)
+        // The list schedule pays when a layer is a few tile waves (416 @ batch 40: 3.08 waves at 26^2, 1.68 at 13^2 - the static rotation
+        // rounds both up: forward 2.74 -> 2.69 ms); with tens of waves the rotation already balances and the work-list reads only cost
+        // (batch 320 @608: 49.5 -> 50.5 ms).
+        int most = 0;
+        for (int k = 0; k < ch.count; ++k) most = std::max(most, ((ch.host[k].p.num_m_tiles + 1) / 2) * ch.host[k].p.num_n_tiles);
+        ch.sched_on = h->chain_sched == 1 || (h->chain_sched >= 2 && most <= kSchedMaxWaves * pairs);
+        if (ch.sched_on)
             if (int e = schedule_chain(h, ch, pairs)) return e;
     }
     h->chain_batch = batch;
@@ -597,7 +605,7 @@ static int launch_chain(fvy_handle* h, const fvy_handle::Chain& ch) {
     ++na;
     cfg.attrs = at; cfg.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_chain_kernel, (const ChainLayer*)ch.dev, ch.count, h->chain_nb, h->chain_a, h->chain_b,
-                                (const int*)(h->chain_sched ? ch.d_sched : nullptr), ch.sched_stride));
+                                (const int*)(ch.sched_on ? ch.d_sched : nullptr), ch.sched_stride));
     h->launches += 1;
     return FVY_OK;
 }

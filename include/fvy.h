@@ -64,7 +64,7 @@ typedef struct {
 #define FVY_CFG_NO_GRAPH 0x01u         /* launch the conv stack kernel by kernel instead of replaying a CUDA graph (FVY_GRAPH=0) */
 #define FVY_CFG_NO_CHAIN 0x02u         /* no layer chains (conv_chain_kernel), one launch per layer (FVY_CHAIN=0) */
 #define FVY_CFG_NO_TILE_FLAGS 0x04u    /* kernel boundaries instead of cross-layer tile dependencies; implies NO_CHAIN (FVY_FLAGS=0) */
-#define FVY_CFG_CHAIN_SCHED 0x08u      /* per-pair work lists from the host list schedule inside the chains (FVY_CHAIN_SCHED=1) */
+#define FVY_CFG_CHAIN_SCHED 0x08u      /* per-pair work lists from the host list schedule inside every chain (FVY_CHAIN_SCHED=1; default: chains of few tile waves) */
 #define FVY_CFG_NO_CHAIN_SCHED 0x10u   /* static rotation inside the chains (FVY_CHAIN_SCHED=0) */
 #define FVY_CFG_NO_OVERLAP_POST 0x20u  /* asynchronous calls post-process on the main stream (FVY_OVERLAP_POST=0) */
 #define FVY_CFG_NO_FUSED_STEM 0x40u    /* conv_0 and conv_1 as two kernels with the 4-phase activation in HBM (FVY_FUSE_STEM=0) */
