@@ -599,6 +599,13 @@ def run_train(args, D):
     torch.cuda.empty_cache()
     tr16 = T.DataParallelTrainer(hps, device=f"cuda:{local}", stream=stream, bucket_mb=args.bucket_mb, autocast_bf16=True)
     ms16, _ = timed(tr16, args.steps)
+    del tr16
+    torch.cuda.empty_cache()
+    # the same fp32 step with the input gradients of the eligible stride-1 convolutions on this repo's tcgen05 kernel (bf16 operands)
+    tr_tc = T.DataParallelTrainer(hps, device=f"cuda:{local}", stream=stream, bucket_mb=args.bucket_mb, autocast_bf16=False, fvy_dgrad=True)
+    ms_tc, loss_tc = timed(tr_tc, args.steps)
+    n_tc = sum(1 for c in tr_tc.model.convs.values() if T._tc_eligible(c) and c.bias is None)
+    del tr_tc
     clocks = sampler.stop()
     if rank == 0:
         line = {"metric": "FaceDetector training images/sec (fwd+bwd+allreduce+Adam)", "value": GB / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -614,9 +621,12 @@ def run_train(args, D):
                 "baseline_all_cudnn": {"ms_per_step": ms_cudnn, "value": GB / (ms_cudnn * 1e-3),
                                        "note": "the same fp32 step with BatchNorm / LeakyReLU on torch's modules as well (everything library code)"},
                 "bf16_autocast": {"ms_per_step": ms16, "value": GB / (ms16 * 1e-3), "note": "narrower arithmetic than the reference's training; not the parity number"},
+                "tc_dgrad": {"ms_per_step": ms_tc, "value": GB / (ms_tc * 1e-3), "loss": loss_tc, "layers": n_tc,
+                             "note": "fp32 step with dX of the stride-1 convolutions on conv_igemm_kernel (fvy_conv_run: bf16 operands, fp32 accumulation; "
+                                     "forward and dW stay fp32 on cuDNN); gradient tensors within 3e-2 relative L2 of the all-fp32 step (GPU test) - opt-in, not the parity number"},
                 "compute": "hand-written: BatchNorm (batch statistics) + LeakyReLU forward / backward for all 52 pairs (fvy_bn_leaky_train_*), Keras Adam "
-                           "(fvy_adam_step), bucketed exchange + overlap, weight-stream interop; conv forward / dgrad / wgrad: torch autograd over cuDNN "
-                           "(library code - the part of row f-1 still open)",
+                           "(fvy_adam_step), bucketed exchange + overlap, weight-stream interop; conv forward / dgrad / wgrad of the headline value: torch autograd over cuDNN "
+                           "(library code); `tc_dgrad` is the step with dgrad on this repo's tcgen05 kernel - wgrad is the part of row f-1 still open",
                 "roofline": None, "cpu_baseline": None, "e2e": {"value": GB / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(xs.numel() * 4 + ts.numel() * 4),
                                                                "d2h_bytes_per_step": 4, "note": "every step copies its images / targets from pinned host memory and reads the loss back"},
                 "gpu_launches": None, "clocks": clocks}

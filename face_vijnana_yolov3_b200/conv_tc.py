@@ -1,0 +1,85 @@
+"""Single stride-1 convolutions on the tcgen05 implicit-GEMM kernel (``fvy_conv_*``, include/fvy.h) for the training step.
+
+``TcConv`` is one handle (one shape, one direction); ``conv_dgrad`` is what ``train._ConvFn.backward`` calls: the gradient of a
+stride-1 ``Conv2d`` with respect to its input, dX = conv(dY, flip(W)^T) - the part of the backward pass that Keras / TensorFlow
+hand to cuDNN when the reference trains (face_detection.py:361-381, :602-630).  bf16 operands, fp32 accumulation and output;
+there is no CPU fallback.
+"""
+import ctypes as C
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+class TcConv:
+    """cin -> cout, k x k (k = 1 or 3), stride 1, zero padding k // 2, over (batch <= max_batch, height, width) maps."""
+
+    def __init__(self, device: int, height: int, width: int, cin: int, cout: int, k: int, max_batch: int):
+        self.lib = L.load()
+        self.shape = (height, width, cin, cout, k)
+        self.device, self.max_batch = device, max_batch
+        h = C.c_void_p()
+        L.check(self.lib.fvy_conv_create(device, height, width, cin, cout, k, max_batch, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.fvy_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, w: torch.Tensor, dgrad: bool) -> None:
+        """w: the torch Conv2d weight (Co, Ci, k, k) float32 on this device, contiguous."""
+        assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+        st = torch.cuda.current_stream(w.device).cuda_stream
+        L.check(self.lib.fvy_conv_set_weights(self._h, C.c_void_p(w.data_ptr()), 1 if dgrad else 0, C.c_void_p(st)))
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (B, cin, H, W) float32 in channels_last memory format -> (B, cout, H, W) float32, channels_last."""
+        height, width, cin, cout, _ = self.shape
+        b = x.shape[0]
+        assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (cin, height, width), (tuple(x.shape), self.shape)
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = torch.empty((b, cout, height, width), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        L.check(self.lib.fvy_conv_run(self._h, C.c_void_p(x.data_ptr()), b, C.c_void_p(y.data_ptr()), C.c_void_p(st)))
+        return y
+
+
+_cache: Dict[Tuple, TcConv] = {}
+
+
+def eligible(weight: torch.Tensor, stride: int, padding: int) -> bool:
+    """dgrad of this Conv2d can run on the tcgen05 kernel: stride 1, k in (1, 3) with 'same' padding, Co a multiple of 32
+    (it is the K dimension of the dgrad GEMM), Ci <= 1024."""
+    co, ci, kh, kw = weight.shape
+    return (weight.is_cuda and weight.dtype == torch.float32 and stride == 1 and kh == kw and kh in (1, 3) and padding == kh // 2
+            and co % 32 == 0 and ci <= 1024 and ci % 4 == 0)
+
+
+def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Gradient w.r.t. the input of ``F.conv2d(x, weight, stride=1, padding=k // 2)`` given dy (B, Co, H, W)."""
+    co, ci, k, _ = weight.shape
+    b, _, height, width = dy.shape
+    dev = dy.device.index if dy.device.index is not None else torch.cuda.current_device()
+    key = (dev, height, width, co, ci, k)
+    h = _cache.get(key)
+    if h is None or h.max_batch < b:
+        if h is not None:
+            h.close()
+        h = _cache[key] = TcConv(dev, height, width, co, ci, k, max(b, h.max_batch if h else 0))
+    h.set_weights(weight.detach().contiguous(), dgrad=True)
+    return h.run(dy)
+
+
+def clear_cache() -> None:
+    for h in _cache.values():
+        h.close()
+    _cache.clear()

@@ -980,9 +980,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const OutDesc& od = p.out[o];
                     if ((o == 0 ? head0 : head1) && valid) {
                         float* dst = reinterpret_cast<float*>(od.ptr) + (((long long)img * p.H + h) * p.W + w) * od.c_real;
+                        if ((od.c_real & 3) == 0) {       // wide dense outputs (fvy_conv_run): 16-byte stores
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + c0 + j < od.c_real) dst[n0 + c0 + j] = v[j];
+                            for (int j = 0; j < 32; j += 4)
+                                if (n0 + c0 + j < od.c_real) *reinterpret_cast<float4*>(dst + n0 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + c0 + j < od.c_real) dst[n0 + c0 + j] = v[j];
+                        }
                     }
                 }
                 // stage the bf16 chunk (halo / out-of-image rows as zeros: they ARE the padding of the next layer)

@@ -12,6 +12,8 @@ using namespace fvy;
 // ============================================================================================ C ABI
 extern "C" {
 
+#define NO_CONV_HANDLE(h) do { if ((h) && (h)->conv_mode) return fail(FVY_E_STATE, "single-convolution handle: only fvy_conv_set_weights / fvy_conv_run / fvy_destroy apply"); } while (0)
+
 const char* fvy_last_error(void) { return g_err; }
 const char* fvy_version(void) { return "fvy 0.1 (sm_100a: tcgen05/TMEM/TMA implicit-GEMM conv, bitmask NMS)"; }
 
@@ -39,6 +41,9 @@ void fvy_destroy(fvy_handle* h) {
     delete h;
 }
 
+// Shared tail of fvy_create / fvy_conv_create: device checks, streams and events, plan, scratch.  conv_k > 0 = single-convolution handle.
+static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int conv_k, fvy_handle** out);
+
 int fvy_create(const fvy_config* cfg, fvy_handle** out) {
     if (!cfg || !out) return fail(FVY_E_INVALID, "NULL argument");
     *out = nullptr;
@@ -49,6 +54,10 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
     if (cfg->head == FVY_HEAD_FD6 && cfg->bb_info_c_size != 6) return fail(FVY_E_INVALID, "bb_info_c_size must be 6 (FaceDetector.detect reads channels 0..5)");
     if (cfg->tile_n_max != 0 && cfg->tile_n_max != 32 && cfg->tile_n_max != 64 && cfg->tile_n_max != 128 && cfg->tile_n_max != 256)
         return fail(FVY_E_INVALID, "tile_n_max %d", cfg->tile_n_max);
+    return create_impl(cfg, 0, 0, 0, out);
+}
+
+static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int conv_k, fvy_handle** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(FVY_E_CUDA, "no CUDA device (there is no CPU fallback)"); }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(FVY_E_INVALID, "device %d of %d", cfg->device, ndev);
@@ -59,6 +68,7 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
     fvy_handle* h = new fvy_handle();
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
+    h->conv_mode = conv_k > 0; h->conv_cin = conv_cin; h->conv_cout = conv_cout; h->conv_k = conv_k;
     int e = FVY_OK;
     do {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { e = fail(FVY_E_CUDA, "cudaStreamCreate failed"); break; }
@@ -97,6 +107,7 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
 long long fvy_weight_count(const fvy_handle* h) { return h ? h->weight_count : 0; }
 
 int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats) {
+    NO_CONV_HANDLE(h);
     if (!h || !stream) return fail(FVY_E_INVALID, "NULL argument");
     if (h->cfg.head == FVY_HEAD_NONE) return fail(FVY_E_STATE, "handle has no network");
     if ((long long)n_floats != h->weight_count) return fail(FVY_E_INVALID, "weight stream has %zu floats, network needs %lld", n_floats, h->weight_count);
@@ -146,6 +157,7 @@ int fvy_load_weights(fvy_handle* h, const float* stream, size_t n_floats) {
 }
 
 int fvy_forward(fvy_handle* h, const void* images, int dtype, int batch, float* out0, float* out1, float* out2) {
+    NO_CONV_HANDLE(h);
     if (!h || !images) return fail(FVY_E_INVALID, "NULL argument");
     if (h->cfg.head == FVY_HEAD_NONE) return fail(FVY_E_STATE, "handle has no network");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -169,6 +181,7 @@ int fvy_forward(fvy_handle* h, const void* images, int dtype, int batch, float* 
 int fvy_decode(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch, const fvy_post_params* pp,
                const int* image_hw, int cap, double* nbox, int32_t* ibox, float* objness, float* classes, int32_t* cand,
                int32_t* counts) {
+    NO_CONV_HANDLE(h);
     if (!h) return fail(FVY_E_INVALID, "NULL handle");
     if (int e = check_pp(h, pp)) return e;
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
@@ -199,6 +212,7 @@ int fvy_decode(fvy_handle* h, const float* out0, const float* out1, const float*
 
 int fvy_correct_boxes(fvy_handle* h, const double* nbox, int n, int image_h, int image_w, int net_h, int net_w, int arith,
                       int32_t* ibox) {
+    NO_CONV_HANDLE(h);
     if (!h || !nbox || !ibox) return fail(FVY_E_INVALID, "NULL argument");
     if (n < 0 || (size_t)n > (size_t)h->cfg.max_batch * h->cap) return fail(FVY_E_INVALID, "n %d exceeds scratch capacity", n);
     if (n == 0) return FVY_OK;
@@ -220,6 +234,7 @@ int fvy_correct_boxes(fvy_handle* h, const double* nbox, int n, int image_h, int
 
 int fvy_nms(fvy_handle* h, const int32_t* ibox, const int32_t* counts, int batch, int seg_stride, int nb_class, double nms_thresh,
             float* classes, int32_t* kept_idx, int32_t* kept_counts) {
+    NO_CONV_HANDLE(h);
     if (!h || !ibox || !counts || !classes) return fail(FVY_E_INVALID, "NULL argument");
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
     if (seg_stride < 1 || seg_stride > h->cap) return fail(FVY_E_INVALID, "seg_stride %d outside [1, %d]", seg_stride, h->cap);
@@ -258,6 +273,7 @@ int fvy_nms(fvy_handle* h, const int32_t* ibox, const int32_t* counts, int batch
 }
 
 int fvy_bbox_iou(fvy_handle* h, const int32_t* a, const int32_t* b, int n, double* out) {
+    NO_CONV_HANDLE(h);
     if (!h || !a || !b || !out) return fail(FVY_E_INVALID, "NULL argument");
     if (n < 0 || (size_t)n * 2 > (size_t)h->cfg.max_batch * h->cap) return fail(FVY_E_INVALID, "n %d exceeds scratch capacity", n);
     if (n == 0) return FVY_OK;
@@ -276,6 +292,7 @@ int fvy_bbox_iou(fvy_handle* h, const int32_t* a, const int32_t* b, int n, doubl
 }
 
 int fvy_bbox_iou_fp(fvy_handle* h, const double* a, const double* b, int n, int arith, double* out) {
+    NO_CONV_HANDLE(h);
     if (!h || !a || !b || !out) return fail(FVY_E_INVALID, "NULL argument");
     if (arith != FVY_ARITH_F64 && arith != FVY_ARITH_F32) return fail(FVY_E_INVALID, "arith %d", arith);
     if (n < 0 || (size_t)n * 3 > (size_t)h->cfg.max_batch * h->cap) return fail(FVY_E_INVALID, "n %d exceeds scratch capacity", n);
@@ -294,6 +311,7 @@ int fvy_bbox_iou_fp(fvy_handle* h, const double* a, const double* b, int n, int 
 
 int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batch, int seg_stride, int nb_class, double nms_thresh,
                int arith, float* classes, int32_t* kept_idx, int32_t* kept_counts) {
+    NO_CONV_HANDLE(h);
     if (!h || !box || !counts || !classes) return fail(FVY_E_INVALID, "NULL argument");
     if (arith != FVY_ARITH_F64 && arith != FVY_ARITH_F32) return fail(FVY_E_INVALID, "arith %d", arith);
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
@@ -344,6 +362,7 @@ int fvy_nms_fp(fvy_handle* h, const double* box, const int32_t* counts, int batc
 
 int fvy_map_match(fvy_handle* h, const double* gt_box, const int32_t* gt_off, const double* det_box, const int32_t* det_off, int n_img,
                   double* det_iou, int32_t* img_any) {
+    NO_CONV_HANDLE(h);
     if (!h || !gt_off || !det_off || !det_iou || !img_any) return fail(FVY_E_INVALID, "NULL argument");
     if (n_img < 0) return fail(FVY_E_INVALID, "n_img %d", n_img);
     if (n_img == 0) return FVY_OK;
@@ -386,6 +405,7 @@ int fvy_map_match(fvy_handle* h, const double* gt_box, const int32_t* gt_off, co
 }
 
 int fvy_netout_sigmoid(fvy_handle* h, float* netout, long long n_boxes, int nb_class) {
+    NO_CONV_HANDLE(h);
     if (!h || !netout) return fail(FVY_E_INVALID, "NULL argument");
     if (n_boxes < 0 || nb_class < 1) return fail(FVY_E_INVALID, "bad size");
     if (n_boxes == 0) return FVY_OK;
@@ -450,6 +470,7 @@ static int postprocess_common(fvy_handle* h, const float* out0, const float* out
 
 int fvy_postprocess(fvy_handle* h, const float* out0, const float* out1, const float* out2, int batch, const fvy_post_params* pp,
                     const int* image_hw, int max_out, fvy_det* dets, int32_t* det_counts) {
+    NO_CONV_HANDLE(h);
     if (!h) return fail(FVY_E_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (int e = harvest_async_all(h)) return e;
@@ -544,6 +565,7 @@ int fvy_layer_info(const fvy_handle* h, int layer, int* info) {
 }
 
 int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host) {
+    NO_CONV_HANDLE(h);
     if (!h || !dst_host || layer < 0 || layer >= (int)h->layers.size()) return fail(FVY_E_INVALID, "bad argument");
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d", batch);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -564,6 +586,7 @@ int fvy_layer_output(fvy_handle* h, int layer, int batch, float* dst_host) {
 }
 
 float* fvy_staged_images(fvy_handle* h) {
+    if (h && h->conv_mode) { fail(FVY_E_STATE, "single-convolution handle"); return nullptr; }
     if (!h) return nullptr;
     if (!h->d_staged) {
         cudaSetDevice(h->cfg.device);
@@ -576,6 +599,7 @@ float* fvy_staged_images(fvy_handle* h) {
 }
 
 int fvy_read_staged(fvy_handle* h, int batch, float* dst) {
+    NO_CONV_HANDLE(h);
     if (!h || !dst) return fail(FVY_E_INVALID, "fvy_read_staged: NULL argument");
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "fvy_read_staged: batch %d outside [1, %d]", batch, h->cfg.max_batch);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -587,6 +611,7 @@ int fvy_read_staged(fvy_handle* h, int batch, float* dst) {
 }
 
 int fvy_letterbox_u8(fvy_handle* h, const unsigned char* src, int src_h, int src_w, int w_p, int h_p, int pad_t, int pad_l, int index) {
+    NO_CONV_HANDLE(h);
     if (!h || !src) return fail(FVY_E_INVALID, "fvy_letterbox_u8: NULL argument");
     if (src_h <= 0 || src_w <= 0 || w_p <= 0 || h_p <= 0 || pad_t < 0 || pad_l < 0 || pad_t + h_p > h->cfg.net_h || pad_l + w_p > h->cfg.net_w)
         return fail(FVY_E_INVALID, "fvy_letterbox_u8: %dx%d -> %dx%d at (%d, %d) does not fit the %dx%d network input", src_w, src_h, w_p, h_p, pad_l, pad_t,
@@ -628,6 +653,7 @@ int fvy_last_timing(const fvy_handle* h, float* forward_ms, float* post_ms) {
 }
 
 int fvy_profile_layers(fvy_handle* h, int batch, int iters, float* ms) {
+    NO_CONV_HANDLE(h);
     if (!h || !ms) return fail(FVY_E_INVALID, "NULL argument");
     if (!h->weights_loaded) return fail(FVY_E_STATE, "weights not loaded");
     if (batch < 1 || batch > h->cfg.max_batch || iters < 1) return fail(FVY_E_INVALID, "bad batch/iters");
@@ -809,6 +835,56 @@ int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows,
     bn_bwd_apply_kernel<<<ga, 256, 0, st>>>(x, dy, rows * C / 4, rows, C, gamma, beta, save_mean, save_invstd, slope, workspace, dx);
     CUDA_TRY(cudaGetLastError());
     return FVY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ single convolution (row f-1: dgrad)
+int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int max_batch, fvy_handle** out) {
+    if (!out) return fail(FVY_E_INVALID, "NULL argument");
+    *out = nullptr;
+    if (height < 1 || width < 1 || height > 4096 || width > 4096) return fail(FVY_E_INVALID, "feature map %dx%d", height, width);
+    if (ksize != 1 && ksize != 3) return fail(FVY_E_INVALID, "kernel size %d (1 or 3)", ksize);
+    if (cin < 32 || cin % 32 || cin > 2048) return fail(FVY_E_INVALID, "Cin %d must be a multiple of 32 in [32, 2048]", cin);
+    if (cout < 1 || cout > kMaxCout) return fail(FVY_E_INVALID, "Cout %d outside [1, %d]", cout, kMaxCout);
+    if (max_batch < 1 || max_batch > 1024) return fail(FVY_E_INVALID, "max_batch %d outside [1, 1024]", max_batch);
+    fvy_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device; cfg.net_h = height; cfg.net_w = width; cfg.head = FVY_HEAD_YOLO3; cfg.nb_class = 1; cfg.bb_info_c_size = 6;
+    cfg.max_batch = max_batch; cfg.flags = FVY_CFG_NO_GRAPH | FVY_CFG_NO_CHAIN | FVY_CFG_NO_TILE_FLAGS;
+    return create_impl(&cfg, cin, cout, ksize, out);
+}
+
+int fvy_conv_set_weights(fvy_handle* h, const float* w_dev, int dgrad, void* stream) {
+    if (!h || !w_dev) return fail(FVY_E_INVALID, "NULL argument");
+    if (!h->conv_mode) return fail(FVY_E_STATE, "not a single-convolution handle");
+    if (!is_device_ptr(w_dev)) return fail(FVY_E_INVALID, "fvy_conv_set_weights takes a device pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    Layer& L = h->layers[0];
+    const long long total = (long long)L.cout_pad * L.taps * L.cin_pad;
+    conv_weight_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(
+        w_dev, h->conv_cin, h->conv_cout, L.cout_pad, L.taps, dgrad != 0, L.w);
+    CUDA_TRY(cudaGetLastError());
+    h->weights_loaded = true;
+    return FVY_OK;
+}
+
+int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, void* stream) {
+    if (!h || !x_dev || !y_dev) return fail(FVY_E_INVALID, "NULL argument");
+    if (!h->conv_mode) return fail(FVY_E_STATE, "not a single-convolution handle");
+    if (!h->weights_loaded) return fail(FVY_E_STATE, "fvy_conv_run before fvy_conv_set_weights");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (!is_device_ptr(x_dev) || !is_device_ptr(y_dev)) return fail(FVY_E_INVALID, "fvy_conv_run takes device pointers");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    Layer& L = h->layers[0];
+    const cudaStream_t st = (cudaStream_t)stream, saved = h->stream;
+    const long long groups = (long long)batch * L.Hin * L.Win * (h->conv_cin / 8);
+    pack_padded_kernel<<<(unsigned)std::min<long long>((groups + 255) / 256, (long long)h->num_sms * 32), 256, 0, st>>>(
+        x_dev, batch, L.Hin, L.Win, h->conv_cin, L.p.dom_w, L.p.dom_plane, h->d_conv_in);
+    CUDA_TRY(cudaGetLastError());
+    h->conv_out = y_dev;
+    h->stream = st;                       // the layer is enqueued on the caller's stream, behind the pack kernel
+    const int e = run_layers(h, batch, 0, 1);
+    h->stream = saved;
+    return e;
 }
 
 void* fvy_host_alloc(size_t bytes) {

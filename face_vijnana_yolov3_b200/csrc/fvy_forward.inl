@@ -91,7 +91,8 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
             if (h->last_slot >= 0 && !h->capturing) { CUDA_TRY(cudaEventRecord(h->ev_consumed[h->last_slot], h->stream)); h->last_slot = -1; }
             continue;
         }
-        if (!L.s.bn && L.head_slot >= 0)     // head logits of this call's set
+        if (h->conv_mode) L.p.out[0].ptr = h->conv_out;          // fvy_conv_run: the caller's output tensor
+        else if (!L.s.bn && L.head_slot >= 0)     // head logits of this call's set
             L.p.out[0].ptr = h->logit_set ? h->d_logits_alt[L.head_slot] : h->d_logits[L.head_slot];
         L.p.m_total = batch * L.p.dom_plane;
         L.p.num_m_tiles = (L.p.m_total + kBlockM - 1) / kBlockM;
@@ -145,6 +146,7 @@ static int run_layers(fvy_handle* h, int batch, int first, int last) {
 }
 
 static int forward_enqueue(fvy_handle* h, const void* images, int dtype, int batch) {
+    if (h->conv_mode) return fail(FVY_E_STATE, "single-convolution handle: use fvy_conv_run");
     if (!h->weights_loaded) return fail(FVY_E_STATE, "fvy_forward before fvy_load_weights");
     if (batch < 1 || batch > h->cfg.max_batch) return fail(FVY_E_INVALID, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
     if (dtype != FVY_F32 && dtype != FVY_F64 && dtype != FVY_U8) return fail(FVY_E_INVALID, "dtype %d", dtype);

@@ -9,7 +9,8 @@ namespace fvy {
 struct ConvSpec {
     int idx, cin, cout, k, stride;
     bool bn, leaky;
-    int src;     // conv idx feeding this conv; -1 network input; -2 concat A (up(84), skip_61); -3 concat B (up(96), skip_36)
+    int src;     // conv idx feeding this conv; -1 network input; -2 concat A (up(84), skip_61); -3 concat B (up(96), skip_36);
+                 // -4 a padded bf16 buffer filled by the caller's pack step (single-convolution handles)
     int res;     // conv idx whose stored output is added after the activation, or -1
     int level;   // log2 down-sampling of the OUTPUT
 };
@@ -64,6 +65,12 @@ inline std::vector<ConvSpec> fd6_table(int bb_info_c_size) {
     for (const ConvSpec& c : yolo3_table(1)) if (c.idx <= 73) v.push_back(c);
     v.push_back({kFd6HeadIdx, 1024, bb_info_c_size, 3, 1, false, false, 73, -1, 5});   // face_detection.py:348-352
     return v;
+}
+
+// One stride-1 convolution on its own (fvy_conv_create): no BatchNorm, no bias, no activation, input handed in by the caller
+// (src = -4), dense fp32 output.
+inline std::vector<ConvSpec> single_conv_table(int cin, int cout, int k) {
+    return {ConvSpec{0, cin, cout, k, 1, false, false, -4, -1, 0}};
 }
 
 }  // namespace fvy

@@ -78,7 +78,8 @@ struct TensorBufs { __nv_bfloat16* padded = nullptr; __nv_bfloat16* phase = null
 
 static int build_plan(fvy_handle* h) {
     const fvy_config& c = h->cfg;
-    std::vector<ConvSpec> specs = c.head == FVY_HEAD_YOLO3 ? yolo3_table(c.nb_class) : fd6_table(c.bb_info_c_size);
+    std::vector<ConvSpec> specs = h->conv_mode ? single_conv_table(h->conv_cin, h->conv_cout, h->conv_k)
+                                               : (c.head == FVY_HEAD_YOLO3 ? yolo3_table(c.nb_class) : fd6_table(c.bb_info_c_size));
     const int nmax = c.max_batch;
     // which stored forms does each producer need?
     std::map<int, bool> need_padded, need_phase;
@@ -106,7 +107,7 @@ static int build_plan(fvy_handle* h) {
     auto geom_plane = [&](int level) { return (long long)((c.net_h >> level) + (share_rows(level) ? 1 : 2)) * geom_w(level); };
     // concat buffers (yolo3 only): A = [up(conv_84) 256 | skip_61 512] at level 4, B = [up(conv_96) 128 | skip_36 256] at level 3
     __nv_bfloat16 *catA = nullptr, *catB = nullptr;
-    if (c.head == FVY_HEAD_YOLO3) {
+    if (c.head == FVY_HEAD_YOLO3 && !h->conv_mode) {
         int H, W;
         HW(4, &H, &W);
         if (int e = dev_alloc(h, (void**)&catA, (size_t)nmax * geom_plane(4) * 768 * 2, true)) return e;
@@ -120,6 +121,8 @@ static int build_plan(fvy_handle* h) {
         if (const char* sb = getenv("FVY_STEM_BLOCKS")) if (*sb) h->stem_blocks_per_sm = atoi(sb);
     }
     if (int e = dev_alloc(h, (void**)&h->d_stem_w2, 32 * 32 * 2, true)) return e;
+    if (h->conv_mode)       // the caller's tensor is packed into this padded buffer (halo = the zeros it is allocated with)
+        if (int e = dev_alloc(h, (void**)&h->d_conv_in, (size_t)nmax * geom_plane(0) * h->conv_cin * 2, true)) return e;
     // activation buffers
     for (const ConvSpec& s : specs) {
         int H, W;
@@ -139,8 +142,10 @@ static int build_plan(fvy_handle* h) {
             HW(s.level, &H, &W);
             if (nh >= 3) return fail(FVY_E_INVALID, "more than 3 heads");
             h->gh[nh] = H; h->gw[nh] = W; h->head_c = s.cout;
-            if (int e = dev_alloc(h, (void**)&h->d_logits[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
-            if (int e = dev_alloc(h, (void**)&h->d_logits_alt[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
+            if (!h->conv_mode) {      // a single-convolution handle writes to the caller's tensor
+                if (int e = dev_alloc(h, (void**)&h->d_logits[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
+                if (int e = dev_alloc(h, (void**)&h->d_logits_alt[nh], (size_t)nmax * H * W * s.cout * 4, true)) return e;
+            }
             ++nh;
         }
     const int bn_cap = c.tile_n_max > 0 ? c.tile_n_max : env_int("FVY_BN", 256);
@@ -290,6 +295,7 @@ static int build_plan(fvy_handle* h) {
         } else {
             if (s.src == -2) { a_base = catA; a_pitch = 768; }
             else if (s.src == -3) { a_base = catB; a_pitch = 384; }
+            else if (s.src == -4) { a_base = h->d_conv_in; a_pitch = s.cin; }
             else { a_base = bufs[s.src].padded; a_pitch = s.cin; }
             const int gw = geom_w(s.level);
             a_rows = (uint64_t)nmax * geom_plane(s.level);
@@ -341,7 +347,8 @@ static int build_plan(fvy_handle* h) {
         };
         if (!s.bn) {
             L.head_slot = head_i;
-            add_out(h->d_logits[head_i++], OUT_HEAD_F32, s.cout, 0, s.cout);
+            add_out(h->conv_mode ? (void*)h->d_conv_in /* placeholder: set per call */ : (void*)h->d_logits[head_i], OUT_HEAD_F32, s.cout, 0, s.cout);
+            ++head_i;
         } else {
             if (bufs[s.idx].padded) add_out(bufs[s.idx].padded, OUT_PADDED, s.cout, 0, s.cout);
             if (bufs[s.idx].phase) add_out(bufs[s.idx].phase, OUT_PHASE, s.cout, 0, s.cout);

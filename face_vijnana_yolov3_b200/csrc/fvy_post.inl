@@ -10,6 +10,7 @@ static int total_cands(const fvy_handle* h) {
 
 static int build_post(fvy_handle* h) {
     const fvy_config& c = h->cfg;
+    if (h->conv_mode) return FVY_OK;          // no decode / NMS behind a single convolution
     const int B = c.max_batch;
     if (c.head == FVY_HEAD_NONE || c.head == FVY_HEAD_YOLO3) {
         int i = 0;

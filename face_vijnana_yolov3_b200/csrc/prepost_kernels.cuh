@@ -33,6 +33,44 @@ __global__ void unpack_kernel(OutDesc od, int batch, int H, int W, int C, float*
     }
 }
 
+// ------------------------------------------------------------------------------------------ single convolution (fvy_conv_*)
+// Dense NHWC fp32 -> the interior of a padded bf16 buffer (row pitch dst_w pixels, dst_plane pixels per image): 8 channels per thread.
+__global__ void __launch_bounds__(256) pack_padded_kernel(const float* __restrict__ x, int batch, int H, int W, int C, int dst_w, int dst_plane,
+                                                          __nv_bfloat16* __restrict__ dst) {
+    const int cg = C >> 3;
+    const long long total = (long long)batch * H * W * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        long long t = i / cg;
+        const int w = (int)(t % W); t /= W;
+        const int hh = (int)(t % H);
+        const long long n = t / H;
+        const float4* src = reinterpret_cast<const float4*>(x + (((n * H + hh) * W + w) * (long long)C + g * 8));
+        const float4 a = src[0], b = src[1];
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<unsigned*>(&p0); o.y = *reinterpret_cast<unsigned*>(&p1);
+        o.z = *reinterpret_cast<unsigned*>(&p2); o.w = *reinterpret_cast<unsigned*>(&p3);
+        *reinterpret_cast<uint4*>(dst + ((n * dst_plane + (long long)(hh + 1) * dst_w + (w + 1)) * C + g * 8)) = o;
+    }
+}
+// torch Conv2d weight [Co][Ci][k][k] fp32 -> the plan's [cout_pad][taps][cin] bf16.  dgrad = 0: this convolution (the handle was created
+// with cin = Ci, cout = Co).  dgrad = 1: the convolution that maps dY to dX (handle created with cin = Co, cout = Ci): weights
+// transposed and the taps reversed (both filter axes flipped), dX = conv(dY, flip(W)^T) for a stride-1 'same' convolution.
+__global__ void __launch_bounds__(256) conv_weight_kernel(const float* __restrict__ w, int cin, int cout, int cout_pad, int taps, bool dgrad,
+                                                          __nv_bfloat16* __restrict__ dst) {
+    const long long total = (long long)cout_pad * taps * cin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const int t = (int)((i / cin) % taps);
+        const int o = (int)(i / ((long long)cin * taps));
+        float v = 0.f;
+        if (o < cout) v = dgrad ? w[((long long)ci * cout + o) * taps + (taps - 1 - t)] : w[((long long)o * cin + ci) * taps + t];
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ letterbox (face_detection.py:657-690)
 // cv.resize(image / 255, (w_p, h_p), INTER_CUBIC) + zero border, restated operation for operation (OpenCV resizeGeneric_ for
 // CV_64F: interpolateCubic with A = -0.75 in float, HResizeCubic then VResizeCubic accumulating in double left to right,

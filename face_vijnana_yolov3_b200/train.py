@@ -171,6 +171,33 @@ class _BnLeakyFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None
 
 
+def _tc_eligible(conv: nn.Conv2d) -> bool:
+    from . import conv_tc
+    return conv_tc.eligible(conv.weight, conv.stride[0], conv.padding[0])
+
+
+class _ConvFn(torch.autograd.Function):
+    """A stride-1 Conv2d whose gradient w.r.t. the INPUT runs on this repo's tcgen05 implicit-GEMM kernel (``conv_tc.conv_dgrad``:
+    bf16 operands, fp32 accumulation); the forward and the weight gradient stay on cuDNN in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, padding):
+        ctx.save_for_backward(x, weight)
+        ctx.padding = padding
+        return F.conv2d(x, weight, None, 1, padding)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import conv_tc
+        x, weight = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_tc.conv_dgrad(dy, weight)
+        if ctx.needs_input_grad[1]:
+            dw = torch.nn.grad.conv2d_weight(x, weight.shape, dy, 1, ctx.padding)
+        return dx, dw, None
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # model
 # ----------------------------------------------------------------------------------------------------------------------
@@ -185,6 +212,7 @@ class FdNet(nn.Module):
         super().__init__()
         self.specs = arch.fd6_table(bb_info_c_size)
         self.fvy_bn = False        # True: BatchNorm (training) + LeakyReLU through this repo's kernels (fp32 CUDA tensors only)
+        self.fvy_dgrad = False     # True: input gradients of the stride-1 convolutions on the tcgen05 kernel (bf16 operands)
         self.convs = nn.ModuleDict()
         self.bns = nn.ModuleDict()
         for c in self.specs:
@@ -197,7 +225,13 @@ class FdNet(nn.Module):
         outs: Dict[int, torch.Tensor] = {-1: x}
         y = x
         for c in self.specs:
-            y = self.convs[str(c.idx)](outs[c.src])
+            conv = self.convs[str(c.idx)]
+            xin = outs[c.src]
+            if (self.fvy_dgrad and self.training and conv.bias is None and xin.requires_grad and xin.dtype == torch.float32 and
+                    _tc_eligible(conv)):
+                y = _ConvFn.apply(xin, conv.weight, conv.padding[0])
+            else:
+                y = conv(xin)
             if c.bn and self.fvy_bn and self.training and y.is_cuda and y.dtype == torch.float32:
                 bn = self.bns[str(c.idx)]
                 y = _BnLeakyFn.apply(y, bn.weight, bn.bias, bn, 0.1 if c.leaky else 1.0)
@@ -303,7 +337,8 @@ class DataParallelTrainer:
     """
 
     def __init__(self, hps: dict, device: str = "cpu", bb_info_c_size: int = 6, bucket_mb: float = 32.0, autocast_bf16: bool = False,
-                 stream: Optional[np.ndarray] = None, model: Optional[nn.Module] = None, fvy_bn: Optional[bool] = None):
+                 stream: Optional[np.ndarray] = None, model: Optional[nn.Module] = None, fvy_bn: Optional[bool] = None,
+                 fvy_dgrad: bool = False):
         self.device = torch.device(device)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
@@ -318,6 +353,9 @@ class DataParallelTrainer:
         # BatchNorm + LeakyReLU on this repo's kernels whenever they can run (fp32 on a GPU); torch's modules otherwise
         if hasattr(self.model, "fvy_bn"):
             self.model.fvy_bn = (self.device.type == "cuda" and not self.autocast_bf16) if fvy_bn is None else bool(fvy_bn)
+        # input gradients of the stride-1 convolutions on the tcgen05 kernel (bf16 operands: opt-in, the reference trains in fp32)
+        if hasattr(self.model, "fvy_dgrad"):
+            self.model.fvy_dgrad = bool(fvy_dgrad) and self.device.type == "cuda" and not self.autocast_bf16
         # flat buckets in REVERSE parameter order (= the order autograd finishes gradients in)
         params = [p for p in self.model.parameters() if p.requires_grad]
         limit = int(bucket_mb * (1 << 20) / 4)

@@ -231,6 +231,23 @@ int fvy_bn_leaky_train_forward(const float* x, long long rows, int C, const floa
 int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows, int C, const float* gamma, const float* beta,
                                 const float* save_mean, const float* save_invstd, float slope, float* dx, float* dgamma, float* dbeta,
                                 double* workspace, void* cuda_stream);
+/* Training step, row f-1 (second slice): the gradient of a stride-1 convolution with respect to its INPUT (dgrad) on the tcgen05
+ * implicit-GEMM kernel of the forward path.  Replaces what Keras / TensorFlow run through cuDNN for the backward of every stride-1
+ * Conv2D of the reference's model when it trains (src/space/yolov3_detect.py:206-211 via src/space/face_detection.py:361-381,
+ * :602-630): dX = conv(dY, flip(W)^T), i.e. a 'same' convolution of the output gradient with the weights transposed and both filter
+ * axes reversed.  A single-convolution handle holds one k x k (k = 1 or 3), stride-1, zero-padded convolution cin -> cout over
+ * [batch][height][width] maps without bias or activation: bf16 operands (the caller's float32 tensors are rounded once), float32
+ * accumulation, float32 output.
+ *   fvy_conv_create      : cin a multiple of 32 (the kernel's K chunk), cout <= 1024.  For dgrad of a forward layer Ci -> Co create
+ *                          the handle with cin = Co, cout = Ci.
+ *   fvy_conv_set_weights : w = the torch / Keras-transposed weight tensor [Co][Ci][k][k] float32 in DEVICE memory.  dgrad = 0: this
+ *                          handle computes the forward convolution (cin = Ci, cout = Co); dgrad = 1: it computes dX from dY.
+ *   fvy_conv_run         : x [batch][height][width][cin] float32 NHWC (DEVICE), y [batch][height][width][cout] float32 NHWC (DEVICE);
+ *                          everything is enqueued on `cuda_stream` (the caller's stream), nothing synchronises.
+ * Only fvy_conv_set_weights / fvy_conv_run / fvy_destroy / fvy_launch_count apply to such a handle. */
+int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int max_batch, fvy_handle** out);
+int fvy_conv_set_weights(fvy_handle* h, const float* w_dev, int dgrad, void* cuda_stream);
+int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, void* cuda_stream);
 /* Pre-processing of FaceDetector.evaluate / FaceDetector.test (src/space/face_detection.py:657-690 and :798-835):
  *   image = imread(file) / 255;  image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC);
  *   image = cv.copyMakeBorder(image, pad_t, pad_b, pad_l, pad_r, cv.BORDER_CONSTANT, value=[0, 0, 0])

