@@ -606,6 +606,17 @@ def run_train(args, D):
     ms_tc, loss_tc = timed(tr_tc, args.steps)
     n_tc = sum(1 for c in tr_tc.model.convs.values() if T._tc_eligible(c) and c.bias is None)
     del tr_tc
+    torch.cuda.empty_cache()
+    # ... plus the weight gradients on conv_wgrad_kernel (mode 3), plus the forward on the tcgen05 kernel (mode 7: every stride-1 conv on this repo's kernels)
+    fvy_conv = {}
+    for mode, key in ((3, "fvy_conv_backward"), (7, "fvy_conv_all")):
+        from face_vijnana_yolov3_b200 import conv_tc
+        conv_tc.clear_cache()
+        trm = T.DataParallelTrainer(hps, device=f"cuda:{local}", stream=stream, bucket_mb=args.bucket_mb, autocast_bf16=False, fvy_conv_mode=mode)
+        ms_m, loss_m = timed(trm, args.steps)
+        fvy_conv[key] = {"ms_per_step": ms_m, "value": GB / (ms_m * 1e-3), "loss": loss_m, "mode": mode}
+        del trm
+        torch.cuda.empty_cache()
     clocks = sampler.stop()
     if rank == 0:
         line = {"metric": "FaceDetector training images/sec (fwd+bwd+allreduce+Adam)", "value": GB / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -623,7 +634,11 @@ def run_train(args, D):
                 "bf16_autocast": {"ms_per_step": ms16, "value": GB / (ms16 * 1e-3), "note": "narrower arithmetic than the reference's training; not the parity number"},
                 "tc_dgrad": {"ms_per_step": ms_tc, "value": GB / (ms_tc * 1e-3), "loss": loss_tc, "layers": n_tc,
                              "note": "fp32 step with dX of the stride-1 convolutions on conv_igemm_kernel (fvy_conv_run: bf16 operands, fp32 accumulation; "
-                                     "forward and dW stay fp32 on cuDNN); gradient tensors within 3e-2 relative L2 of the all-fp32 step (GPU test) - opt-in, not the parity number"},
+                                     "forward and dW stay fp32 on cuDNN); gradient buckets within 1e-2 relative L2 of the all-fp32 step (GPU test) - opt-in, not the parity number"},
+                "fvy_conv_backward": dict(fvy_conv["fvy_conv_backward"], note="tc_dgrad plus dW of the stride-1 convolutions (Cin, Cout multiples of 64) on conv_wgrad_kernel "
+                                          "(fvy_conv_wgrad: pixel-dimension GEMM, warp-level bf16 MMAs, fp32 accumulation); forward fp32 on cuDNN"),
+                "fvy_conv_all": dict(fvy_conv["fvy_conv_all"], note="forward, dX and dW of every stride-1 convolution on this repo's kernels (bf16 operands): compare with bf16_autocast, "
+                                     "the library's step at the same operand precision"),
                 "compute": "hand-written: BatchNorm (batch statistics) + LeakyReLU forward / backward for all 52 pairs (fvy_bn_leaky_train_*), Keras Adam "
                            "(fvy_adam_step), bucketed exchange + overlap, weight-stream interop; conv forward / dgrad / wgrad of the headline value: torch autograd over cuDNN "
                            "(library code); `tc_dgrad` is the step with dgrad on this repo's tcgen05 kernel - wgrad is the part of row f-1 still open",

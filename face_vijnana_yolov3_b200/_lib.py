@@ -45,7 +45,8 @@ SYMBOLS = ["fvy_last_error", "fvy_version", "fvy_create", "fvy_destroy", "fvy_lo
            "fvy_layer_info", "fvy_layer_output", "fvy_launch_count", "fvy_last_timing", "fvy_profile_layers", "fvy_run_layer", "fvy_timer_start", "fvy_timer_stop", "fvy_sync",
            "fvy_detect_async", "fvy_host_alloc", "fvy_host_free", "fvy_adam_step", "fvy_letterbox_u8", "fvy_staged_images", "fvy_read_staged",
            "fvy_bbox_iou_fp", "fvy_nms_fp", "fvy_netout_sigmoid", "fvy_timer_breakdown", "fvy_map_match",
-           "fvy_bn_leaky_train_forward", "fvy_bn_leaky_train_backward", "fvy_conv_create", "fvy_conv_set_weights", "fvy_conv_run"]
+           "fvy_bn_leaky_train_forward", "fvy_bn_leaky_train_backward", "fvy_conv_create", "fvy_conv_set_weights", "fvy_conv_run",
+           "fvy_conv_wgrad_scratch_rows", "fvy_conv_wgrad"]
 
 _lib = None
 
@@ -112,6 +113,10 @@ def load():
     L.fvy_conv_set_weights.argtypes = [vp, vp, C.c_int, vp]
     L.fvy_conv_run.restype = C.c_int
     L.fvy_conv_run.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.fvy_conv_wgrad_scratch_rows.restype = C.c_longlong
+    L.fvy_conv_wgrad_scratch_rows.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.fvy_conv_wgrad.restype = C.c_int
+    L.fvy_conv_wgrad.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.fvy_bn_leaky_train_backward.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp]
     L.fvy_adam_step.restype = C.c_int
     L.fvy_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]

@@ -79,7 +79,67 @@ def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return h.run(dy)
 
 
+def conv_forward(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``F.conv2d(x, weight, stride=1, padding=k // 2)`` on the tcgen05 kernel (bf16 operands, fp32 accumulation and output)."""
+    co, ci, k, _ = weight.shape
+    b, _, height, width = x.shape
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    key = ("fwd", dev, height, width, ci, co, k)
+    h = _cache.get(key)
+    if h is None or h.max_batch < b:
+        if h is not None:
+            h.close()
+        h = _cache[key] = TcConv(dev, height, width, ci, co, k, max(b, h.max_batch if h else 0))
+    h.set_weights(weight.detach().contiguous(), dgrad=False)
+    return h.run(x)
+
+
+def forward_eligible(weight: torch.Tensor, stride: int, padding: int) -> bool:
+    co, ci, kh, kw = weight.shape
+    return (weight.is_cuda and weight.dtype == torch.float32 and stride == 1 and kh == kw and kh in (1, 3) and padding == kh // 2
+            and ci % 32 == 0 and co <= 1024 and co % 4 == 0)
+
+
+_scratch: Dict[Tuple, Tuple[int, torch.Tensor]] = {}
+
+
+def _scratch_for(dev: int, height: int, width: int, channels: int, batch: int, which: str) -> torch.Tensor:
+    """Zeroed-once bf16 operand buffer of ``fvy_conv_wgrad`` for one (map, channels) shape; grown (and re-zeroed) for a larger batch."""
+    key = (dev, height, width, channels, which)
+    have = _scratch.get(key)
+    if have is None or have[0] < batch:
+        rows = L.load().fvy_conv_wgrad_scratch_rows(batch, height, width)
+        have = _scratch[key] = (batch, torch.zeros(rows * channels, dtype=torch.bfloat16, device=f"cuda:{dev}"))
+    return have[1]
+
+
+def wgrad_eligible(weight: torch.Tensor, stride: int, padding: int) -> bool:
+    co, ci, kh, kw = weight.shape
+    return (weight.is_cuda and weight.dtype == torch.float32 and stride == 1 and kh == kw and kh in (1, 3) and padding == kh // 2
+            and ci % 64 == 0 and co % 64 == 0)
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int) -> torch.Tensor:
+    """Gradient w.r.t. the weight (Co, Ci, k, k) of ``F.conv2d(x, weight, stride=1, padding=k // 2)`` given x (B, Ci, H, W) and
+    dy (B, Co, H, W), both float32 (rounded once to bf16; fp32 accumulation)."""
+    lib = L.load()
+    b, ci, height, width = x.shape
+    co = dy.shape[1]
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    x = x.contiguous(memory_format=torch.channels_last)
+    dy = dy.contiguous(memory_format=torch.channels_last)
+    xs = _scratch_for(dev, height, width, ci, b, "x")
+    ys = _scratch_for(dev, height, width, co, b, "dy")
+    dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=x.device)
+    work = torch.empty_like(dw) if k > 1 else None
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    P = lambda t: C.c_void_p(t.data_ptr())
+    L.check(lib.fvy_conv_wgrad(P(x), P(dy), b, height, width, ci, co, k, P(xs), P(ys), P(dw), P(work) if work is not None else None, C.c_void_p(st)))
+    return dw
+
+
 def clear_cache() -> None:
     for h in _cache.values():
         h.close()
     _cache.clear()
+    _scratch.clear()

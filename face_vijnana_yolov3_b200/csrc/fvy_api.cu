@@ -887,6 +887,80 @@ int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, voi
     return e;
 }
 
+// ------------------------------------------------------------------------------------------ weight gradient (row f-1: wgrad)
+static void wgrad_geometry(int batch, int H, int W, int* pitch, long long* plane, int* lead, long long* rows_k, long long* rows_total) {
+    *pitch = W + 1; *plane = (long long)(H + 1) * (W + 1);
+    *lead = (*pitch + 1 + 7) & ~7;
+    *rows_k = ((long long)batch * *plane + kWtKC - 1) / kWtKC * kWtKC;        // a multiple of both kernels' K chunk (64 and 32 pixels)
+    *rows_total = *lead + *rows_k + *pitch + 2 + 8;
+}
+long long fvy_conv_wgrad_scratch_rows(int batch, int height, int width) {
+    int pitch, lead; long long plane, rows_k, total;
+    wgrad_geometry(batch, height, width, &pitch, &plane, &lead, &rows_k, &total);
+    return total;
+}
+int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int height, int width, int cin, int cout, int ksize,
+                   void* x_scratch, void* dy_scratch, float* dw_dev, float* dw_work, void* cuda_stream) {
+    if (!x_dev || !dy_dev || !x_scratch || !dy_scratch || !dw_dev) return fail(FVY_E_INVALID, "fvy_conv_wgrad: NULL argument");
+    if (ksize != 1 && ksize != 3) return fail(FVY_E_INVALID, "fvy_conv_wgrad: kernel size %d (1 or 3)", ksize);
+    if (cin < 64 || cin % 64 || cout < 64 || cout % 64) return fail(FVY_E_INVALID, "fvy_conv_wgrad: Cin %d / Cout %d must be multiples of 64", cin, cout);
+    if (batch < 1 || height < 1 || width < 1) return fail(FVY_E_INVALID, "fvy_conv_wgrad: batch %d, map %dx%d", batch, height, width);
+    int pitch, lead; long long plane, rows_k, total;
+    wgrad_geometry(batch, height, width, &pitch, &plane, &lead, &rows_k, &total);
+    if (rows_k + pitch + 2 >= (1ll << 31)) return fail(FVY_E_INVALID, "fvy_conv_wgrad: %lld rows overflow int32", rows_k);
+    const cudaStream_t st = (cudaStream_t)cuda_stream;
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    __nv_bfloat16* xs = (__nv_bfloat16*)x_scratch + (size_t)lead * cin;
+    __nv_bfloat16* ys = (__nv_bfloat16*)dy_scratch + (size_t)lead * cout;
+    // rows behind the packed images (the round-up of the K range and the reach of the taps) may hold pixels of an earlier, larger batch
+    const long long tail0 = (long long)batch * plane, tail_rows = rows_k - tail0 + pitch + 2;
+    CUDA_TRY(cudaMemsetAsync(xs + tail0 * cin, 0, (size_t)tail_rows * cin * 2, st));
+    CUDA_TRY(cudaMemsetAsync(ys + tail0 * cout, 0, (size_t)tail_rows * cout * 2, st));
+    CUDA_TRY(cudaMemsetAsync(dw_dev, 0, (size_t)cout * cin * ksize * ksize * 4, st));
+    const long long gx = (long long)batch * height * width * (cin / 8), gy = (long long)batch * height * width * (cout / 8);
+    pack_padded_kernel<<<(unsigned)std::min<long long>((gx + 255) / 256, (long long)num_sms * 32), 256, 0, st>>>(x_dev, batch, height, width, cin, pitch, (int)plane, xs);
+    pack_padded_kernel<<<(unsigned)std::min<long long>((gy + 255) / 256, (long long)num_sms * 32), 256, 0, st>>>(dy_dev, batch, height, width, cout, pitch, (int)plane, ys);
+    static const int tc_env = [] { const char* v = getenv("FVY_WGRAD_TC"); return v && *v ? atoi(v) : 1; }();
+    if (tc_env && cout % 128 == 0) {
+        // tcgen05 path: both operands as they are (MN-major descriptors), 128 output channels x up to 256 input channels per item
+        CUtensorMap map_dy, map_x;
+        if (int e = make_tmap_2d(&map_dy, (const __nv_bfloat16*)dy_scratch, (uint64_t)cout, (uint64_t)total, (uint64_t)cout, 64, 64)) return e;
+        if (int e = make_tmap_2d(&map_x, (const __nv_bfloat16*)x_scratch, (uint64_t)cin, (uint64_t)total, (uint64_t)cin, 64, 64)) return e;
+        WgradTcParams p;
+        p.cin = cin; p.cout = cout; p.taps = ksize * ksize; p.pitch = pitch; p.lead = lead; p.chunks = (int)(rows_k / kWtKC);
+        p.n_tile = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
+        const int base_items = (cout / 128) * (cin / p.n_tile) * p.taps;
+        // one round of items: an item's epilogue (its reds) only overlaps the MMAs of a following item, and every extra pixel range is
+        // one more red per output element
+        p.ksplit = std::max(1, std::min(std::max(1, p.chunks / 4), num_sms / base_items));
+        const bool permute = p.taps > 1;
+        if (permute && !dw_work) return fail(FVY_E_INVALID, "fvy_conv_wgrad: dw_work is required for a 3 x 3 filter");
+        p.dw = permute ? dw_work : dw_dev;
+        if (permute) CUDA_TRY(cudaMemsetAsync(dw_work, 0, (size_t)cout * cin * p.taps * 4, st));
+        const int items = base_items * p.ksplit;
+        const int smem = wt_smem_bytes(p.n_tile);
+        static bool attr_tc = false;
+        if (!attr_tc) { CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wt_smem_bytes(256))); attr_tc = true; }
+        wgrad_tc_kernel<<<std::min(items, num_sms), kWtThreads, smem, st>>>(map_dy, map_x, p);
+        if (permute) wgrad_permute_kernel<<<num_sms * 4, 256, 0, st>>>(dw_work, cout, cin, p.taps, dw_dev);
+        CUDA_TRY(cudaGetLastError());
+        return FVY_OK;
+    }
+    const int chunks = (int)(rows_k / kWgKC);
+    dim3 grid(cout / 64, cin / 64, 1);
+    grid.z = (unsigned)std::max(1, std::min(chunks, (2 * num_sms + (int)(grid.x * grid.y) - 1) / (int)(grid.x * grid.y)));
+    if (ksize == 3) {
+        static bool attr = false;
+        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<9>::kBytes)); attr = true; }
+        conv_wgrad_kernel<9><<<grid, kWgThreads, WgSmem<9>::kBytes, st>>>(xs, ys, (int)rows_k, pitch, cin, cout, dw_dev);
+    } else {
+        conv_wgrad_kernel<1><<<grid, kWgThreads, WgSmem<1>::kBytes, st>>>(xs, ys, (int)rows_k, pitch, cin, cout, dw_dev);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FVY_OK;
+}
+
 void* fvy_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }

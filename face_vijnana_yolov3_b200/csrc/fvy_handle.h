@@ -25,6 +25,8 @@
 #include "stem_conv1_fused.cuh"
 #include "prepost_kernels.cuh"
 #include "train_kernels.cuh"
+#include "wgrad_kernel.cuh"
+#include "wgrad_tc_sm100.cuh"
 
 namespace fvy {
 

@@ -171,19 +171,31 @@ class _BnLeakyFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None
 
 
+def _bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
 def _tc_eligible(conv: nn.Conv2d) -> bool:
     from . import conv_tc
     return conv_tc.eligible(conv.weight, conv.stride[0], conv.padding[0])
 
 
 class _ConvFn(torch.autograd.Function):
-    """A stride-1 Conv2d whose gradient w.r.t. the INPUT runs on this repo's tcgen05 implicit-GEMM kernel (``conv_tc.conv_dgrad``:
-    bf16 operands, fp32 accumulation); the forward and the weight gradient stay on cuDNN in fp32."""
+    """A stride-1 Conv2d on this repo's kernels, bf16 operands with fp32 accumulation (``conv_tc``).  ``mode`` bits: 1 = the gradient
+    w.r.t. the INPUT on the tcgen05 implicit-GEMM kernel (``conv_dgrad``), 2 = the gradient w.r.t. the WEIGHT on ``conv_wgrad_kernel``
+    (warp-level tensor-core MMAs), 4 = the forward on the tcgen05 kernel as well.  Whatever a bit leaves out runs on cuDNN in fp32.
+    Bit 8 (tests): the same arithmetic emulated with torch - fp32 library convolutions on operands rounded to bf16 - in place of the
+    kernels, so that a whole step on the kernels can be checked against a reference that differs only in summation order."""
 
     @staticmethod
-    def forward(ctx, x, weight, padding):
+    def forward(ctx, x, weight, padding, mode):
+        from . import conv_tc
         ctx.save_for_backward(x, weight)
-        ctx.padding = padding
+        ctx.padding, ctx.mode = padding, mode
+        if (mode & 4) and conv_tc.forward_eligible(weight, 1, padding):
+            if mode & 8:
+                return F.conv2d(_bf16_round(x), _bf16_round(weight), None, 1, padding)
+            return conv_tc.conv_forward(x, weight)
         return F.conv2d(x, weight, None, 1, padding)
 
     @staticmethod
@@ -191,11 +203,20 @@ class _ConvFn(torch.autograd.Function):
         from . import conv_tc
         x, weight = ctx.saved_tensors
         dx = dw = None
+        emu = bool(ctx.mode & 8)
         if ctx.needs_input_grad[0]:
-            dx = conv_tc.conv_dgrad(dy, weight)
+            if (ctx.mode & 1) and conv_tc.eligible(weight, 1, ctx.padding):
+                dx = (torch.nn.grad.conv2d_input(x.shape, _bf16_round(weight), _bf16_round(dy), 1, ctx.padding) if emu
+                      else conv_tc.conv_dgrad(dy, weight))
+            else:
+                dx = torch.nn.grad.conv2d_input(x.shape, weight, dy, 1, ctx.padding)
         if ctx.needs_input_grad[1]:
-            dw = torch.nn.grad.conv2d_weight(x, weight.shape, dy, 1, ctx.padding)
-        return dx, dw, None
+            if (ctx.mode & 2) and conv_tc.wgrad_eligible(weight, 1, ctx.padding):
+                dw = (torch.nn.grad.conv2d_weight(_bf16_round(x), weight.shape, _bf16_round(dy), 1, ctx.padding) if emu
+                      else conv_tc.conv_wgrad(x, dy, weight.shape[2]))
+            else:
+                dw = torch.nn.grad.conv2d_weight(x, weight.shape, dy, 1, ctx.padding)
+        return dx, dw, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -213,6 +234,7 @@ class FdNet(nn.Module):
         self.specs = arch.fd6_table(bb_info_c_size)
         self.fvy_bn = False        # True: BatchNorm (training) + LeakyReLU through this repo's kernels (fp32 CUDA tensors only)
         self.fvy_dgrad = False     # True: input gradients of the stride-1 convolutions on the tcgen05 kernel (bf16 operands)
+        self.fvy_conv_mode = 0     # _ConvFn mode bits (1 dgrad, 2 wgrad, 4 forward on this repo's kernels); fvy_dgrad = True is mode 1
         self.convs = nn.ModuleDict()
         self.bns = nn.ModuleDict()
         for c in self.specs:
@@ -227,9 +249,10 @@ class FdNet(nn.Module):
         for c in self.specs:
             conv = self.convs[str(c.idx)]
             xin = outs[c.src]
-            if (self.fvy_dgrad and self.training and conv.bias is None and xin.requires_grad and xin.dtype == torch.float32 and
-                    _tc_eligible(conv)):
-                y = _ConvFn.apply(xin, conv.weight, conv.padding[0])
+            mode = self.fvy_conv_mode | (1 if self.fvy_dgrad else 0)
+            if (mode and self.training and conv.bias is None and conv.stride[0] == 1 and xin.is_cuda and xin.dtype == torch.float32 and
+                    c.src != -1):
+                y = _ConvFn.apply(xin, conv.weight, conv.padding[0], mode)
             else:
                 y = conv(xin)
             if c.bn and self.fvy_bn and self.training and y.is_cuda and y.dtype == torch.float32:
@@ -338,7 +361,7 @@ class DataParallelTrainer:
 
     def __init__(self, hps: dict, device: str = "cpu", bb_info_c_size: int = 6, bucket_mb: float = 32.0, autocast_bf16: bool = False,
                  stream: Optional[np.ndarray] = None, model: Optional[nn.Module] = None, fvy_bn: Optional[bool] = None,
-                 fvy_dgrad: bool = False):
+                 fvy_dgrad: bool = False, fvy_conv_mode: int = 0):
         self.device = torch.device(device)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
@@ -356,6 +379,7 @@ class DataParallelTrainer:
         # input gradients of the stride-1 convolutions on the tcgen05 kernel (bf16 operands: opt-in, the reference trains in fp32)
         if hasattr(self.model, "fvy_dgrad"):
             self.model.fvy_dgrad = bool(fvy_dgrad) and self.device.type == "cuda" and not self.autocast_bf16
+            self.model.fvy_conv_mode = int(fvy_conv_mode) if (self.device.type == "cuda" and not self.autocast_bf16) else 0
         # flat buckets in REVERSE parameter order (= the order autograd finishes gradients in)
         params = [p for p in self.model.parameters() if p.requires_grad]
         limit = int(bucket_mb * (1 << 20) / 4)

@@ -248,6 +248,19 @@ int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows,
 int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int max_batch, fvy_handle** out);
 int fvy_conv_set_weights(fvy_handle* h, const float* w_dev, int dgrad, void* cuda_stream);
 int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, void* cuda_stream);
+/* Training step, row f-1 (third slice): the gradient of a stride-1, zero-padded k x k convolution (k = 1 or 3) with respect to its
+ * WEIGHTS - the other half of what cuDNN does for the reference's Conv2D layers when it trains (same lines as above):
+ *   dW[co][ci][r][s] = sum over batch, y, x of dY[n][y][x][co] * X[n][y + r - k/2][x + s - k/2][ci]      (zero outside the map)
+ * x [batch][height][width][cin] and dy [batch][height][width][cout] are float32 NHWC tensors in DEVICE memory (rounded once to
+ * bf16; fp32 accumulation), dw [cout][cin][k][k] float32 (the torch / Keras-transposed layout) is overwritten.  cin and cout must be
+ * multiples of 64.  x_scratch / dy_scratch: DEVICE buffers of fvy_conv_wgrad_scratch_rows(max batch, height, width) * cin (resp.
+ * cout) * 2 bytes that the caller ZEROES ONCE and then only hands to this function for that (height, width, channels) - they hold
+ * the bf16 operands in the shared-halo pixel-major form, whose halo pixels and margins stay zero.  dw_work: DEVICE scratch of the size
+ * of dw (the tcgen05 kernel accumulates per tap, [k*k][cout][cin]; may be NULL for k = 1).  Enqueued on `cuda_stream`.
+ * cout a multiple of 128: wgrad_tc_kernel (tcgen05.mma with MN-major operand descriptors); otherwise conv_wgrad_kernel (mma.sync). */
+long long fvy_conv_wgrad_scratch_rows(int batch, int height, int width);
+int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int height, int width, int cin, int cout, int ksize,
+                   void* x_scratch, void* dy_scratch, float* dw_dev, float* dw_work, void* cuda_stream);
 /* Pre-processing of FaceDetector.evaluate / FaceDetector.test (src/space/face_detection.py:657-690 and :798-835):
  *   image = imread(file) / 255;  image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC);
  *   image = cv.copyMakeBorder(image, pad_t, pad_b, pad_l, pad_r, cv.BORDER_CONSTANT, value=[0, 0, 0])

@@ -1,7 +1,8 @@
 #!/bin/bash
+timeout 900 python -m pytest tests/test_gpu_round2.py -q -m gpu -k "fvy_conv_kernels" -p no:cacheprovider -s > gpurun_out/r2s_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|^E  |passed|failed|timed out|fvy:|worst" gpurun_out/r2s_pytest.log | head -20
 timeout 900 python bench.py --config train > gpurun_out/r2s_train.json 2> gpurun_out/r2s_train.err || tail -5 gpurun_out/r2s_train.err
 python - <<'PY'
 import json
 d = json.load(open("gpurun_out/r2s_train.json"))
-print("train N=1: %.2f ms/step | all-cuDNN %.2f | bf16 autocast %.2f | tc dgrad %.2f (%d layers, loss %.6f vs %.6f)" % (d["ms_per_step"], d["baseline_all_cudnn"]["ms_per_step"], d["bf16_autocast"]["ms_per_step"], d["tc_dgrad"]["ms_per_step"], d["tc_dgrad"]["layers"], d["tc_dgrad"]["loss"], d["loss"]))
+print("train N=1: %.2f ms/step | all-cuDNN %.2f | bf16 autocast %.2f | tc dgrad %.2f | fvy backward %.2f | fvy all %.2f" % (d["ms_per_step"], d["baseline_all_cudnn"]["ms_per_step"], d["bf16_autocast"]["ms_per_step"], d["tc_dgrad"]["ms_per_step"], d["fvy_conv_backward"]["ms_per_step"], d["fvy_conv_all"]["ms_per_step"]))
 PY
