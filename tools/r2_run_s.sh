@@ -1,5 +1,4 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_round2.py -q -m gpu -k "fvy_conv_kernels" -p no:cacheprovider -s > gpurun_out/r2s_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|^E  |passed|failed|timed out|fvy:|worst" gpurun_out/r2s_pytest.log | head -20
 timeout 900 python bench.py --config train > gpurun_out/r2s_train.json 2> gpurun_out/r2s_train.err || tail -5 gpurun_out/r2s_train.err
 python - <<'PY'
 import json
