@@ -108,7 +108,7 @@ def load():
     L.fvy_bn_leaky_train_forward.argtypes = [vp, C.c_longlong, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]
     L.fvy_bn_leaky_train_backward.restype = C.c_int
     L.fvy_conv_create.restype = C.c_int
-    L.fvy_conv_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.fvy_conv_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.fvy_conv_set_weights.restype = C.c_int
     L.fvy_conv_set_weights.argtypes = [vp, vp, C.c_int, vp]
     L.fvy_conv_run.restype = C.c_int
@@ -116,7 +116,7 @@ def load():
     L.fvy_conv_wgrad_scratch_rows.restype = C.c_longlong
     L.fvy_conv_wgrad_scratch_rows.argtypes = [C.c_int, C.c_int, C.c_int]
     L.fvy_conv_wgrad.restype = C.c_int
-    L.fvy_conv_wgrad.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.fvy_conv_wgrad.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.fvy_bn_leaky_train_backward.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp]
     L.fvy_adam_step.restype = C.c_int
     L.fvy_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]

@@ -42,7 +42,7 @@ void fvy_destroy(fvy_handle* h) {
 }
 
 // Shared tail of fvy_create / fvy_conv_create: device checks, streams and events, plan, scratch.  conv_k > 0 = single-convolution handle.
-static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int conv_k, fvy_handle** out);
+static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int conv_k, fvy_handle** out, int conv_stride = 1);
 
 int fvy_create(const fvy_config* cfg, fvy_handle** out) {
     if (!cfg || !out) return fail(FVY_E_INVALID, "NULL argument");
@@ -57,7 +57,7 @@ int fvy_create(const fvy_config* cfg, fvy_handle** out) {
     return create_impl(cfg, 0, 0, 0, out);
 }
 
-static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int conv_k, fvy_handle** out) {
+static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int conv_k, fvy_handle** out, int conv_stride) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(FVY_E_CUDA, "no CUDA device (there is no CPU fallback)"); }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(FVY_E_INVALID, "device %d of %d", cfg->device, ndev);
@@ -68,7 +68,7 @@ static int create_impl(const fvy_config* cfg, int conv_cin, int conv_cout, int c
     fvy_handle* h = new fvy_handle();
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
-    h->conv_mode = conv_k > 0; h->conv_cin = conv_cin; h->conv_cout = conv_cout; h->conv_k = conv_k;
+    h->conv_mode = conv_k > 0; h->conv_cin = conv_cin; h->conv_cout = conv_cout; h->conv_k = conv_k; h->conv_stride = conv_stride;
     int e = FVY_OK;
     do {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { e = fail(FVY_E_CUDA, "cudaStreamCreate failed"); break; }
@@ -838,11 +838,13 @@ int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows,
 }
 
 // ------------------------------------------------------------------------------------------ single convolution (row f-1: dgrad)
-int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int max_batch, fvy_handle** out) {
+int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int stride, int max_batch, fvy_handle** out) {
     if (!out) return fail(FVY_E_INVALID, "NULL argument");
     *out = nullptr;
     if (height < 1 || width < 1 || height > 4096 || width > 4096) return fail(FVY_E_INVALID, "feature map %dx%d", height, width);
     if (ksize != 1 && ksize != 3) return fail(FVY_E_INVALID, "kernel size %d (1 or 3)", ksize);
+    if (stride != 1 && !(stride == 2 && ksize == 3 && height % 2 == 0 && width % 2 == 0 && cin % 64 == 0))
+        return fail(FVY_E_INVALID, "stride %d (1, or 2 for a 3 x 3 filter over an even-sized map with Cin a multiple of 64)", stride);
     if (cin < 32 || cin % 32 || cin > 2048) return fail(FVY_E_INVALID, "Cin %d must be a multiple of 32 in [32, 2048]", cin);
     if (cout < 1 || cout > kMaxCout) return fail(FVY_E_INVALID, "Cout %d outside [1, %d]", cout, kMaxCout);
     if (max_batch < 1 || max_batch > 1024) return fail(FVY_E_INVALID, "max_batch %d outside [1, 1024]", max_batch);
@@ -850,18 +852,19 @@ int fvy_conv_create(int device, int height, int width, int cin, int cout, int ks
     memset(&cfg, 0, sizeof(cfg));
     cfg.device = device; cfg.net_h = height; cfg.net_w = width; cfg.head = FVY_HEAD_YOLO3; cfg.nb_class = 1; cfg.bb_info_c_size = 6;
     cfg.max_batch = max_batch; cfg.flags = FVY_CFG_NO_GRAPH | FVY_CFG_NO_CHAIN | FVY_CFG_NO_TILE_FLAGS;
-    return create_impl(&cfg, cin, cout, ksize, out);
+    return create_impl(&cfg, cin, cout, ksize, out, stride);
 }
 
 int fvy_conv_set_weights(fvy_handle* h, const float* w_dev, int dgrad, void* stream) {
     if (!h || !w_dev) return fail(FVY_E_INVALID, "NULL argument");
     if (!h->conv_mode) return fail(FVY_E_STATE, "not a single-convolution handle");
+    if (dgrad && h->conv_stride != 1) return fail(FVY_E_INVALID, "dgrad weights on a stride-2 handle");
     if (!is_device_ptr(w_dev)) return fail(FVY_E_INVALID, "fvy_conv_set_weights takes a device pointer");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     Layer& L = h->layers[0];
     const long long total = (long long)L.cout_pad * L.taps * L.cin_pad;
     conv_weight_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(
-        w_dev, h->conv_cin, h->conv_cout, L.cout_pad, L.taps, dgrad != 0, L.w);
+        w_dev, h->conv_cin, h->conv_cout, L.cout_pad, L.taps, dgrad != 0, L.tap_perm, L.w);
     CUDA_TRY(cudaGetLastError());
     h->weights_loaded = true;
     return FVY_OK;
@@ -877,8 +880,12 @@ int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, voi
     Layer& L = h->layers[0];
     const cudaStream_t st = (cudaStream_t)stream, saved = h->stream;
     const long long groups = (long long)batch * L.Hin * L.Win * (h->conv_cin / 8);
-    pack_padded_kernel<<<(unsigned)std::min<long long>((groups + 255) / 256, (long long)h->num_sms * 32), 256, 0, st>>>(
-        x_dev, batch, L.Hin, L.Win, h->conv_cin, L.p.dom_w, L.p.dom_plane, h->d_conv_in);
+    if (h->conv_stride == 2)
+        pack_phase_kernel<<<(unsigned)std::min<long long>((groups + 255) / 256, (long long)h->num_sms * 32), 256, 0, st>>>(
+            x_dev, batch, L.Hin, L.Win, h->conv_cin, L.p.dom_w, L.p.dom_plane, (long long)h->cfg.max_batch * L.p.dom_plane, h->d_conv_in);
+    else
+        pack_padded_kernel<<<(unsigned)std::min<long long>((groups + 255) / 256, (long long)h->num_sms * 32), 256, 0, st>>>(
+            x_dev, batch, L.Hin, L.Win, h->conv_cin, L.p.dom_w, L.p.dom_plane, h->d_conv_in);
     CUDA_TRY(cudaGetLastError());
     h->conv_out = y_dev;
     h->stream = st;                       // the layer is enqueued on the caller's stream, behind the pack kernel
@@ -899,12 +906,13 @@ long long fvy_conv_wgrad_scratch_rows(int batch, int height, int width) {
     wgrad_geometry(batch, height, width, &pitch, &plane, &lead, &rows_k, &total);
     return total;
 }
-int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int height, int width, int cin, int cout, int ksize,
+int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int height, int width, int cin, int cout, int ksize, int stride,
                    void* x_scratch, void* dy_scratch, float* dw_dev, float* dw_work, void* cuda_stream) {
     if (!x_dev || !dy_dev || !x_scratch || !dy_scratch || !dw_dev) return fail(FVY_E_INVALID, "fvy_conv_wgrad: NULL argument");
     if (ksize != 1 && ksize != 3) return fail(FVY_E_INVALID, "fvy_conv_wgrad: kernel size %d (1 or 3)", ksize);
     if (cin < 64 || cin % 64 || cout < 64 || cout % 64) return fail(FVY_E_INVALID, "fvy_conv_wgrad: Cin %d / Cout %d must be multiples of 64", cin, cout);
     if (batch < 1 || height < 1 || width < 1) return fail(FVY_E_INVALID, "fvy_conv_wgrad: batch %d, map %dx%d", batch, height, width);
+    if (stride != 1 && !(stride == 2 && ksize == 3 && cout % 128 == 0)) return fail(FVY_E_INVALID, "fvy_conv_wgrad: stride %d (2 needs a 3 x 3 filter and Cout a multiple of 128)", stride);
     int pitch, lead; long long plane, rows_k, total;
     wgrad_geometry(batch, height, width, &pitch, &plane, &lead, &rows_k, &total);
     if (rows_k + pitch + 2 >= (1ll << 31)) return fail(FVY_E_INVALID, "fvy_conv_wgrad: %lld rows overflow int32", rows_k);
@@ -918,17 +926,32 @@ int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int heigh
     CUDA_TRY(cudaMemsetAsync(xs + tail0 * cin, 0, (size_t)tail_rows * cin * 2, st));
     CUDA_TRY(cudaMemsetAsync(ys + tail0 * cout, 0, (size_t)tail_rows * cout * 2, st));
     CUDA_TRY(cudaMemsetAsync(dw_dev, 0, (size_t)cout * cin * ksize * ksize * 4, st));
-    const long long gx = (long long)batch * height * width * (cin / 8), gy = (long long)batch * height * width * (cout / 8);
-    pack_padded_kernel<<<(unsigned)std::min<long long>((gx + 255) / 256, (long long)num_sms * 32), 256, 0, st>>>(x_dev, batch, height, width, cin, pitch, (int)plane, xs);
+    // height / width are the OUTPUT's (= dY's) map; a stride-2 layer's input is twice that and is packed as four phase planes, `total` rows apart
+    const int s2 = stride == 2 ? 2 : 1;
+    const long long gx = (long long)batch * height * s2 * width * s2 * (cin / 8), gy = (long long)batch * height * width * (cout / 8);
+    if (stride == 2)
+        pack_phase_kernel<<<(unsigned)std::min<long long>((gx + 255) / 256, (long long)num_sms * 32), 256, 0, st>>>(x_dev, batch, 2 * height, 2 * width, cin, pitch, (int)plane, total, xs);
+    else
+        pack_padded_kernel<<<(unsigned)std::min<long long>((gx + 255) / 256, (long long)num_sms * 32), 256, 0, st>>>(x_dev, batch, height, width, cin, pitch, (int)plane, xs);
     pack_padded_kernel<<<(unsigned)std::min<long long>((gy + 255) / 256, (long long)num_sms * 32), 256, 0, st>>>(dy_dev, batch, height, width, cout, pitch, (int)plane, ys);
     static const int tc_env = [] { const char* v = getenv("FVY_WGRAD_TC"); return v && *v ? atoi(v) : 1; }();
     if (tc_env && cout % 128 == 0) {
         // tcgen05 path: both operands as they are (MN-major descriptors), 128 output channels x up to 256 input channels per item
         CUtensorMap map_dy, map_x;
         if (int e = make_tmap_2d(&map_dy, (const __nv_bfloat16*)dy_scratch, (uint64_t)cout, (uint64_t)total, (uint64_t)cout, 64, 64)) return e;
-        if (int e = make_tmap_2d(&map_x, (const __nv_bfloat16*)x_scratch, (uint64_t)cin, (uint64_t)total, (uint64_t)cin, 64, 64)) return e;
+        if (int e = make_tmap_2d(&map_x, (const __nv_bfloat16*)x_scratch, (uint64_t)cin, (uint64_t)total * (stride == 2 ? 4 : 1), (uint64_t)cin, 64, 64)) return e;
         WgradTcParams p;
-        p.cin = cin; p.cout = cout; p.taps = ksize * ksize; p.pitch = pitch; p.lead = lead; p.chunks = (int)(rows_k / kWtKC);
+        p.cin = cin; p.cout = cout; p.taps = ksize * ksize; p.lead = lead; p.chunks = (int)(rows_k / kWtKC);
+        for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, q = t % 3;
+            if (ksize == 1) p.tap_row[t] = 0;
+            else if (stride == 1) p.tap_row[t] = (r - 1) * pitch + (q - 1);
+            else {      // phase (r & 1, q & 1), position shifted by (r >> 1, q >> 1) - 1
+                const long long v = (long long)(((r & 1) << 1) | (q & 1)) * total + ((r >> 1) - 1) * pitch + ((q >> 1) - 1);
+                if (v >= (1ll << 31)) return fail(FVY_E_INVALID, "fvy_conv_wgrad: phase offset overflows int32");
+                p.tap_row[t] = (int)v;
+            }
+        }
         p.n_tile = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
         const int base_items = (cout / 128) * (cin / p.n_tile) * p.taps;
         // one round of items: an item's epilogue (its reds) only overlaps the MMAs of a following item, and every extra pixel range is
@@ -947,6 +970,7 @@ int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int heigh
         CUDA_TRY(cudaGetLastError());
         return FVY_OK;
     }
+    if (stride == 2) return fail(FVY_E_INVALID, "fvy_conv_wgrad: stride 2 runs on the tcgen05 kernel only (FVY_WGRAD_TC=0 is set)");
     const int chunks = (int)(rows_k / kWgKC);
     dim3 grid(cout / 64, cin / 64, 1);
     grid.z = (unsigned)std::max(1, std::min(chunks, (2 * num_sms + (int)(grid.x * grid.y) - 1) / (int)(grid.x * grid.y)));

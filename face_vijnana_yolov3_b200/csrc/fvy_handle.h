@@ -170,7 +170,7 @@ struct fvy_handle {
     bool fuse_stem = false; bool stem_phase_valid = false;
     CUtensorMap tmap_w1f; FuseParams fuse;
     // single-convolution handle (fvy_conv_create): one stride-1 layer, input packed from the caller's NHWC fp32 tensor, fp32 output
-    bool conv_mode = false; int conv_cin = 0, conv_cout = 0, conv_k = 0;
+    bool conv_mode = false; int conv_cin = 0, conv_cout = 0, conv_k = 0, conv_stride = 1;
     __nv_bfloat16* d_conv_in = nullptr; float* conv_out = nullptr;
     long long launches = 0;
     long long weight_count = 0;

@@ -67,10 +67,10 @@ inline std::vector<ConvSpec> fd6_table(int bb_info_c_size) {
     return v;
 }
 
-// One stride-1 convolution on its own (fvy_conv_create): no BatchNorm, no bias, no activation, input handed in by the caller
+// One convolution on its own (fvy_conv_create; stride 2: 3 x 3 reading the 4-phase form, the handle's map size is the INPUT's): no BatchNorm, no bias, no activation, input handed in by the caller
 // (src = -4), dense fp32 output.
-inline std::vector<ConvSpec> single_conv_table(int cin, int cout, int k) {
-    return {ConvSpec{0, cin, cout, k, 1, false, false, -4, -1, 0}};
+inline std::vector<ConvSpec> single_conv_table(int cin, int cout, int k, int stride) {
+    return {ConvSpec{0, cin, cout, k, stride, false, false, -4, -1, stride == 2 ? 1 : 0}};
 }
 
 }  // namespace fvy

@@ -78,7 +78,7 @@ struct TensorBufs { __nv_bfloat16* padded = nullptr; __nv_bfloat16* phase = null
 
 static int build_plan(fvy_handle* h) {
     const fvy_config& c = h->cfg;
-    std::vector<ConvSpec> specs = h->conv_mode ? single_conv_table(h->conv_cin, h->conv_cout, h->conv_k)
+    std::vector<ConvSpec> specs = h->conv_mode ? single_conv_table(h->conv_cin, h->conv_cout, h->conv_k, h->conv_stride)
                                                : (c.head == FVY_HEAD_YOLO3 ? yolo3_table(c.nb_class) : fd6_table(c.bb_info_c_size));
     const int nmax = c.max_batch;
     // which stored forms does each producer need?
@@ -122,7 +122,7 @@ static int build_plan(fvy_handle* h) {
     }
     if (int e = dev_alloc(h, (void**)&h->d_stem_w2, 32 * 32 * 2, true)) return e;
     if (h->conv_mode)       // the caller's tensor is packed into this padded buffer (halo = the zeros it is allocated with)
-        if (int e = dev_alloc(h, (void**)&h->d_conv_in, (size_t)nmax * geom_plane(0) * h->conv_cin * 2, true)) return e;
+        if (int e = dev_alloc(h, (void**)&h->d_conv_in, (size_t)(h->conv_stride == 2 ? 4 * nmax * geom_plane(1) : nmax * geom_plane(0)) * h->conv_cin * 2, true)) return e;
     // activation buffers
     for (const ConvSpec& s : specs) {
         int H, W;
@@ -286,7 +286,7 @@ static int build_plan(fvy_handle* h) {
             // shift AND the rows of the domain are the rows of the stored output (TMA stores).
             const long long plane = geom_plane(s.level);
             const int gw = geom_w(s.level);
-            a_base = bufs[s.src].phase; a_rows = (uint64_t)(4 * nmax * plane); a_pitch = s.cin;
+            a_base = s.src == -4 ? h->d_conv_in : bufs[s.src].phase; a_rows = (uint64_t)(4 * nmax * plane); a_pitch = s.cin;
             p.dom_plane = (int)plane; p.dom_w = gw; p.dom_off = 1;
             for (int r = 0; r < 3; ++r)
                 for (int q = 0; q < 3; ++q)

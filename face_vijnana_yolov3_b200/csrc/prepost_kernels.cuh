@@ -55,16 +55,43 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(const float* __restric
         *reinterpret_cast<uint4*>(dst + ((n * dst_plane + (long long)(hh + 1) * dst_w + (w + 1)) * C + g * 8)) = o;
     }
 }
+// The same into the 4-phase form a stride-2 consumer reads: padded pixel (hp, wp) = (y + 1, x + 1) of image n goes to phase
+// (hp & 1, wp & 1), position (hp >> 1, wp >> 1) of planes with row pitch dst_w and dst_plane rows per image; the four phases are
+// phase_rows rows apart.
+__global__ void __launch_bounds__(256) pack_phase_kernel(const float* __restrict__ x, int batch, int H, int W, int C, int dst_w, int dst_plane,
+                                                         long long phase_rows, __nv_bfloat16* __restrict__ dst) {
+    const int cg = C >> 3;
+    const long long total = (long long)batch * H * W * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        long long t = i / cg;
+        const int w = (int)(t % W); t /= W;
+        const int hh = (int)(t % H);
+        const long long n = t / H;
+        const float4* src = reinterpret_cast<const float4*>(x + (((n * H + hh) * W + w) * (long long)C + g * 8));
+        const float4 a = src[0], b = src[1];
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<unsigned*>(&p0); o.y = *reinterpret_cast<unsigned*>(&p1);
+        o.z = *reinterpret_cast<unsigned*>(&p2); o.w = *reinterpret_cast<unsigned*>(&p3);
+        const int hp = hh + 1, wp = w + 1;
+        const long long row = (long long)(((hp & 1) << 1) | (wp & 1)) * phase_rows + n * dst_plane + (long long)(hp >> 1) * dst_w + (wp >> 1);
+        *reinterpret_cast<uint4*>(dst + (row * C + g * 8)) = o;
+    }
+}
 // torch Conv2d weight [Co][Ci][k][k] fp32 -> the plan's [cout_pad][taps][cin] bf16.  dgrad = 0: this convolution (the handle was created
 // with cin = Ci, cout = Co).  dgrad = 1: the convolution that maps dY to dX (handle created with cin = Co, cout = Ci): weights
 // transposed and the taps reversed (both filter axes flipped), dX = conv(dY, flip(W)^T) for a stride-1 'same' convolution.
+// tap_perm: the plan of a stride-2 layer stores the column taps of a filter row in the order 0, 2, 1.
 __global__ void __launch_bounds__(256) conv_weight_kernel(const float* __restrict__ w, int cin, int cout, int cout_pad, int taps, bool dgrad,
-                                                          __nv_bfloat16* __restrict__ dst) {
+                                                          bool tap_perm, __nv_bfloat16* __restrict__ dst) {
     const long long total = (long long)cout_pad * taps * cin;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin);
-        const int t = (int)((i / cin) % taps);
+        int t = (int)((i / cin) % taps);
         const int o = (int)(i / ((long long)cin * taps));
+        if (tap_perm) { const int q = t % 3; t = t - q + (q == 0 ? 0 : (q == 1 ? 2 : 1)); }      // stored position -> column tap
         float v = 0.f;
         if (o < cout) v = dgrad ? w[((long long)ci * cout + o) * taps + (taps - 1 - t)] : w[((long long)o * cin + ci) * taps + t];
         dst[i] = __float2bfloat16_rn(v);

@@ -20,7 +20,8 @@ __host__ __device__ constexpr int wt_stage_bytes(int n) { return (128 + n) * kWt
 __host__ __device__ constexpr int wt_smem_bytes(int n) { return 1024 + kWtStages * wt_stage_bytes(n) + 1024; }
 
 struct WgradTcParams {
-    int cin, cout, taps, pitch;      // pitch: row pitch (pixels) of the shared-halo geometry
+    int cin, cout, taps;
+    int tap_row[9];                  // row offset of tap t's X operand relative to dY's row (stride 1: (r-1) pitch + (s-1); stride 2: + its phase plane)
     int lead;                        // rows in front of pixel 0 in both buffers
     int chunks;                      // K chunks of 64 pixels
     int ksplit, n_tile;              // pixel ranges per (m, n, tap); input channels per item (64, 128 or 256)
@@ -75,7 +76,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 int mt, nt, tap, c0, c1;
                 decode(item, mt, nt, tap, c0, c1);
-                const int shift = p.taps == 9 ? (tap / 3 - 1) * p.pitch + (tap % 3 - 1) : 0;
+                const int shift = p.tap_row[tap];
                 for (int c = c0; c < c1; ++c) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = ring + (size_t)s * stage_bytes;

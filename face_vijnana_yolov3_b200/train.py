@@ -183,20 +183,21 @@ def _tc_eligible(conv: nn.Conv2d) -> bool:
 class _ConvFn(torch.autograd.Function):
     """A stride-1 Conv2d on this repo's kernels, bf16 operands with fp32 accumulation (``conv_tc``).  ``mode`` bits: 1 = the gradient
     w.r.t. the INPUT on the tcgen05 implicit-GEMM kernel (``conv_dgrad``), 2 = the gradient w.r.t. the WEIGHT on ``conv_wgrad_kernel``
-    (warp-level tensor-core MMAs), 4 = the forward on the tcgen05 kernel as well.  Whatever a bit leaves out runs on cuDNN in fp32.
+    (tcgen05 with MN-major operands; warp-level MMAs for 64-wide layers), 4 = the forward on the tcgen05 kernel as well.  The
+    backbone's stride-2 3 x 3 layers take bits 2 and 4 (their dgrad stays on cuDNN).  Whatever a bit leaves out runs on cuDNN in fp32.
     Bit 8 (tests): the same arithmetic emulated with torch - fp32 library convolutions on operands rounded to bf16 - in place of the
     kernels, so that a whole step on the kernels can be checked against a reference that differs only in summation order."""
 
     @staticmethod
-    def forward(ctx, x, weight, padding, mode):
+    def forward(ctx, x, weight, padding, mode, stride=1):
         from . import conv_tc
         ctx.save_for_backward(x, weight)
-        ctx.padding, ctx.mode = padding, mode
-        if (mode & 4) and conv_tc.forward_eligible(weight, 1, padding):
+        ctx.padding, ctx.mode, ctx.stride = padding, mode, stride
+        if (mode & 4) and conv_tc.forward_eligible(weight, stride, padding):
             if mode & 8:
-                return F.conv2d(_bf16_round(x), _bf16_round(weight), None, 1, padding)
-            return conv_tc.conv_forward(x, weight)
-        return F.conv2d(x, weight, None, 1, padding)
+                return F.conv2d(_bf16_round(x), _bf16_round(weight), None, stride, padding)
+            return conv_tc.conv_forward(x, weight, stride)
+        return F.conv2d(x, weight, None, stride, padding)
 
     @staticmethod
     def backward(ctx, dy):
@@ -204,19 +205,20 @@ class _ConvFn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         dx = dw = None
         emu = bool(ctx.mode & 8)
+        stride = ctx.stride
         if ctx.needs_input_grad[0]:
-            if (ctx.mode & 1) and conv_tc.eligible(weight, 1, ctx.padding):
+            if (ctx.mode & 1) and conv_tc.eligible(weight, stride, ctx.padding):
                 dx = (torch.nn.grad.conv2d_input(x.shape, _bf16_round(weight), _bf16_round(dy), 1, ctx.padding) if emu
                       else conv_tc.conv_dgrad(dy, weight))
             else:
-                dx = torch.nn.grad.conv2d_input(x.shape, weight, dy, 1, ctx.padding)
+                dx = torch.nn.grad.conv2d_input(x.shape, weight, dy, stride, ctx.padding)
         if ctx.needs_input_grad[1]:
-            if (ctx.mode & 2) and conv_tc.wgrad_eligible(weight, 1, ctx.padding):
-                dw = (torch.nn.grad.conv2d_weight(_bf16_round(x), weight.shape, _bf16_round(dy), 1, ctx.padding) if emu
-                      else conv_tc.conv_wgrad(x, dy, weight.shape[2]))
+            if (ctx.mode & 2) and conv_tc.wgrad_eligible(weight, stride, ctx.padding):
+                dw = (torch.nn.grad.conv2d_weight(_bf16_round(x), weight.shape, _bf16_round(dy), stride, ctx.padding) if emu
+                      else conv_tc.conv_wgrad(x, dy, weight.shape[2], stride))
             else:
-                dw = torch.nn.grad.conv2d_weight(x, weight.shape, dy, 1, ctx.padding)
-        return dx, dw, None, None
+                dw = torch.nn.grad.conv2d_weight(x, weight.shape, dy, stride, ctx.padding)
+        return dx, dw, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -250,9 +252,8 @@ class FdNet(nn.Module):
             conv = self.convs[str(c.idx)]
             xin = outs[c.src]
             mode = self.fvy_conv_mode | (1 if self.fvy_dgrad else 0)
-            if (mode and self.training and conv.bias is None and conv.stride[0] == 1 and xin.is_cuda and xin.dtype == torch.float32 and
-                    c.src != -1):
-                y = _ConvFn.apply(xin, conv.weight, conv.padding[0], mode)
+            if mode and self.training and conv.bias is None and xin.is_cuda and xin.dtype == torch.float32 and c.src != -1:
+                y = _ConvFn.apply(xin, conv.weight, conv.padding[0], mode, conv.stride[0])
             else:
                 y = conv(xin)
             if c.bn and self.fvy_bn and self.training and y.is_cuda and y.dtype == torch.float32:

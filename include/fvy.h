@@ -239,13 +239,15 @@ int fvy_bn_leaky_train_backward(const float* x, const float* dy, long long rows,
  * [batch][height][width] maps without bias or activation: bf16 operands (the caller's float32 tensors are rounded once), float32
  * accumulation, float32 output.
  *   fvy_conv_create      : cin a multiple of 32 (the kernel's K chunk), cout <= 1024.  For dgrad of a forward layer Ci -> Co create
- *                          the handle with cin = Co, cout = Ci.
+ *                          the handle with cin = Co, cout = Ci.  stride = 2 (forward only): a 3 x 3 filter with the reference's
+ *                          ZeroPadding2D(1) + 'valid' geometry over an even-sized height x width INPUT (yolov3_detect.py:204-211),
+ *                          cin a multiple of 64; y is then [batch][height/2][width/2][cout].
  *   fvy_conv_set_weights : w = the torch / Keras-transposed weight tensor [Co][Ci][k][k] float32 in DEVICE memory.  dgrad = 0: this
  *                          handle computes the forward convolution (cin = Ci, cout = Co); dgrad = 1: it computes dX from dY.
  *   fvy_conv_run         : x [batch][height][width][cin] float32 NHWC (DEVICE), y [batch][height][width][cout] float32 NHWC (DEVICE);
  *                          everything is enqueued on `cuda_stream` (the caller's stream), nothing synchronises.
  * Only fvy_conv_set_weights / fvy_conv_run / fvy_destroy / fvy_launch_count apply to such a handle. */
-int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int max_batch, fvy_handle** out);
+int fvy_conv_create(int device, int height, int width, int cin, int cout, int ksize, int stride, int max_batch, fvy_handle** out);
 int fvy_conv_set_weights(fvy_handle* h, const float* w_dev, int dgrad, void* cuda_stream);
 int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, void* cuda_stream);
 /* Training step, row f-1 (third slice): the gradient of a stride-1, zero-padded k x k convolution (k = 1 or 3) with respect to its
@@ -257,9 +259,12 @@ int fvy_conv_run(fvy_handle* h, const float* x_dev, int batch, float* y_dev, voi
  * cout) * 2 bytes that the caller ZEROES ONCE and then only hands to this function for that (height, width, channels) - they hold
  * the bf16 operands in the shared-halo pixel-major form, whose halo pixels and margins stay zero.  dw_work: DEVICE scratch of the size
  * of dw (the tcgen05 kernel accumulates per tap, [k*k][cout][cin]; may be NULL for k = 1).  Enqueued on `cuda_stream`.
- * cout a multiple of 128: wgrad_tc_kernel (tcgen05.mma with MN-major operand descriptors); otherwise conv_wgrad_kernel (mma.sync). */
+ * cout a multiple of 128: wgrad_tc_kernel (tcgen05.mma with MN-major operand descriptors); otherwise conv_wgrad_kernel (mma.sync).
+ * stride = 2 (k = 3, cout a multiple of 128): height / width are dY's map, x is [batch][2 height][2 width][cin] and x_scratch holds four
+ * phase planes: 4 * fvy_conv_wgrad_scratch_rows(batch, ...) * cin * 2 bytes, spaced by that (batch-dependent) row count - hand a stride-2
+ * x_scratch to calls of ONE batch size only (zero it again before using it with another). */
 long long fvy_conv_wgrad_scratch_rows(int batch, int height, int width);
-int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int height, int width, int cin, int cout, int ksize,
+int fvy_conv_wgrad(const float* x_dev, const float* dy_dev, int batch, int height, int width, int cin, int cout, int ksize, int stride,
                    void* x_scratch, void* dy_scratch, float* dw_dev, float* dw_work, void* cuda_stream);
 /* Pre-processing of FaceDetector.evaluate / FaceDetector.test (src/space/face_detection.py:657-690 and :798-835):
  *   image = imread(file) / 255;  image = cv.resize(image, (w_p, h_p), interpolation=cv.INTER_CUBIC);

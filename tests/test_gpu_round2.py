@@ -582,7 +582,7 @@ def test_training_step_with_tc_dgrad():
 
 
 @pytest.mark.parametrize("ci,co,k,hw,b", [(256, 512, 3, 26, 8), (512, 1024, 3, 13, 8), (512, 256, 1, 26, 8), (64, 128, 3, 104, 3),
-                                           (128, 64, 1, 104, 2), (128, 256, 3, 52, 4), (64, 64, 3, 7, 5)])
+                                           (128, 64, 1, 104, 2), (128, 256, 3, 52, 4), (64, 64, 3, 7, 5), (32, 64, 3, 208, 2), (64, 32, 1, 208, 2)])
 def test_conv_wgrad_matches_torch(ci, co, k, hw, b):
     """fvy_conv_wgrad (weight gradient of a stride-1 convolution: pixel-dimension GEMM on warp-level bf16 MMAs, split over the pixel
     range, fp32 atomics) against torch.nn.grad.conv2d_weight in float32 with TF32 off.  Relative L2 <= 1e-4 against torch fed the same
@@ -646,4 +646,33 @@ def test_training_step_with_fvy_conv_kernels(mode):
     assert w_fvy <= 1.3 * w_emu, (w_fvy, w_emu)
     if mode == 3:
         assert w_fvy <= 2e-2, w_fvy
+    conv_tc.clear_cache()
+
+
+@pytest.mark.parametrize("ci,co,hw,b", [(64, 128, 208, 2), (128, 256, 104, 3), (256, 512, 52, 8), (512, 1024, 26, 8)])
+def test_conv_tc_stride2_forward_and_wgrad_match_torch(ci, co, hw, b):
+    """The backbone's stride-2 3 x 3 layers (ZeroPadding2D(1) + 'valid', yolov3_detect.py:204-211 = conv2d(stride 2, padding 1) on an
+    even map) on the single-convolution handle - the inference kernel's 4-phase input form, filled by a phase pack kernel - and their
+    weight gradient on wgrad_tc_kernel with the X boxes taken from the phase planes.  Same tolerances as the stride-1 tests."""
+    import torch
+    import torch.nn.functional as F
+    from face_vijnana_yolov3_b200 import conv_tc
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(ci + co)
+    rl = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm().clamp_min(1e-30))
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    w = (torch.randn(co, ci, 3, 3, device="cuda") * (2.0 / (ci * 9)) ** 0.5).contiguous()
+    x = torch.randn(b, ci, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = conv_tc.conv_forward(x, w, stride=2)
+    assert y.shape == (b, co, hw // 2, hw // 2)
+    assert rl(y, F.conv2d(bf(x), bf(w), None, 2, 1)) <= 1e-4
+    assert rl(y, F.conv2d(x, w, None, 2, 1)) <= 1e-2
+    dy = torch.randn(b, co, hw // 2, hw // 2, device="cuda").contiguous(memory_format=torch.channels_last)
+    dw = conv_tc.conv_wgrad(x, dy, 3, stride=2)
+    assert rl(dw, torch.nn.grad.conv2d_weight(bf(x), w.shape, bf(dy), 2, 1)) <= 1e-4
+    assert rl(dw, torch.nn.grad.conv2d_weight(x, w.shape, dy, 2, 1)) <= 1e-2
+    nb = max(1, b // 3)
+    dw2 = conv_tc.conv_wgrad(x[:nb], dy[:nb], 3, stride=2)
+    assert rl(dw2, torch.nn.grad.conv2d_weight(bf(x[:nb]), w.shape, bf(dy[:nb]), 2, 1)) <= 1e-4
     conv_tc.clear_cache()
