@@ -180,6 +180,15 @@ def _tc_eligible(conv: nn.Conv2d) -> bool:
     return conv_tc.eligible(conv.weight, conv.stride[0], conv.padding[0])
 
 
+def _conv_fn_useful(conv: nn.Conv2d, mode: int) -> bool:
+    """At least one of the pieces `mode` asks for can run on this repo's kernels for this layer (otherwise the plain module is used:
+    one fused cuDNN backward instead of two separate calls)."""
+    from . import conv_tc
+    w, s, p = conv.weight, conv.stride[0], conv.padding[0]
+    return bool(((mode & 1) and conv_tc.eligible(w, s, p)) or ((mode & 2) and conv_tc.wgrad_eligible(w, s, p)) or
+                ((mode & 4) and conv_tc.forward_eligible(w, s, p)))
+
+
 class _ConvFn(torch.autograd.Function):
     """A stride-1 Conv2d on this repo's kernels, bf16 operands with fp32 accumulation (``conv_tc``).  ``mode`` bits: 1 = the gradient
     w.r.t. the INPUT on the tcgen05 implicit-GEMM kernel (``conv_dgrad``), 2 = the gradient w.r.t. the WEIGHT on ``conv_wgrad_kernel``
@@ -252,7 +261,8 @@ class FdNet(nn.Module):
             conv = self.convs[str(c.idx)]
             xin = outs[c.src]
             mode = self.fvy_conv_mode | (1 if self.fvy_dgrad else 0)
-            if mode and self.training and conv.bias is None and xin.is_cuda and xin.dtype == torch.float32 and c.src != -1:
+            if (mode and self.training and conv.bias is None and xin.is_cuda and xin.dtype == torch.float32 and c.src != -1 and
+                    _conv_fn_useful(conv, mode)):
                 y = _ConvFn.apply(xin, conv.weight, conv.padding[0], mode, conv.stride[0])
             else:
                 y = conv(xin)

@@ -637,7 +637,8 @@ def test_training_step_with_fvy_conv_kernels(mode):
         res[name] = (loss, [g.clone() for g in tr.flat_g])
         del tr
     assert np.isfinite(res["fvy"][0]) and all(bool(torch.isfinite(g).all()) for g in res["fvy"][1])
-    assert abs(res["fvy"][0] - res["fp32"][0]) <= (1e-6 if mode == 3 else 2e-3) * max(1.0, abs(res["fp32"][0]))
+    assert abs(res["fvy"][0] - res["fp32"][0]) <= (1e-6 if mode == 3 else 5e-3) * max(1.0, abs(res["fp32"][0]))
+    assert abs(res["fvy"][0] - res["emu"][0]) <= (1e-6 if mode == 3 else 5e-3) * max(1.0, abs(res["emu"][0]))
 
     def worst(a, b):
         return max(float((p.double() - q.double()).norm() / q.double().norm().clamp_min(1e-30)) for p, q in zip(a, b))
