@@ -235,3 +235,42 @@ def test_trained_weights_flow_into_the_inference_engine():
     rel = np.linalg.norm(out - ref) / np.linalg.norm(ref)
     assert rel < 2e-2, rel
     eng.close()
+
+
+@pytest.mark.parametrize("stride,k", [(1, 3), (2, 3), (1, 1)])
+def test_conv_fn_plain_path_equals_module_autograd(stride, k):
+    """train._ConvFn with no kernel bit set (what every piece falls back to: explicit torch.nn.grad calls with the layer's stride and
+    padding) gives the same output and gradients as nn.Conv2d's own autograd - CPU, float64-free, exact up to summation order."""
+    import torch
+    from face_vijnana_yolov3_b200 import train as T
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(8, 12, k, stride, padding=k // 2, bias=False)
+    x1 = torch.randn(2, 8, 10, 10, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    w2 = conv.weight.detach().clone().requires_grad_(True)
+    y1 = conv(x1)
+    y2 = T._ConvFn.apply(x2, w2, k // 2, 0, stride)
+    g = torch.randn_like(y1)
+    y1.backward(g); y2.backward(g)
+    assert torch.allclose(y1, y2, atol=1e-6)
+    assert torch.allclose(x1.grad, x2.grad, atol=1e-5)
+    assert torch.allclose(conv.weight.grad, w2.grad, atol=1e-4)
+
+
+def test_conv_kernel_modes_are_inert_without_a_gpu():
+    """On the CPU nothing is eligible for the tensor-core kernels: FdNet with every mode bit set takes the plain modules (no import of
+    the CUDA library, same result as mode 0), and the eligibility helpers say no."""
+    import torch
+    from face_vijnana_yolov3_b200 import conv_tc, train as T
+    torch.manual_seed(2)
+    m = T.FdNet(6)
+    m.train()
+    x = torch.rand(1, 3, 64, 64)
+    m.fvy_conv_mode = 0
+    y0 = m(x)
+    m.fvy_conv_mode = 7
+    y7 = m(x)
+    assert torch.equal(y0, y7)
+    w = m.convs["3"].weight
+    assert not conv_tc.eligible(w, 1, 1) and not conv_tc.wgrad_eligible(w, 1, 1) and not conv_tc.forward_eligible(w, 1, 1)
+    assert not T._conv_fn_useful(m.convs["3"], 7)
