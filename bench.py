@@ -46,6 +46,21 @@ def _lib_sha16():
         return None
 
 
+def _src_sha16():
+    """Identity of the library's SOURCES (csrc/ + include/fvy.h, sorted by name).  nvcc's output is not byte-reproducible (two builds of
+    the same tree differ), so evidence captured on one build of these sources is matched to another build of them by this hash."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "face_vijnana_yolov3_b200", "csrc")
+    try:
+        for name in sorted(os.listdir(d)):
+            if name.endswith((".cu", ".cuh", ".h", ".inl")):
+                h.update(name.encode()); h.update(open(os.path.join(d, name), "rb").read())
+        h.update(open(os.path.join(ROOT, "include", "fvy.h"), "rb").read())
+    except OSError:
+        return None
+    return h.hexdigest()[:16]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -376,8 +391,9 @@ def run_detect(args, D):
             roofline["traffic_unit"] = "bytes per launch (DRAM read + write, ncu; average over the conv launches of one step)"
             roofline["traffic_per_step"] = tr.get("dram_bytes_per_step")
             roofline["algorithmic_bytes_per_step_unfused"] = tr.get("algorithmic_bytes_per_step_unfused")
-            roofline["traffic_build"] = tr.get("libfvy_sha16")
-            roofline["traffic_is_this_build"] = tr.get("libfvy_sha16") == _lib_sha16() and (tr.get("batch"), tr.get("net")) == (B, S)
+            roofline["traffic_build"] = tr.get("libfvy_src_sha16") or tr.get("libfvy_sha16")
+            same = (tr.get("libfvy_src_sha16") == _src_sha16()) if tr.get("libfvy_src_sha16") else (tr.get("libfvy_sha16") == _lib_sha16())
+            roofline["traffic_is_this_build"] = bool(same) and (tr.get("batch"), tr.get("net")) == (B, S)
         except Exception:
             pass
     # Decode + NMS (HBM bound): algorithmic bytes per SURVEY 8(d) / the post-processing's CUDA-event time inside the timed steps
@@ -458,7 +474,7 @@ def run_detect(args, D):
                            "l2": "no explicit flush: each step streams ~3.4 GB of activations (>> 126 MB L2) between reuses of the input"},
                 "roofline": roofline, "roofline_post": roofline_post, "sustained": sustained, "cpu_baseline": cpu_baseline, "e2e": e2e,
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "kept_boxes_last_step": kept,
-                "libfvy_sha16": _lib_sha16()}
+                "libfvy_sha16": _lib_sha16(), "libfvy_src_sha16": _src_sha16()}
         print(json.dumps(line), file=_OUT, flush=True)
     eng.close()
     return 0

@@ -59,9 +59,16 @@ def traffic(src, dst_csv, dst_json):
     import hashlib, os
     so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "face_vijnana_yolov3_b200", "libfvy.so")
     sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hs = hashlib.sha256()          # the library's sources: nvcc output is not byte-reproducible, bench.py matches builds by this hash
+    for name in sorted(os.listdir(os.path.join(root, "face_vijnana_yolov3_b200", "csrc"))):
+        if name.endswith((".cu", ".cuh", ".h", ".inl")):
+            hs.update(name.encode()); hs.update(open(os.path.join(root, "face_vijnana_yolov3_b200", "csrc", name), "rb").read())
+    hs.update(open(os.path.join(root, "include", "fvy.h"), "rb").read())
+    src_sha = hs.hexdigest()[:16]
     js = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none, one forward ({len(sel)} launches: stem_strip_kernel, "
                     "conv_igemm_kernel and conv_chain_kernel), batch 40 @416, tools/evidence_r02.sh",
-          "libfvy_sha16": sha, "batch": 40, "net": 416,
+          "libfvy_sha16": sha, "libfvy_src_sha16": src_sha, "batch": 40, "net": 416,
           "launches": len(sel), "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr, "dram_bytes_per_step": rd + wr,
           "dram_bytes_per_launch": (rd + wr) / len(sel), "algorithmic_bytes_per_step_unfused": 7640332544, "ncu_time_sum_us": t / 1e3,
           "note": "writes that are still resident in the 126 MB L2 when a kernel ends are counted as reads of the next kernel or not at all; the sum over the forward is the meaningful figure"}
