@@ -117,3 +117,24 @@ def test_facedetector_letterbox_geometry_follows_reference():
             w_p, h_p, pad_t, pad_b, pad_l, pad_r = LB.geometry(w, h, size)
             assert fd._letterbox_geom(w, h) == (w_p, h_p, pad_t, pad_l)
             assert pad_t + h_p + pad_b == size and pad_l + w_p + pad_r == size
+
+
+def test_traffic_profile_is_stamped_with_a_source_hash():
+    """profiles/conv_traffic.json (what bench.py's roofline.traffic reads) names the library sources it was captured on; bench.py
+    recomputes that hash from csrc/ + include/fvy.h.  A mismatch only means the evidence is older than the sources (bench.py then
+    reports traffic_is_this_build = false), so it is a skip, not a failure."""
+    import importlib.util
+    import json
+    import os
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    src = bench._src_sha16()
+    assert isinstance(src, str) and len(src) == 16 and int(src, 16) >= 0
+    assert src == bench._src_sha16()                      # deterministic
+    tr = json.load(open(os.path.join(root, "profiles", "conv_traffic.json")))
+    assert tr["dram_bytes_per_step"] > 0 and tr["launches"] == 44 and (tr["batch"], tr["net"]) == (40, 416)
+    if tr.get("libfvy_src_sha16") != src:
+        pytest.skip("profiles/conv_traffic.json was captured on older sources than this tree")
