@@ -271,7 +271,10 @@ class FaceDetector(object):
         if device is None:
             device = f"cuda:{self.device}" if torch.cuda.is_available() else "cpu"
         seq = T.TrainingSequence(self.raw_data_path, self.hps, self.nn_arch, self.CELL_SIZE)
-        trainer = T.DataParallelTrainer(self.hps, device=device, bb_info_c_size=self.nn_arch['bb_info_c_size'], stream=self._stream)
+        # hps['fvy_conv_mode'] (optional, not a reference key; default 0 = the reference's fp32 arithmetic): bits 1 / 2 / 4 put the
+        # stride-1 convolutions' dgrad / wgrad / forward on this repo's bf16 tensor-core kernels (train._ConvFn)
+        trainer = T.DataParallelTrainer(self.hps, device=device, bb_info_c_size=self.nn_arch['bb_info_c_size'], stream=self._stream,
+                                        fvy_conv_mode=int(self.hps.get('fvy_conv_mode', 0)))
         for epoch in range(self.hps['epochs']):
             for i in range(len(seq)):
                 images, gts = seq[i]
